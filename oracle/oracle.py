@@ -1,0 +1,385 @@
+"""numpy/ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs may import this module.  Nothing under `rs_detection_b200/` does.
+
+* `rsdet_oracle.c`  -> `liborsdet_oracle.so`: C restatement of the reference arithmetic
+  (parity PINNED against `oracle/_ref`, see the header of the C file; merge NMS UNPINNED
+  because Shapely/GEOS is not available).
+* the functions defined in Python below restate the reference's *glue* in numpy, each
+  citing the reference file:line it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(HERE, "rsdet_oracle.c")
+_SO = os.path.join(HERE, "liborsdet_oracle.so")
+
+_f = np.float32
+_pf = C.POINTER(C.c_float)
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int)
+_pu8 = C.POINTER(C.c_uint8)
+
+
+def build(force: bool = False) -> str:
+    """gcc -O2 -ffp-contract=off: IEEE single ops exactly as written (no FMA contraction)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared",
+                               "-fPIC", _SRC, "-o", _SO, "-lm"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orc_rotated_iou_pair.restype = C.c_float
+        L.orc_rotated_iou_pair.argtypes = [_pf, _pf, C.c_int, C.c_int, C.c_int]
+        L.orc_box_iou_rotated.argtypes = [_pf, C.c_int, _pf, C.c_int, C.c_int, C.c_int, _pf]
+        L.orc_nms_rotated.argtypes = [_pf, _pi, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _pu8]
+        L.orc_roi_align_rotated_fwd.argtypes = [_pf, _pf] + [C.c_int] * 4 + [C.c_float] + [C.c_int] * 4 + [_pf]
+        L.orc_roi_align_rotated_bwd.argtypes = [_pf, _pf] + [C.c_int] * 5 + [C.c_float] + [C.c_int] * 4 + [_pf]
+        L.orc_poly_iou.restype = C.c_float
+        L.orc_poly_iou.argtypes = [_pf, _pf]
+        L.orc_poly_iou_matrix.argtypes = [_pf, C.c_int, _pf, C.c_int, C.c_int, _pf]
+        L.orc_poly_nms_sorted.argtypes = [_pf, C.c_int, C.c_float, _pu8]
+        L.orc_convex_quad_intersection_area.restype = C.c_double
+        L.orc_convex_quad_intersection_area.argtypes = [_pd, _pd]
+        L.orc_iou_poly.restype = C.c_double
+        L.orc_iou_poly.argtypes = [_pd, _pd]
+        L.orc_merge_nms.restype = C.c_int
+        L.orc_merge_nms.argtypes = [_pd, _pi, C.c_int, C.c_double, _pi]
+        L.orc_hbb_nms.restype = C.c_int
+        L.orc_hbb_nms.argtypes = [_pd, _pi, C.c_int, C.c_double, _pi]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(_pf)
+
+
+def _c32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------- IoU
+def box_iou_rotated(boxes1, boxes2, version: int = 0, sort_kind: int = 0):
+    """jdet.ops.box_iou_rotated (python/jdet/ops/box_iou_rotated.py:502-509) for version 0,
+    the kernel part of box_iou_rotated_v1 (box_iou_rotated_v1.py:507-513) for version 1.
+    sort_kind 0 = reference CPU hull sort, 1 = reference CUDA hull sort."""
+    b1, b2 = _c32(boxes1).reshape(-1, 5), _c32(boxes2).reshape(-1, 5)
+    out = np.zeros((b1.shape[0], b2.shape[0]), np.float32)
+    if out.size:
+        lib().orc_box_iou_rotated(_fp(b1), b1.shape[0], _fp(b2), b2.shape[0], version, sort_kind, _fp(out))
+    return out
+
+
+def box_iou_rotated_v1(boxes1, boxes2, sort_kind: int = 0, literal_quirk: bool = False):
+    """python/jdet/ops/box_iou_rotated_v1.py:507-524 including the tiny-box zeroing.
+
+    The reference guard reads `boxes[:, [2,3]].min(1)[0] < 0.001`; Jittor's `min(dim)`
+    returns values only, so `[0]` selects box 0's min side and the test degenerates to a
+    scalar applied to ALL rows (literal_quirk=True reproduces that reading).  The default
+    follows the evident intent (per-box test), which is what the CUDA path implements;
+    the two agree whenever no box has a side < 1e-3 (all shipped fixtures)."""
+    b1, b2 = _c32(boxes1).reshape(-1, 5), _c32(boxes2).reshape(-1, 5)
+    ious = box_iou_rotated(b1, b2, 1, sort_kind)
+    if b1.shape[0] and b2.shape[0]:
+        s1 = b1[:, 2:4].min(1) < 0.001
+        s2 = b2[:, 2:4].min(1) < 0.001
+        if literal_quirk:
+            s1 = np.full_like(s1, s1[0])
+            s2 = np.full_like(s2, s2[0])
+        ious[s1, :] = 0.0
+        ious[:, s2] = 0.0
+    return ious
+
+
+# ----------------------------------------------------------------------------- assignment
+def max_iou_assign(overlaps, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.5, match_low_quality=False,
+                   gt_max_assign_all=True, gt_labels=None, assigned_labels_filled=-1):
+    """MaxIoUAssigner.assign_wrt_overlaps, python/jdet/models/boxes/assigner.py:111-170.
+    overlaps (G, n) -> (assigned_gt_inds int32 (n,), max_overlaps (n,), labels or None).
+    argmax ties resolve to the first maximum."""
+    ov = np.asarray(overlaps, np.float32)
+    G, n = ov.shape
+    gt_inds = np.full((n,), -1, np.int32)
+    argmax = ov.argmax(0)
+    maxov = ov.max(0)
+    if isinstance(neg_iou_thr, tuple):
+        gt_inds[(maxov >= np.float32(neg_iou_thr[0])) & (maxov < np.float32(neg_iou_thr[1]))] = 0
+    else:
+        gt_inds[(maxov >= 0) & (maxov < np.float32(neg_iou_thr))] = 0
+    pos = maxov >= np.float32(pos_iou_thr)
+    gt_inds[pos] = argmax[pos] + 1
+    if match_low_quality:
+        gt_argmax = ov.argmax(1)
+        gt_max = ov.max(1)
+        for i in range(G):
+            if gt_max[i] >= np.float32(min_pos_iou):
+                if gt_max_assign_all:
+                    gt_inds[ov[i] == gt_max[i]] = i + 1
+                else:
+                    gt_inds[gt_argmax[i]] = i + 1
+    labels = None
+    if gt_labels is not None:
+        labels = np.full((n,), assigned_labels_filled, np.int32)
+        p = gt_inds > 0
+        labels[p] = np.asarray(gt_labels)[gt_inds[p] - 1]
+    return gt_inds, maxov, labels
+
+
+# ----------------------------------------------------------------------------- NMS
+def _argsort_desc(scores):
+    # descending, first occurrence first on ties (tests use distinct scores anyway)
+    return np.argsort(-np.asarray(scores, np.float64), kind="stable").astype(np.int32)
+
+
+def nms_rotated_keep(dets, order, thr, box_len=5, ge=False, sort_kind=0):
+    """keep mask (bool, ORIGINAL index space): nms_rotated_cpu (ge=True,
+    python/jdet/ops/nms_rotated.py:414-449,495-504) / nms_rotated_cuda (ge=False, :353-411,450-493)."""
+    d = _c32(dets).reshape(-1, box_len)
+    o = np.ascontiguousarray(order, np.int32)
+    keep = np.zeros((d.shape[0],), np.uint8)
+    if d.shape[0]:
+        lib().orc_nms_rotated(_fp(d), o.ctypes.data_as(_pi), d.shape[0], box_len, float(thr), int(ge), sort_kind,
+                              keep.ctypes.data_as(_pu8))
+    return keep.astype(bool)
+
+
+def nms_rotated(dets, scores, thr, ge=False):
+    """python/jdet/ops/nms_rotated.py:527-538 -> kept indices ascending (jt.where(keep)[0])."""
+    dets = _c32(dets)
+    if dets.size == 0:
+        return np.zeros((0,), np.int64)
+    keep = nms_rotated_keep(dets, _argsort_desc(scores), thr, 5, ge)
+    return np.nonzero(keep)[0]
+
+
+def ml_nms_rotated(dets, scores, labels, thr, ge=False):
+    """python/jdet/ops/nms_rotated.py:515-525."""
+    d6 = np.concatenate([_c32(dets), np.asarray(labels).astype(np.float32)[:, None]], 1)
+    keep = nms_rotated_keep(d6, _argsort_desc(scores), thr, 6, ge)
+    return np.nonzero(keep)[0]
+
+
+def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None, ge=False):
+    """python/jdet/ops/nms_rotated.py:540-596, including the `keep.size(0) > max_num`
+    truncation quirk (max_num=-1 drops the last detection, :590-591)."""
+    mb, ms = _c32(multi_bboxes), _c32(multi_scores)
+    num_classes = ms.shape[1] - 1
+    if mb.shape[1] > 5:
+        bboxes = mb.reshape(ms.shape[0], -1, 5)[:, 1:]
+    else:
+        bboxes = np.broadcast_to(mb[:, None], (mb.shape[0], num_classes, 5))
+    scores = ms[:, 1:]
+    valid = scores > np.float32(score_thr)
+    bboxes = bboxes[valid]
+    if score_factors is not None:
+        scores = scores * _c32(score_factors)[:, None]
+    scores = scores[valid]
+    labels = np.nonzero(valid)[1]
+    if bboxes.size == 0:
+        return np.zeros((0, 6), np.float32), np.zeros((0,), np.int32)
+    iou_thr = dict(nms_cfg).get("iou_thr", 0.1)
+    keep = ml_nms_rotated(bboxes, scores, labels, iou_thr, ge)
+    bboxes, scores, labels = bboxes[keep], scores[keep], labels[keep]
+    inds = _argsort_desc(scores)
+    if keep.shape[0] > max_num:
+        inds = inds[:max_num]
+    bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
+    return np.concatenate([bboxes, scores[:, None]], 1), labels.astype(np.int32)
+
+
+def poly_iou_matrix(p, q):
+    """devPolyIoU (python/jdet/ops/nms_poly.py:113-133) on rows of 8 (or 9) floats."""
+    p, q = _c32(p), _c32(q)
+    assert p.shape[1] == q.shape[1] and p.shape[1] in (8, 9)
+    out = np.zeros((p.shape[0], q.shape[0]), np.float32)
+    if out.size:
+        lib().orc_poly_iou_matrix(_fp(p), p.shape[0], _fp(q), q.shape[0], p.shape[1], _fp(out))
+    return out
+
+
+def poly_nms(boxes, thr):
+    """python/jdet/ops/nms_poly.py:187-232 -> order_t[keep] (descending-score order)."""
+    b = _c32(boxes).reshape(-1, 9)
+    order = _argsort_desc(b[:, 8])
+    bs = np.ascontiguousarray(b[order])
+    keep = np.zeros((b.shape[0],), np.uint8)
+    if b.shape[0]:
+        lib().orc_poly_nms_sorted(_fp(bs), b.shape[0], float(thr), keep.ctypes.data_as(_pu8))
+    return order[keep.astype(bool)].astype(np.int64)
+
+
+def multiclass_poly_nms(bboxes, scores, labels, thr):
+    """python/jdet/ops/nms_poly.py:234-245."""
+    b = _c32(bboxes)
+    max_coordinate = b.max() - b.min()
+    offsets = np.asarray(labels).astype(np.float32) * (max_coordinate + np.float32(1))
+    b_nms = b + offsets[:, None]
+    keep = poly_nms(np.concatenate([b_nms, _c32(scores)[:, None]], 1), thr)
+    dets = np.concatenate([b[keep], _c32(scores)[keep][:, None]], 1)
+    return dets, np.asarray(labels)[keep]
+
+
+# ----------------------------------------------------------------------------- transforms
+def obb2poly(obb):
+    """python/jdet/ops/bbox_transforms.py:612-623 (float32)."""
+    o = _c32(obb)
+    cx, cy, w, h, t = [o[..., i] for i in range(5)]
+    Cos, Sin = np.cos(t), np.sin(t)
+    v1x, v1y = w / 2 * Cos, -w / 2 * Sin
+    v2x, v2y = -h / 2 * Sin, -h / 2 * Cos
+    return np.stack([cx + v1x + v2x, cy + v1y + v2y, cx + v1x - v2x, cy + v1y - v2y,
+                     cx - v1x - v2x, cy - v1y - v2y, cx - v1x + v2x, cy - v1y + v2y], -1).astype(np.float32)
+
+
+def obb2hbb(obb):
+    """python/jdet/ops/bbox_transforms.py:626-632."""
+    o = _c32(obb)
+    cx, cy, w, h, t = [o[..., i] for i in range(5)]
+    Cos, Sin = np.cos(t), np.sin(t)
+    xb = np.abs(w / 2 * Cos) + np.abs(h / 2 * Sin)
+    yb = np.abs(w / 2 * Sin) + np.abs(h / 2 * Cos)
+    return np.stack([cx - xb, cy - yb, cx + xb, cy + yb], -1).astype(np.float32)
+
+
+def poly2hbb(polys):
+    """python/jdet/ops/bbox_transforms.py:602-609."""
+    p = _c32(polys)
+    p = p.reshape(*p.shape[:-1], p.shape[-1] // 2, 2)
+    return np.concatenate([p.min(-2), p.max(-2)], -1)
+
+
+# ----------------------------------------------------------------------------- RoIAlignRotated
+def roi_align_rotated_fwd(feat, rois, output_size, spatial_scale, sampling_ratio, version=1):
+    """ROIAlignRotated_v1 (version=1, python/jdet/ops/roi_align_rotated_v1.py:300-326) /
+    ROIAlignRotated (version=0, roi_align_rotated.py:256-283)."""
+    feat, rois = _c32(feat), _c32(rois).reshape(-1, 6)
+    N, Cc, H, W = feat.shape
+    ph, pw = output_size
+    out = np.zeros((rois.shape[0], Cc, ph, pw), np.float32)
+    if out.size:
+        lib().orc_roi_align_rotated_fwd(_fp(feat), _fp(rois), rois.shape[0], Cc, H, W, np.float32(spatial_scale),
+                                        int(sampling_ratio), ph, pw, int(version), _fp(out))
+    return out
+
+
+def roi_align_rotated_bwd(grad, rois, feat_shape, spatial_scale, sampling_ratio, version=1):
+    """_RotatedROIAlign_v1.grad, python/jdet/ops/roi_align_rotated_v1.py:327-351."""
+    grad, rois = _c32(grad), _c32(rois).reshape(-1, 6)
+    N, Cc, H, W = feat_shape
+    gin = np.zeros(feat_shape, np.float32)
+    lib().orc_roi_align_rotated_bwd(_fp(grad), _fp(rois), rois.shape[0], N, Cc, H, W, np.float32(spatial_scale),
+                                    int(sampling_ratio), grad.shape[2], grad.shape[3], int(version), _fp(gin))
+    return gin
+
+
+def map_roi_levels(rois, num_levels, finest_scale=56):
+    """OrientedSingleRoIExtractor.map_roi_levels, python/jdet/models/roi_extractors/oriented_single_level.py:53-71
+    (float32 like the Jittor ops)."""
+    r = _c32(rois)
+    scale = np.sqrt(r[:, 3] * r[:, 4])
+    lv = np.floor(np.log2(scale / np.float32(finest_scale) + np.float32(1e-6)))
+    return np.clip(lv, 0, num_levels - 1).astype(np.int64)
+
+
+def roi_rescale(rois, scale_factor):
+    """oriented_single_level.py:73-89; scale_factor = (h_factor, w_factor)."""
+    if scale_factor is None:
+        return rois
+    hs, ws = (scale_factor, scale_factor) if np.isscalar(scale_factor) else scale_factor
+    r = _c32(rois).copy()
+    r[:, 3] = np.float32(ws) * r[:, 3]
+    r[:, 4] = np.float32(hs) * r[:, 4]
+    return r
+
+
+def oriented_extractor_fwd(feats, rois, featmap_strides, output_size=(7, 7), sampling_ratio=2,
+                           extend_factor=(1.4, 1.2), finest_scale=56, version=1):
+    """OrientedSingleRoIExtractor.execute, oriented_single_level.py:91-114.  Returns (roi_feats, levels)."""
+    rois = _c32(rois).reshape(-1, 6)
+    if len(feats) == 1:
+        return roi_align_rotated_fwd(feats[0], rois, output_size, 1 / featmap_strides[0], sampling_ratio, version), None
+    C_ = feats[0].shape[1]
+    out = np.zeros((rois.shape[0], C_, output_size[0], output_size[1]), np.float32)
+    rois = roi_rescale(rois, extend_factor)
+    lv = map_roi_levels(rois, len(feats), finest_scale)
+    for i in range(len(feats)):
+        inds = lv == i
+        if inds.any():
+            out[inds] += roi_align_rotated_fwd(feats[i], rois[inds], output_size, 1 / featmap_strides[i],
+                                               sampling_ratio, version)
+    return out, lv
+
+
+def oriented_extractor_bwd(grad, feats_shapes, rois, featmap_strides, sampling_ratio=2, extend_factor=(1.4, 1.2),
+                           finest_scale=56, version=1):
+    """Gradient of oriented_extractor_fwd w.r.t. each feature level (what Jittor autograd composes from
+    the masked scatter + _RotatedROIAlign_v1.grad per level)."""
+    rois = roi_rescale(_c32(rois).reshape(-1, 6), extend_factor)
+    lv = map_roi_levels(rois, len(feats_shapes), finest_scale)
+    grad = _c32(grad)
+    outs = []
+    for i, shp in enumerate(feats_shapes):
+        inds = lv == i
+        if inds.any():
+            outs.append(roi_align_rotated_bwd(np.ascontiguousarray(grad[inds]), rois[inds], shp, 1 / featmap_strides[i],
+                                              sampling_ratio, version))
+        else:
+            outs.append(np.zeros(shp, np.float32))
+    return outs
+
+
+# ----------------------------------------------------------------------------- merge stage
+def iou_poly(p, q):
+    """python/jdet/ops/nms_poly.py:247-252 (Shapely stand-in, float64; PARITY UNPINNED)."""
+    p = np.ascontiguousarray(p, np.float64).reshape(8)
+    q = np.ascontiguousarray(q, np.float64).reshape(8)
+    return lib().orc_iou_poly(p.ctypes.data_as(_pd), q.ctypes.data_as(_pd))
+
+
+def py_cpu_nms_poly_fast(dets, thresh):
+    """python/jdet/data/devkits/result_merge.py:66-127 -> list of kept indices in score order."""
+    d = np.ascontiguousarray(dets, np.float64).reshape(-1, 9)
+    n = d.shape[0]
+    if n == 0:
+        return []
+    order = np.ascontiguousarray(d[:, 8].argsort()[::-1], np.int32)
+    keep = np.zeros((n,), np.int32)
+    nk = lib().orc_merge_nms(d.ctypes.data_as(_pd), order.ctypes.data_as(_pi), n, float(thresh), keep.ctypes.data_as(_pi))
+    return keep[:nk].tolist()
+
+
+def hbb_nms(boxes, thresh):
+    """merge.py:14-27 `nms` -> np.array of kept indices in score order."""
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
+    n = b.shape[0]
+    if n == 0:
+        return np.array([], np.int64)
+    order = np.ascontiguousarray(b[:, 4].argsort()[::-1], np.int32)
+    keep = np.zeros((n,), np.int32)
+    nk = lib().orc_hbb_nms(b.ctypes.data_as(_pd), order.ctypes.data_as(_pi), n, float(thresh), keep.ctypes.data_as(_pi))
+    return keep[:nk].astype(np.int64)
+
+
+def poly2origpoly(poly, x, y, rate):
+    """python/jdet/data/devkits/result_merge.py:196-203."""
+    p = np.asarray(poly, np.float64).copy()
+    p[..., 0::2] = (p[..., 0::2] + x) / float(rate)
+    p[..., 1::2] = (p[..., 1::2] + y) / float(rate)
+    return p
