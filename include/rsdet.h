@@ -1,0 +1,162 @@
+/*
+ * rsdet.h -- C ABI of librsdet.so: the B200 (sm_100a) rotated-box hot path for JDet / RS_detection.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: every op is a
+ * C++/CUDA string handed to Jittor's `jt.code`, which passes raw `in<i>_p / out0_p` pointers and
+ * shapes.  Each entry point below replaces one such JIT body (cited `file:line`, relative to the
+ * reference's `python/jdet/`), and is what a `jt.code` one-liner / ctypes stub binds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns all memory
+ *     (inputs, outputs, workspace); the library never allocates, frees or retains pointers;
+ *   - all work is enqueued on `stream` (a `cudaStream_t`, passed as void*; NULL = legacy default
+ *     stream, which is what Jittor uses); no entry point synchronises the host;
+ *   - return value: 0 = RSDET_OK, negative = RSDET_E* argument error, positive = cudaError_t;
+ *   - workspace: `*_workspace_bytes()` returns the exact requirement for the given sizes; pass at
+ *     least that many bytes, 256-byte aligned;
+ *   - box formats: obb = [cx, cy, w, h, theta(rad)], roi = [batch, cx, cy, w, h, theta],
+ *     poly = [x1,y1,...,x4,y4]; fp32 unless stated; row-major, densely packed.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns a CUDA error.
+ */
+#ifndef RSDET_H_
+#define RSDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSDET_OK 0
+#define RSDET_EINVAL (-1)     /* bad size / flag / null pointer */
+#define RSDET_EWORKSPACE (-2) /* workspace too small */
+#define RSDET_ELIMIT (-3)     /* size above a documented limit */
+
+#define RSDET_MAX_LEVELS 8
+
+/* library version (major*10000 + minor*100 + patch) and error text */
+int rsdet_version(void);
+const char* rsdet_error_string(int code);
+
+/* ---------------------------------------------------------------- box transforms
+ * ops/bbox_transforms.py:612-623 (obb2poly), :626-632 (obb2hbb), :602-609 (poly2hbb).  n rows. */
+int rsdet_obb2poly(const float* obb, int n, float* poly, void* stream);
+int rsdet_obb2hbb(const float* obb, int n, float* hbb, void* stream);
+int rsdet_poly2hbb(const float* poly, int n, int num_points, float* hbb, void* stream);
+
+/* ---------------------------------------------------------------- rotated IoU
+ * ops/box_iou_rotated.py:502-509 + kernel :413-461 (version 0);
+ * ops/box_iou_rotated_v1.py:507-524 + kernel :418-466 (version 1: clockwise-positive angle).
+ * boxes1 (n1,5), boxes2 (n2,5) -> ious (n1,n2).  `zero_tiny` != 0 applies the v1 wrapper's
+ * guard (rows/cols whose min(w,h) < 1e-3 are zeroed, box_iou_rotated_v1.py:515-522). */
+size_t rsdet_box_iou_rotated_workspace_bytes(int n1, int n2);
+int rsdet_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n2, int version, int zero_tiny,
+                          float* ious, void* workspace, size_t workspace_bytes, void* stream);
+
+/* models/boxes/assigner.py:111-170 (MaxIoUAssigner.assign_wrt_overlaps) on a (num_gts, n) overlaps
+ * matrix: per-column max/argmax (first maximum wins), neg/pos thresholds, optional low-quality
+ * matching (`match_low_quality`, `gt_max_assign_all`).  neg_lo/neg_hi: negatives are
+ * neg_lo <= max < neg_hi (a scalar neg_iou_thr t is passed as (0, t)).  gt_labels may be NULL
+ * (then assigned_labels may be NULL).  Outputs: assigned_gt_inds int32 (n), max_overlaps fp32 (n),
+ * assigned_labels int32 (n). */
+size_t rsdet_assign_workspace_bytes(int num_gts);
+int rsdet_assign_wrt_overlaps(const float* overlaps, int num_gts, int n, float pos_iou_thr, float neg_lo, float neg_hi,
+                              float min_pos_iou, int match_low_quality, int gt_max_assign_all, const int32_t* gt_labels,
+                              int32_t labels_fill, int32_t* assigned_gt_inds, float* max_overlaps,
+                              int32_t* assigned_labels, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- NMS (rotated / poly / merge)
+ * One engine, four pair predicates.  `kind`: */
+#define RSDET_NMS_ROTATED 0 /* dets (n,5) fp32 obb; suppress IoU >  thr: ops/nms_rotated.py:353-411,450-493 */
+#define RSDET_NMS_ROTATED_GE 1 /* same, suppress IoU >= thr (the CPU body, ops/nms_rotated.py:414-449)        */
+#define RSDET_NMS_POLY 2    /* dets (n,8) fp32 quads, devPolyIoU > thr: ops/nms_poly.py:113-185,187-232       */
+#define RSDET_NMS_MERGE 3   /* dets (n,8) fp64 quads in scene coords; hbb prefilter then polygon IoU > thr:
+                               data/devkits/result_merge.py:66-127 + ops/nms_poly.py:247-252              */
+#define RSDET_NMS_HBB 4     /* dets (n,4) fp64 [x1,y1,x2,y2]; suppress IoU >= thr (merge.py:14-27)         */
+
+/* Greedy NMS in descending-score order, independently inside each label group (labels == NULL: one
+ * group).  Equivalent to the reference's label-gated IoU (ops/nms_rotated.py:281-286) and to one
+ * reference call per class / per scene file.
+ *   dets    : (n, row_floats(kind)) of fp32 or fp64 as the kind says
+ *   scores  : (n) fp32, or fp64 for MERGE/HBB
+ *   labels  : (n) int32 group ids (any values) or NULL
+ *   thr     : scalar threshold, used when thr_per_label == NULL
+ *   thr_per_label : optional device array indexed by label value (0 <= label < num_thr)
+ *                   (result_merge.py:26-27 per-class thresholds)
+ * Outputs (any may be NULL):
+ *   keep_mask     uint8 (n), 1 = kept, ORIGINAL index space  (the `keep` bool Var of nms_rotated_cuda)
+ *   keep_sorted_idx int64 (n): kept ORIGINAL indices in ascending index order  (jt.where(keep)[0])
+ *   keep_score_idx  int64 (n): kept ORIGINAL indices in descending score order (order_t[keep], poly_nms;
+ *                              py_cpu_nms_poly_fast's python list)
+ *   num_keep      int32 (1) device counter
+ * Score ties are broken by lower original index first (the reference leaves this unspecified). */
+size_t rsdet_nms_workspace_bytes(int kind, int n);
+int rsdet_nms(int kind, const void* dets, const void* scores, const int32_t* labels, int n, double thr,
+              const double* thr_per_label, int num_thr, uint8_t* keep_mask, int64_t* keep_sorted_idx,
+              int64_t* keep_score_idx, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ops/nms_rotated.py:540-596 (multiclass_nms_rotated) fused: candidate selection scores[:,1:] >
+ * score_thr (column 0 = background), label-aware rotated NMS (IoU > iou_thr), descending-score
+ * ordering and top-`max_num` truncation (max_num < 0 reproduces the reference's `keep.size(0) >
+ * max_num` slice `inds[:max_num]`, i.e. drops the last detection).
+ *   multi_bboxes : (n,5) or (n,5*(num_classes+1)) as bbox_dim says;  multi_scores : (n,num_classes+1)
+ *   score_factors: (n) or NULL
+ *   out_dets (cap,6) [cx,cy,w,h,theta,score], out_labels int32 (cap), out_count int32 (1);
+ *   cap = n*num_classes rows must be available. */
+size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes);
+int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_dim, const float* multi_scores, int n,
+                                 int num_classes, float score_thr, float iou_thr, int max_num,
+                                 const float* score_factors, float* out_dets, int32_t* out_labels, int32_t* out_count,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- RoIAlignRotated
+ * ops/roi_align_rotated_v1.py:300-351 (kernels :71-147, :193-298) and ops/roi_align_rotated.py:256-307,
+ * plus the level mapping / RoI extension / per-level scatter of
+ * models/roi_extractors/oriented_single_level.py:53-114 fused into ONE launch. */
+typedef struct {
+    int num_levels;                        /* 1..RSDET_MAX_LEVELS; 1 = plain single-map op            */
+    int batch;                             /* N of every feature map                                  */
+    int channels;                          /* C (multiple of 4)                                       */
+    int height[RSDET_MAX_LEVELS];
+    int width[RSDET_MAX_LEVELS];
+    float spatial_scale[RSDET_MAX_LEVELS]; /* 1/stride                                                */
+    int pooled_h, pooled_w;                /* output_size                                             */
+    int sampling_ratio;                    /* >0 fixed grid, <=0 adaptive ceil(roi/pooled)            */
+    int version;                           /* 1 = ROIAlignRotated_v1 (-0.5, clockwise), 0 = v0        */
+    float extend_w, extend_h;              /* RoI extension (1.2, 1.4 in orcnn configs); 1,1 = none   */
+    float finest_scale;                    /* 56; used when num_levels > 1                            */
+    int channels_last;                     /* features (and grads) are NHWC instead of NCHW           */
+} rsdet_roi_align_cfg;
+
+/* feats[l]: (N,C,H_l,W_l) fp32 (NCHW, or NHWC when channels_last); rois (K,6);
+ * out (K,C,ph,pw) fp32 -- always the reference's NCHW-style layout.  levels_out: optional int32 (K). */
+size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward);
+int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, const float* const* feats_host, const float* rois,
+                                    int num_rois, float* out, int32_t* levels_out, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+/* grad_out (K,C,ph,pw) -> grad_feats[l] (N,C,H_l,W_l), fully overwritten (zero-filled + accumulated). */
+int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, const float* grad_out, const float* rois,
+                                     int num_rois, float* const* grad_feats_host, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* NCHW <-> NHWC transposes of one fp32 map (exposed so a caller can keep a channels-last pyramid). */
+int rsdet_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream);
+int rsdet_nhwc_to_nchw(const float* src, int n, int c, int h, int w, float* dst, void* stream);
+
+/* ops/nms_poly.py:247-252 `iou_poly` (Shapely in the reference; convex clipping in float64 here) for n
+ * ALIGNED pairs: polys1 (n,8), polys2 (n,8) fp64 -> ious (n) fp64 = inter / max(a1 + a2 - inter, 0.01). */
+int rsdet_iou_poly_pairs(const double* polys1, const double* polys2, int n, double* ious, void* stream);
+
+/* ---------------------------------------------------------------- merge-stage helper
+ * data/devkits/result_merge.py:196-203 poly2origpoly: scene = (tile_poly + (x,y)) / rate, fp64.
+ * polys (n,8) fp64 in-tile coords; offs (n,3) fp64 [x, y, rate] per row. */
+int rsdet_poly2origpoly(const double* polys, const double* offs, int n, double* out, void* stream);
+
+/* counters for bench.py's `gpu_launches`: number of kernels this library has launched so far */
+unsigned long long rsdet_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSDET_H_ */

@@ -1,0 +1,683 @@
+// nms.cu -- segmented bitmask NMS engine with four pair predicates (compile with -fmad=false).
+//
+// Replaces, for the whole greedy-NMS family of the reference:
+//   nms_rotated_cuda_kernel + host mask scan   python/jdet/ops/nms_rotated.py:353-411, 450-493
+//   nms_rotated_cpu greedy loop                python/jdet/ops/nms_rotated.py:414-449
+//   ml_nms_rotated / nms_rotated glue          python/jdet/ops/nms_rotated.py:515-538
+//   multiclass_nms_rotated                     python/jdet/ops/nms_rotated.py:540-596
+//   poly_nms_kernel + host mask scan           python/jdet/ops/nms_poly.py:135-185, 187-232
+//   py_cpu_nms_poly_fast (+ Shapely iou_poly)  python/jdet/data/devkits/result_merge.py:66-127
+//   merge.py `nms`                             merge.py:14-27
+//
+// Design (B200-first, not a translation):
+//   1. device radix sort (CUB = plumbing) by score, then stably by label -> every label group
+//      ("segment": a class, or a (scene,class) pair in the merge stage) is contiguous and
+//      score-descending.  Label-gated IoU (nms_rotated.py:281-286) == independent NMS per segment.
+//   2. per-box preprocessing once (RBox / MBox), in sorted order.
+//   3. ONE persistent kernel walks the upper-triangular 64x64 tiles of every segment (work list
+//      derived on the device from a tiny segment table; no host round trip): bounding-circle / hbb
+//      reject on all pairs, warp-ballot compaction of the survivors into a shared-memory queue, dense
+//      evaluation of the survivors, 64-bit suppression words.  The reference launches the full n^2
+//      grid (its triangular early-out is commented out, nms_rotated.py:363) over ALL labels; here the
+//      mask is block-sparse per segment (sum n_s*ceil(n_s/64) words instead of n*ceil(n/64)).
+//   4. on-device greedy scan, one CTA per segment: 64 rows are resolved from the diagonal word in
+//      registers, then their suppression words are OR-ed into the shared-memory `remv` vector by all
+//      threads.  The reference does this on the HOST after cudaDeviceSynchronize, reading the mask
+//      through managed memory (nms_rotated.py:475-492).
+//   5. compaction (CUB select) to the three index orders the reference's callers expect.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "common.cuh"
+#include "poly_iou.cuh"
+#include "rotated_iou.cuh"
+
+namespace rsdet {
+
+constexpr int kNmsThreads = 128;
+constexpr int kReduceThreads = 256;
+constexpr size_t kCubTempBytes = 8u << 20;
+
+// ----------------------------------------------------------------------------- predicates
+struct PolyBox { float p[8]; };
+struct HBox { double x1, y1, x2, y2; };
+
+template <int KIND> struct Traits;
+
+template <> struct Traits<RSDET_NMS_ROTATED> {
+    using Box = RBox; using Raw = float; using Thr = float;
+    static constexpr int kRow = 5; static constexpr bool kScratch = true;
+    __device__ static Box prep(const Raw* r) { return prep_rbox(r, 0); }
+    __device__ static bool candidate(const Box& a, const Box& b) { return rbox_may_overlap(a, b); }
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2* q) {
+        return rotated_iou_pair<kNmsThreads>(a, b, q) > thr;
+    }
+};
+template <> struct Traits<RSDET_NMS_ROTATED_GE> : Traits<RSDET_NMS_ROTATED> {
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2* q) {
+        return rotated_iou_pair<kNmsThreads>(a, b, q) >= thr;
+    }
+};
+template <> struct Traits<RSDET_NMS_POLY> {
+    using Box = PolyBox; using Raw = float; using Thr = float;
+    static constexpr int kRow = 8; static constexpr bool kScratch = false;
+    __device__ static Box prep(const Raw* r) { Box b; for (int i = 0; i < 8; i++) b.p[i] = r[i]; return b; }
+    __device__ static bool candidate(const Box&, const Box&) { return true; }  // see poly_iou.cuh
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return poly_iou_f32(a.p, b.p) > thr; }
+};
+template <> struct Traits<RSDET_NMS_MERGE> {
+    using Box = MBox; using Raw = double; using Thr = double;
+    static constexpr int kRow = 8; static constexpr bool kScratch = false;
+    __device__ static Box prep(const Raw* r) {
+        Box b;
+        double x1 = r[0], x2 = r[0], y1 = r[1], y2 = r[1];
+        for (int i = 0; i < 4; i++) {
+            b.p[2 * i] = r[2 * i]; b.p[2 * i + 1] = r[2 * i + 1];
+            x1 = fmin(x1, r[2 * i]); x2 = fmax(x2, r[2 * i]);
+            y1 = fmin(y1, r[2 * i + 1]); y2 = fmax(y2, r[2 * i + 1]);
+        }
+        b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2;
+        return b;
+    }
+    __device__ static bool candidate(const Box& a, const Box& b) { return merge_hbb_overlap(a, b); }
+    // survivors are `iou <= thr` (result_merge.py:118)
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return !(iou_poly_d(a, b) <= thr); }
+};
+template <> struct Traits<RSDET_NMS_HBB> {
+    using Box = HBox; using Raw = double; using Thr = double;
+    static constexpr int kRow = 4; static constexpr bool kScratch = false;
+    __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
+    __device__ static bool candidate(const Box& a, const Box& b) {
+        return fmin(a.x2, b.x2) > fmax(a.x1, b.x1) && fmin(a.y2, b.y2) > fmax(a.y1, b.y1);
+    }
+    // merge.py:21-25: survivors are `iou < thresh`
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
+        double tlx = fmax(a.x1, b.x1), tly = fmax(a.y1, b.y1), brx = fmin(a.x2, b.x2), bry = fmin(a.y2, b.y2);
+        double ov = (brx - tlx) * (bry - tly);
+        double iou = ov / ((a.x2 - a.x1) * (a.y2 - a.y1) + (b.x2 - b.x1) * (b.y2 - b.y1) - ov);
+        return !(iou < thr);
+    }
+};
+
+// ----------------------------------------------------------------------------- segment table
+struct SegTable {
+    int* hdr;              // [0]=nseg [1]=n_eff [2]=tile counter  (+ [4..5] total tiles as long long)
+    int* seg_start;        // nseg+1
+    long long* tile_pref;  // nseg+1
+    long long* mask_off;   // nseg+1 (in 64-bit words)
+    double* seg_thr;       // nseg
+};
+
+__device__ __forceinline__ uint32_t desc_key(float s) {
+    uint32_t u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~u;
+}
+__device__ __forceinline__ unsigned long long desc_key(double s) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(s);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    return ~u;
+}
+
+// rows that are not live (multiclass candidates below score_thr) carry score -inf and sort last
+template <typename ScoreT, typename KeyT>
+__global__ void make_keys_kernel(const ScoreT* __restrict__ scores, int n_max, KeyT* __restrict__ keys, int* __restrict__ idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_max) return;
+    keys[i] = (KeyT)desc_key(scores[i]);
+    idx[i] = i;
+}
+
+__global__ void label_keys_kernel(const int32_t* __restrict__ labels, const int* __restrict__ idx, int n_max,
+                                  const int* __restrict__ n_dev, uint32_t* __restrict__ lkeys) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_max) return;
+    int n = n_dev ? min(*n_dev, n_max) : n_max;
+    lkeys[p] = p < n ? ((uint32_t)labels[idx[p]] ^ 0x80000000u) : 0xffffffffu;
+}
+
+template <int KIND>
+__global__ void prep_sorted_kernel(const typename Traits<KIND>::Raw* __restrict__ dets, const int32_t* __restrict__ labels,
+                                   const int* __restrict__ idx, int n_max, const int* __restrict__ n_dev,
+                                   typename Traits<KIND>::Box* __restrict__ boxes, int32_t* __restrict__ label_sorted) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_max) return;
+    int n = n_dev ? min(*n_dev, n_max) : n_max;
+    if (p >= n) return;
+    int src = idx[p];
+    boxes[p] = Traits<KIND>::prep(dets + (size_t)src * Traits<KIND>::kRow);
+    if (labels) label_sorted[p] = labels[src];
+}
+
+// exclusive scan of one long long per thread across a 1024-thread CTA; returns the CTA total via *total
+__device__ long long block_excl_scan(long long v, long long* s_warp, long long* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        long long s = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        s_warp[lane] = s;
+    }
+    __syncthreads();
+    long long warp_off = w ? s_warp[w - 1] : 0;
+    *total = s_warp[31];
+    __syncthreads();
+    return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(1024)
+segment_table_kernel(const int32_t* __restrict__ label_sorted, int n_max, const int* __restrict__ n_dev, double thr,
+                     const double* __restrict__ thr_per_label, int num_thr, SegTable tb) {
+    __shared__ long long s_warp[32];
+    const int tid = threadIdx.x;
+    const int n = n_dev ? min(*n_dev, n_max) : n_max;
+    const int chunk = ceil_div(n > 0 ? n : 1, 1024);
+    const int p0 = min(n, tid * chunk), p1 = min(n, p0 + chunk);
+    int cnt = 0;
+    for (int p = p0; p < p1; p++)
+        cnt += (p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1]);
+    long long total;
+    int off = (int)block_excl_scan(cnt, s_warp, &total);
+    const int nseg = (int)total;
+    for (int p = p0; p < p1; p++)
+        if ((p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1])) tb.seg_start[off++] = p;
+    if (tid == 0) tb.seg_start[nseg] = n;
+    __syncthreads();
+    long long carry_t = 0, carry_w = 0;
+    for (int base = 0; base < nseg; base += 1024) {
+        int s = base + tid;
+        long long tiles = 0, words = 0;
+        if (s < nseg) {
+            int st = tb.seg_start[s];
+            long long ns = tb.seg_start[s + 1] - st;
+            long long T = (ns + 63) / 64;
+            tiles = T * (T + 1) / 2;
+            words = ns * T;
+            double t = thr;
+            if (thr_per_label && label_sorted) {
+                int l = label_sorted[st];
+                if (l >= 0 && l < num_thr) t = thr_per_label[l];
+            }
+            tb.seg_thr[s] = t;
+        }
+        long long tt, tw;
+        long long et = block_excl_scan(tiles, s_warp, &tt);
+        long long ew = block_excl_scan(words, s_warp, &tw);
+        if (s < nseg) { tb.tile_pref[s] = carry_t + et; tb.mask_off[s] = carry_w + ew; }
+        carry_t += tt; carry_w += tw;
+    }
+    if (tid == 0) {
+        tb.tile_pref[nseg] = carry_t;
+        tb.mask_off[nseg] = carry_w;
+        tb.hdr[0] = nseg; tb.hdr[1] = n; tb.hdr[2] = 0;
+        *(long long*)(tb.hdr + 4) = carry_t;
+    }
+}
+
+// ----------------------------------------------------------------------------- mask tiles
+template <int KIND>
+__global__ void __launch_bounds__(kNmsThreads)
+mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable tb, unsigned long long* __restrict__ mask) {
+    using Tr = Traits<KIND>;
+    using Box = typename Tr::Box;
+    __shared__ Box s_row[64];
+    __shared__ Box s_col[64];
+    __shared__ unsigned short s_queue[64 * 64];
+    __shared__ unsigned long long s_mask[64];
+    __shared__ float2 s_pts[Tr::kScratch ? 24 * kNmsThreads : 1];
+    __shared__ int s_count;
+    __shared__ long long s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nseg = tb.hdr[0];
+    const long long total = *(const long long*)(tb.hdr + 4);
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = (long long)atomicAdd((unsigned int*)&tb.hdr[2], 1u);
+        __syncthreads();
+        const long long t = s_tile;
+        if (t >= total) break;
+        // segment lookup
+        int lo = 0, hi = nseg;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (tb.tile_pref[mid] <= t) lo = mid; else hi = mid;
+        }
+        const int s = lo;
+        const long long u = t - tb.tile_pref[s];
+        const int st = tb.seg_start[s];
+        const int ns = tb.seg_start[s + 1] - st;
+        const int T = (ns + 63) >> 6;
+        // row-major upper triangle: row rb holds T-rb tiles, preceded by rb*T - rb*(rb-1)/2
+        int rb = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)u)) * 0.5);
+        rb = max(0, min(rb, T - 1));
+        while (rb > 0 && (long long)rb * T - (long long)rb * (rb - 1) / 2 > u) rb--;
+        while ((long long)(rb + 1) * T - (long long)(rb + 1) * rb / 2 <= u) rb++;
+        const int cb = rb + (int)(u - ((long long)rb * T - (long long)rb * (rb - 1) / 2));
+        const int nr = min(64, ns - rb * 64), nc = min(64, ns - cb * 64);
+        const typename Tr::Thr thr = (typename Tr::Thr)tb.seg_thr[s];
+
+        if (tid < 64) {
+            if (tid < nr) s_row[tid] = boxes[st + rb * 64 + tid];
+            s_mask[tid] = 0ull;
+        } else if (tid - 64 < nc) {
+            s_col[tid - 64] = boxes[st + cb * 64 + tid - 64];
+        }
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+
+        const bool diag = rb == cb;
+        for (int p = tid; p < 64 * 64; p += kNmsThreads) {
+            int r = p >> 6, c = p & 63;
+            bool cand = r < nr && c < nc && (!diag || c > r);
+            if (cand) cand = Tr::candidate(s_row[r], s_col[c]);
+            unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+            }
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int qi = tid; qi < cnt; qi += kNmsThreads) {
+            int p = s_queue[qi];
+            int r = p >> 6, c = p & 63;
+            if (Tr::suppress(s_row[r], s_col[c], thr, s_pts + (Tr::kScratch ? tid : 0)))
+                atomicOr(&s_mask[r], 1ull << c);
+        }
+        __syncthreads();
+        if (tid < nr) mask[tb.mask_off[s] + (long long)(rb * 64 + tid) * T + cb] = s_mask[tid];
+    }
+}
+
+// ----------------------------------------------------------------------------- greedy scan
+__global__ void __launch_bounds__(kReduceThreads)
+reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted) {
+    extern __shared__ unsigned long long s_remv[];
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_keep;
+    const int tid = threadIdx.x;
+    const int nseg = tb.hdr[0];
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int st = tb.seg_start[s];
+        const int ns = tb.seg_start[s + 1] - st;
+        const int T = (ns + 63) >> 6;
+        const unsigned long long* m = mask + tb.mask_off[s];
+        __syncthreads();
+        for (int j = tid; j < T; j += kReduceThreads) s_remv[j] = 0ull;
+        __syncthreads();
+        for (int b = 0; b < T; b++) {
+            const int nr = min(64, ns - b * 64);
+            if (tid < 64) s_diag[tid] = tid < nr ? m[(long long)(b * 64 + tid) * T + b] : 0ull;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long d[64];
+#pragma unroll
+                for (int i = 0; i < 64; i++) d[i] = s_diag[i];
+                unsigned long long r = s_remv[b], kb = 0ull;
+                if (nr < 64) r |= ~0ull << nr;  // rows past the segment end are "removed"
+#pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    bool alive = !((r >> i) & 1ull);
+                    if (alive) { kb |= 1ull << i; r |= d[i]; }
+                }
+                s_keep = kb;
+            }
+            __syncthreads();
+            const unsigned long long kb = s_keep;
+            if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            if (kb) {
+                for (int j = b + 1 + tid; j < T; j += kReduceThreads) {
+                    unsigned long long acc = 0ull;
+                    const unsigned long long* col = m + (long long)(b * 64) * T + j;
+#pragma unroll 8
+                    for (int i = 0; i < 64; i++)
+                        if ((kb >> i) & 1ull) acc |= col[(long long)i * T];
+                    s_remv[j] |= acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- outputs
+__global__ void scatter_keep_kernel(const uint8_t* __restrict__ keep_sorted, const int* __restrict__ idx, int n_max,
+                                    const int* __restrict__ n_dev, uint8_t* __restrict__ keep_mask) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_max) return;
+    int n = n_dev ? min(*n_dev, n_max) : n_max;
+    keep_mask[idx[p]] = p < n ? keep_sorted[p] : (uint8_t)0;
+}
+
+__global__ void score_order_flags_kernel(const uint8_t* __restrict__ keep_mask, const int* __restrict__ idx_score, int n_max,
+                                         uint8_t* __restrict__ flags, int64_t* __restrict__ vals) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_max) return;
+    int i = idx_score[p];
+    flags[p] = keep_mask[i];
+    vals[p] = (int64_t)i;
+}
+
+// ----------------------------------------------------------------------------- engine
+struct NmsArgs {
+    int kind;
+    const void* dets;
+    const void* scores;
+    const int32_t* labels;
+    int n_max;
+    const int* n_dev;
+    double thr;
+    const double* thr_per_label;
+    int num_thr;
+    uint8_t* keep_mask;
+    int64_t* keep_sorted_idx;
+    int64_t* keep_score_idx;
+    int32_t* num_keep;
+};
+
+static size_t box_bytes(int kind) {
+    switch (kind) {
+        case RSDET_NMS_ROTATED: case RSDET_NMS_ROTATED_GE: return sizeof(RBox);
+        case RSDET_NMS_POLY: return sizeof(PolyBox);
+        case RSDET_NMS_MERGE: return sizeof(MBox);
+        default: return sizeof(HBox);
+    }
+}
+
+size_t nms_ws_bytes(int kind, int n) {
+    size_t N = (size_t)(n > 0 ? n : 1);
+    size_t b = 0;
+    b += 2 * ws_bytes<unsigned long long>(N);  // score keys (double buffer)
+    b += 4 * ws_bytes<int>(N);                 // idx (pass 1, pass 2 double buffers)
+    b += 2 * ws_bytes<uint32_t>(N);            // label keys
+    b += align256(box_bytes(kind) * N);
+    b += ws_bytes<int32_t>(N);                                         // label_sorted
+    b += ws_bytes<int>(64) + ws_bytes<int>(N + 2) + 2 * ws_bytes<long long>(N + 2) + ws_bytes<double>(N + 1);
+    b += ws_bytes<unsigned long long>(N * ((N + 63) / 64));            // mask (worst case: one segment)
+    b += 3 * ws_bytes<uint8_t>(N);                                     // keep_sorted, keep_mask tmp, flags
+    b += 2 * ws_bytes<int64_t>(N);                                     // vals, scratch index output
+    b += ws_bytes<int>(64);                                            // scratch count
+    b += align256(kCubTempBytes + 16 * N);
+    return b;
+}
+
+template <int KIND>
+static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
+                        unsigned long long* mask, cudaStream_t st, bool mask_phase) {
+    using Tr = Traits<KIND>;
+    if (!mask_phase) {
+        prep_sorted_kernel<KIND><<<ceil_div(a.n_max, 256), 256, 0, st>>>((const typename Tr::Raw*)a.dets, a.labels, idx, a.n_max,
+                                                                        a.n_dev, (typename Tr::Box*)boxes, label_sorted);
+    } else {
+        long long T = (a.n_max + 63) / 64;
+        long long tiles = T * (T + 1) / 2;
+        int grid = (int)(tiles < (long long)kNumSMs * 4 ? tiles : (long long)kNumSMs * 4);
+        mask_tiles_kernel<KIND><<<grid, kNmsThreads, 0, st>>>((const typename Tr::Box*)boxes, tb, mask);
+    }
+    count_launch();
+}
+
+static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
+                          unsigned long long* mask, cudaStream_t st, bool mask_phase) {
+    switch (a.kind) {
+        case RSDET_NMS_ROTATED: launch_kind<RSDET_NMS_ROTATED>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+        case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+        case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+        case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+        default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+    }
+}
+
+int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int n = a.n_max;
+    if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB) return RSDET_EINVAL;
+    if (n == 0) {
+        if (a.num_keep) cudaMemsetAsync(a.num_keep, 0, sizeof(int32_t), st);
+        return cuda_status();
+    }
+    if (!a.dets || !a.scores) return RSDET_EINVAL;
+    if (n > (1 << 20)) return RSDET_ELIMIT;  // remv vector must fit shared memory (n/64 words)
+    if (workspace_bytes < nms_ws_bytes(a.kind, n)) return RSDET_EWORKSPACE;
+    const bool f64 = a.kind == RSDET_NMS_MERGE || a.kind == RSDET_NMS_HBB;
+    const size_t N = (size_t)n;
+
+    Workspace ws(workspace, workspace_bytes);
+    unsigned long long* keyA = ws.take<unsigned long long>(N);
+    unsigned long long* keyB = ws.take<unsigned long long>(N);
+    int* idxA = ws.take<int>(N);
+    int* idxB = ws.take<int>(N);
+    int* idxC = ws.take<int>(N);
+    int* idxD = ws.take<int>(N);
+    uint32_t* lkA = ws.take<uint32_t>(N);
+    uint32_t* lkB = ws.take<uint32_t>(N);
+    void* boxes = ws.take<char>(box_bytes(a.kind) * N);
+    int32_t* label_sorted = ws.take<int32_t>(N);
+    SegTable tb;
+    tb.hdr = ws.take<int>(64);
+    tb.seg_start = ws.take<int>(N + 2);
+    tb.tile_pref = ws.take<long long>(N + 2);
+    tb.mask_off = ws.take<long long>(N + 2);
+    tb.seg_thr = ws.take<double>(N + 1);
+    unsigned long long* mask = ws.take<unsigned long long>(N * ((N + 63) / 64));
+    uint8_t* keep_sorted = ws.take<uint8_t>(N);
+    uint8_t* keep_tmp = ws.take<uint8_t>(N);
+    uint8_t* flags = ws.take<uint8_t>(N);
+    int64_t* vals = ws.take<int64_t>(N);
+    int64_t* idx_scratch = ws.take<int64_t>(N);
+    int* cnt_scratch = ws.take<int>(64);
+    size_t cub_bytes = kCubTempBytes + 16 * N;
+    void* cub_tmp = ws.take<char>(cub_bytes);
+    if (!ws.ok()) return RSDET_EWORKSPACE;
+
+    // 1. sort by score (descending, stable -> lower index first on ties)
+    const int* idx_score;
+    if (f64) {
+        make_keys_kernel<double, unsigned long long><<<ceil_div(n, 256), 256, 0, st>>>((const double*)a.scores, n, keyA, idxA);
+        cub::DoubleBuffer<unsigned long long> dk(keyA, keyB);
+        cub::DoubleBuffer<int> dv(idxA, idxB);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 64, st);
+        if (need > cub_bytes) return RSDET_EWORKSPACE;
+        cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 64, st);
+        idx_score = dv.Current();
+    } else {
+        uint32_t* kA = (uint32_t*)keyA;
+        uint32_t* kB = (uint32_t*)keyB;
+        make_keys_kernel<float, uint32_t><<<ceil_div(n, 256), 256, 0, st>>>((const float*)a.scores, n, kA, idxA);
+        cub::DoubleBuffer<uint32_t> dk(kA, kB);
+        cub::DoubleBuffer<int> dv(idxA, idxB);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 32, st);
+        if (need > cub_bytes) return RSDET_EWORKSPACE;
+        cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 32, st);
+        idx_score = dv.Current();
+    }
+    count_launch(4);
+    // 2. stable sort by label -> segments
+    const int* idx_ls = idx_score;
+    if (a.labels) {
+        label_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.labels, idx_score, n, a.n_dev, lkA);
+        cudaMemcpyAsync(idxC, idx_score, sizeof(int) * N, cudaMemcpyDeviceToDevice, st);
+        cub::DoubleBuffer<uint32_t> dk(lkA, lkB);
+        cub::DoubleBuffer<int> dv(idxC, idxD);
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 32, st);
+        if (need > cub_bytes) return RSDET_EWORKSPACE;
+        cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 32, st);
+        idx_ls = dv.Current();
+        count_launch(5);
+    }
+    // 3. per-box preprocessing in sorted order, segment table
+    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, false);
+    segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr, tb);
+    count_launch();
+    // 4. suppression mask over the upper-triangular tiles of every segment
+    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true);
+    // 5. greedy scan
+    {
+        size_t smem = sizeof(unsigned long long) * ((N + 63) / 64);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_done = true;
+        }
+        reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted);
+        count_launch();
+    }
+    // 6. outputs
+    uint8_t* km = a.keep_mask ? a.keep_mask : keep_tmp;
+    scatter_keep_kernel<<<ceil_div(n, 256), 256, 0, st>>>(keep_sorted, idx_ls, n, a.n_dev, km);
+    count_launch();
+    bool counted = false;
+    if (a.keep_sorted_idx || (a.num_keep && !a.keep_score_idx)) {
+        int64_t* out = a.keep_sorted_idx ? a.keep_sorted_idx : idx_scratch;
+        int* cnt = a.num_keep ? a.num_keep : cnt_scratch;
+        thrust::counting_iterator<int64_t> it(0);
+        size_t need = 0;
+        cub::DeviceSelect::Flagged(nullptr, need, it, km, out, cnt, n, st);
+        if (need > cub_bytes) return RSDET_EWORKSPACE;
+        cub::DeviceSelect::Flagged(cub_tmp, need, it, km, out, cnt, n, st);
+        counted = true;
+        count_launch(2);
+    }
+    if (a.keep_score_idx) {
+        score_order_flags_kernel<<<ceil_div(n, 256), 256, 0, st>>>(km, idx_score, n, flags, vals);
+        int* cnt = (a.num_keep && !counted) ? a.num_keep : cnt_scratch;
+        size_t need = 0;
+        cub::DeviceSelect::Flagged(nullptr, need, vals, flags, a.keep_score_idx, cnt, n, st);
+        if (need > cub_bytes) return RSDET_EWORKSPACE;
+        cub::DeviceSelect::Flagged(cub_tmp, need, vals, flags, a.keep_score_idx, cnt, n, st);
+        count_launch(3);
+    }
+    return cuda_status();
+}
+
+// ----------------------------------------------------------------------------- multiclass_nms_rotated
+// nms_rotated.py:562-575: expand (n, C) candidates in row-major order; invalid ones get score -inf and
+// label INT_MAX so that both sorts push them behind the *n_valid live rows.
+__global__ void mc_expand_kernel(const float* __restrict__ bboxes, int bbox_dim, const float* __restrict__ scores, int n, int C,
+                                 float score_thr, const float* __restrict__ factors, float* __restrict__ cbox,
+                                 float* __restrict__ cscore, int32_t* __restrict__ clabel, int* __restrict__ n_valid) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = e < n * C;
+    int i = in ? e / C : 0, c = in ? e % C : 0;
+    float s = in ? scores[(size_t)i * (C + 1) + c + 1] : 0.f;
+    bool valid = in && s > score_thr;
+    if (in) {
+        const float* b = bbox_dim > 5 ? bboxes + (size_t)i * bbox_dim + (c + 1) * 5 : bboxes + (size_t)i * 5;
+#pragma unroll
+        for (int k = 0; k < 5; k++) cbox[(size_t)e * 5 + k] = b[k];
+        if (factors) s = s * factors[i];
+        cscore[e] = valid ? s : -INFINITY;
+        clabel[e] = valid ? c : 0x7fffffff;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, __popc(m));
+}
+
+// nms_rotated.py:577-596: kept candidates arrive in descending-score order; apply the max_num slice.
+__global__ void mc_output_kernel(const int64_t* __restrict__ keep_score_idx, const int32_t* __restrict__ num_keep, int max_num,
+                                 const float* __restrict__ cbox, const float* __restrict__ cscore,
+                                 const int32_t* __restrict__ clabel, float* __restrict__ out_dets,
+                                 int32_t* __restrict__ out_labels, int32_t* __restrict__ out_count, int cap) {
+    int nk = *num_keep;
+    int cnt = nk;
+    if (nk > max_num) cnt = max_num >= 0 ? max_num : max(nk + max_num, 0);  // python inds[:max_num]
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *out_count = cnt;
+    if (r >= cnt || r >= cap) return;
+    int e = (int)keep_score_idx[r];
+#pragma unroll
+    for (int k = 0; k < 5; k++) out_dets[(size_t)r * 6 + k] = cbox[(size_t)e * 5 + k];
+    out_dets[(size_t)r * 6 + 5] = cscore[e];
+    out_labels[r] = clabel[e];
+}
+
+// iou_poly (nms_poly.py:247-252) for n aligned pairs of float64 quads
+__global__ void iou_poly_pairs_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    MBox A = Traits<RSDET_NMS_MERGE>::prep(a + (size_t)i * 8);
+    MBox B = Traits<RSDET_NMS_MERGE>::prep(b + (size_t)i * 8);
+    out[i] = iou_poly_d(A, B);
+}
+
+}  // namespace rsdet
+
+using namespace rsdet;
+
+extern "C" int rsdet_iou_poly_pairs(const double* polys1, const double* polys2, int n, double* ious, void* stream) {
+    if (n < 0) return RSDET_EINVAL;
+    if (n == 0) return RSDET_OK;
+    if (!polys1 || !polys2 || !ious) return RSDET_EINVAL;
+    iou_poly_pairs_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(polys1, polys2, n, ious);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" size_t rsdet_nms_workspace_bytes(int kind, int n) { return nms_ws_bytes(kind, n); }
+
+extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const int32_t* labels, int n, double thr,
+                         const double* thr_per_label, int num_thr, uint8_t* keep_mask, int64_t* keep_sorted_idx,
+                         int64_t* keep_score_idx, int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
+    NmsArgs a{kind, dets, scores, labels, n, nullptr, thr, thr_per_label, num_thr, keep_mask, keep_sorted_idx, keep_score_idx, num_keep};
+    return nms_run(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes) {
+    size_t cap = (size_t)(n > 0 ? n : 1) * (size_t)(num_classes > 0 ? num_classes : 1);
+    return ws_bytes<float>(cap * 5) + ws_bytes<float>(cap) + ws_bytes<int32_t>(cap) + ws_bytes<int>(64) +
+           ws_bytes<int64_t>(cap) + ws_bytes<int32_t>(64) + nms_ws_bytes(RSDET_NMS_ROTATED, (int)cap);
+}
+
+extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_dim, const float* multi_scores, int n,
+                                            int num_classes, float score_thr, float iou_thr, int max_num,
+                                            const float* score_factors, float* out_dets, int32_t* out_labels,
+                                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 0 || num_classes <= 0 || !out_count) return RSDET_EINVAL;
+    if (bbox_dim != 5 && bbox_dim != 5 * (num_classes + 1)) return RSDET_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        cudaMemsetAsync(out_count, 0, sizeof(int32_t), st);
+        return cuda_status();
+    }
+    if (!multi_bboxes || !multi_scores || !out_dets || !out_labels) return RSDET_EINVAL;
+    long long capll = (long long)n * num_classes;
+    if (capll > (1 << 20)) return RSDET_ELIMIT;
+    int cap = (int)capll;
+    if (workspace_bytes < rsdet_multiclass_nms_rotated_workspace_bytes(n, num_classes)) return RSDET_EWORKSPACE;
+    Workspace ws(workspace, workspace_bytes);
+    float* cbox = ws.take<float>((size_t)cap * 5);
+    float* cscore = ws.take<float>(cap);
+    int32_t* clabel = ws.take<int32_t>(cap);
+    int* n_valid = ws.take<int>(64);
+    int64_t* kidx = ws.take<int64_t>(cap);
+    int32_t* nkeep = ws.take<int32_t>(64);
+    void* sub = ws.base + ws.used;
+    size_t sub_bytes = workspace_bytes - ws.used;
+    cudaMemsetAsync(n_valid, 0, sizeof(int), st);
+    mc_expand_kernel<<<ceil_div(cap, 256), 256, 0, st>>>(multi_bboxes, bbox_dim, multi_scores, n, num_classes, score_thr,
+                                                        score_factors, cbox, cscore, clabel, n_valid);
+    count_launch();
+    NmsArgs a{RSDET_NMS_ROTATED, cbox, cscore, clabel, cap, n_valid, (double)iou_thr, nullptr, 0, nullptr, nullptr, kidx, nkeep};
+    int rc = nms_run(a, sub, sub_bytes, st);
+    if (rc != RSDET_OK) return rc;
+    mc_output_kernel<<<ceil_div(cap, 256), 256, 0, st>>>(kidx, nkeep, max_num, cbox, cscore, clabel, out_dets, out_labels,
+                                                        out_count, cap);
+    count_launch();
+    return cuda_status();
+}

@@ -1,0 +1,589 @@
+// roi_align.cu -- multi-level RoIAlignRotated forward / backward for sm_100a.
+//
+// Replaces ROIAlignRotatedForward / ROIAlignBackward (python/jdet/ops/roi_align_rotated_v1.py:71-147,
+// 193-298; v0: roi_align_rotated.py:60-126, 164-254) AND the Python level loop around them
+// (python/jdet/models/roi_extractors/oriented_single_level.py:91-114): RoI extension, level mapping,
+// four per-level launches, boolean gathers and masked scatter-adds become ONE launch.
+//
+// The op is a gather (fwd) / scatter (bwd): ~0.6 FLOP per byte, HBM/L2 bound.  Plan:
+//   * features are read channels-last (NHWC): one bilinear tap = one contiguous C*4-byte row, read as
+//     coalesced 16-byte vectors (a warp covers 512 contiguous bytes).  NCHW inputs (Jittor's layout)
+//     are transposed once per call by a tiled transpose into the workspace; callers that keep a
+//     channels-last pyramid skip it (cfg.channels_last).
+//   * one CTA per RoI.  Phase A: the RoI's sampling grid (pooled_h*pooled_w*grid^2 samples -> 4 tap
+//     offsets + 4 weights each) is computed ONCE by the first threads and staged in shared memory; the
+//     reference recomputes it, sin/cos included, in every one of its K*C*49 threads.
+//   * Phase B: thread = (channel quad, bin group); 16 independent 16-byte loads in flight per bin.
+//   * the (C,7,7) output block of a RoI is contiguous in the reference layout; results are staged in
+//     shared memory in a [k][bin][quad+1] layout (conflict-free both ways) and written with streaming
+//     16-byte stores, so the 50 KB block leaves the SM fully coalesced and does not evict features
+//     from L2.
+//   * backward: same tap table; gradients are accumulated channels-last with 16-byte vector
+//     reductions (red.global.add.v4.f32: one L2 atomic op per 4 channels instead of the reference's 4
+//     scalar atomicAdd), then transposed back to NCHW, which also produces the dense zero-filled
+//     output the reference gets from cudaMemsetAsync.
+//
+// Sample coordinates are computed with explicitly un-contracted IEEE operations in the reference's
+// order: the validity test `y < -1 || y > H` is discontinuous, so coordinates must not drift.
+#include "common.cuh"
+
+namespace rsdet {
+
+constexpr int kRoiThreads = 256;
+constexpr int kMaxSamples = 1024;  // fast path: pooled_h*pooled_w*grid_h*grid_w
+
+struct LevelSet {
+    const float* feat[RSDET_MAX_LEVELS];  // channels-last maps
+    float* grad[RSDET_MAX_LEVELS];
+    int H[RSDET_MAX_LEVELS], W[RSDET_MAX_LEVELS];
+    float scale[RSDET_MAX_LEVELS];
+    int num_levels, batch, C;
+    int PH, PW, sampling_ratio, version;
+    float extend_w, extend_h, finest_scale;
+};
+
+// ---------------------------------------------------------------------------------- transposes
+// (N, C, HW) <-> (N, HW, C), 32x32 tiles through padded shared memory.
+struct TransposeJob {
+    const float* src[RSDET_MAX_LEVELS];
+    float* dst[RSDET_MAX_LEVELS];
+    int HW[RSDET_MAX_LEVELS];
+    int tile_begin[RSDET_MAX_LEVELS + 1];  // prefix of tiles over levels
+    int num_levels, N, C;
+};
+
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
+    __shared__ float tile[32][33];
+    int t = blockIdx.x;
+    int l = 0;
+    while (l + 1 < job.num_levels && t >= job.tile_begin[l + 1]) l++;
+    t -= job.tile_begin[l];
+    const int HW = job.HW[l], C = job.C;
+    const int tiles_hw = ceil_div(HW, 32), tiles_c = ceil_div(C, 32);
+    const int n = t / (tiles_hw * tiles_c);
+    const int r = t % (tiles_hw * tiles_c);
+    const int hw0 = (r % tiles_hw) * 32, c0 = (r / tiles_hw) * 32;
+    const float* src = job.src[l] + (size_t)n * C * HW;
+    float* dst = job.dst[l] + (size_t)n * C * HW;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (TO_NHWC) {  // src [C][HW] -> dst [HW][C]
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int c = c0 + ty + 8 * k, hw = hw0 + tx;
+            if (c < C && hw < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)c * HW + hw);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int hw = hw0 + ty + 8 * k, c = c0 + tx;
+            if (c < C && hw < HW) dst[(size_t)hw * C + c] = tile[tx][ty + 8 * k];
+        }
+    } else {  // src [HW][C] -> dst [C][HW]
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int hw = hw0 + ty + 8 * k, c = c0 + tx;
+            if (c < C && hw < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)hw * C + c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int c = c0 + ty + 8 * k, hw = hw0 + tx;
+            if (c < C && hw < HW) dst[(size_t)c * HW + hw] = tile[tx][ty + 8 * k];
+        }
+    }
+}
+
+static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
+                            int C, cudaStream_t st) {
+    TransposeJob job;
+    job.num_levels = L; job.N = N; job.C = C;
+    int total = 0;
+    for (int l = 0; l < L; l++) {
+        job.src[l] = src[l]; job.dst[l] = dst[l]; job.HW[l] = H[l] * W[l];
+        job.tile_begin[l] = total;
+        total += N * ceil_div(job.HW[l], 32) * ceil_div(C, 32);
+    }
+    job.tile_begin[L] = total;
+    if (total == 0) return RSDET_OK;
+    if (to_nhwc) transpose_kernel<true><<<total, 256, 0, st>>>(job);
+    else transpose_kernel<false><<<total, 256, 0, st>>>(job);
+    count_launch();
+    return cuda_status();
+}
+
+// ---------------------------------------------------------------------------------- geometry
+struct RoiGeom {
+    int batch, level, gh, gw;
+    float cw, ch, bin_h, bin_w, start_h, start_w, cosv, sinv;
+};
+
+// oriented_single_level.py:73-89 (roi_rescale), :53-71 (map_roi_levels); roi_align_rotated_v1.py:85-120
+__device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ r, const LevelSet& L) {
+    RoiGeom g;
+    g.batch = (int)r[0];
+    float w = __fmul_rn(L.extend_w, r[3]);
+    float h = __fmul_rn(L.extend_h, r[4]);
+    int lvl = 0;
+    if (L.num_levels > 1) {
+        float s = sqrtf(__fmul_rn(w, h));
+        float t = floorf(log2f(__fadd_rn(__fdiv_rn(s, L.finest_scale), 1e-6f)));
+        t = fminf(fmaxf(t, 0.f), (float)(L.num_levels - 1));
+        lvl = (int)t;
+    }
+    g.level = lvl;
+    const float sc = L.scale[lvl];
+    if (L.version == 1) {
+        g.cw = __fsub_rn(__fmul_rn(r[1], sc), 0.5f);
+        g.ch = __fsub_rn(__fmul_rn(r[2], sc), 0.5f);
+    } else {
+        g.cw = __fmul_rn(r[1], sc);
+        g.ch = __fmul_rn(r[2], sc);
+    }
+    float rw = fmaxf(__fmul_rn(w, sc), 1.f);
+    float rh = fmaxf(__fmul_rn(h, sc), 1.f);
+    g.bin_h = __fdiv_rn(rh, (float)L.PH);
+    g.bin_w = __fdiv_rn(rw, (float)L.PW);
+    g.gh = L.sampling_ratio > 0 ? L.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)L.PH));
+    g.gw = L.sampling_ratio > 0 ? L.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)L.PW));
+    g.start_h = -rh * 0.5f;
+    g.start_w = -rw * 0.5f;
+    g.cosv = cosf(r[5]);
+    g.sinv = sinf(r[5]);
+    return g;
+}
+
+__device__ __forceinline__ void sample_xy(const RoiGeom& g, int version, int ph, int pw, int iy, int ix, float& x, float& y) {
+    float yy = __fadd_rn(__fadd_rn(g.start_h, __fmul_rn((float)ph, g.bin_h)),
+                         __fdiv_rn(__fmul_rn((float)iy + .5f, g.bin_h), (float)g.gh));
+    float xx = __fadd_rn(__fadd_rn(g.start_w, __fmul_rn((float)pw, g.bin_w)),
+                         __fdiv_rn(__fmul_rn((float)ix + .5f, g.bin_w), (float)g.gw));
+    if (version == 1) {  // clockwise-positive, roi_align_rotated_v1.py:133-134
+        x = __fadd_rn(__fadd_rn(__fmul_rn(xx, g.cosv), __fmul_rn(yy, g.sinv)), g.cw);
+        y = __fadd_rn(__fsub_rn(__fmul_rn(yy, g.cosv), __fmul_rn(xx, g.sinv)), g.ch);
+    } else {  // roi_align_rotated.py:116-117
+        x = __fadd_rn(__fsub_rn(__fmul_rn(xx, g.cosv), __fmul_rn(yy, g.sinv)), g.cw);
+        y = __fadd_rn(__fadd_rn(__fmul_rn(xx, g.sinv), __fmul_rn(yy, g.cosv)), g.ch);
+    }
+}
+
+struct Taps {
+    int o[4];    // pixel offsets (y*W+x) of lt, rt, lb, rb; all 0 when the sample is out of range
+    float w[4];  // bilinear weights; all 0 when out of range
+};
+
+// bilinear_interpolate(_gradient): roi_align_rotated_v1.py:23-68, 149-190
+__device__ __forceinline__ Taps make_taps(int H, int W, float y, float x) {
+    Taps t;
+    if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) {
+        t.o[0] = t.o[1] = t.o[2] = t.o[3] = 0;
+        t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+        return t;
+    }
+    if (y < 0) y = 0;
+    if (x < 0) x = 0;
+    int y_low = (int)y, x_low = (int)x, y_high, x_high;
+    if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else y_high = y_low + 1;
+    if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else x_high = x_low + 1;
+    float ly = __fsub_rn(y, (float)y_low), lx = __fsub_rn(x, (float)x_low);
+    float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+    t.o[0] = y_low * W + x_low;  t.o[1] = y_low * W + x_high;
+    t.o[2] = y_high * W + x_low; t.o[3] = y_high * W + x_high;
+    t.w[0] = __fmul_rn(hy, hx); t.w[1] = __fmul_rn(hy, lx); t.w[2] = __fmul_rn(ly, hx); t.w[3] = __fmul_rn(ly, lx);
+    return t;
+}
+
+__device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_cs_v4(float* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldg_cs_v4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// shared-memory layout of the fast path
+//   taps   : nsamp * Taps (32 B each)
+//   stage  : [4][nbins][Q+1] floats   (k = channel within quad, Q = quads per CTA chunk)
+__host__ __device__ inline int quads_per_chunk(int C) { return (C / 4) < 64 ? (C / 4) : 64; }
+
+// ---------------------------------------------------------------------------------- forward (fast)
+__global__ void __launch_bounds__(kRoiThreads)
+roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int roi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nbins = L.PH * L.PW;
+    const int spb = L.sampling_ratio * L.sampling_ratio;  // samples per bin (fast path: fixed grid)
+    const int nsamp = nbins * spb;
+    const int Q = quads_per_chunk(L.C);
+    const int chunk0 = blockIdx.y * Q * 4;                 // first channel of this chunk
+    const int Qc = min(Q, (L.C - chunk0) / 4);             // quads in this chunk
+    Taps* s_taps = reinterpret_cast<Taps*>(smem_raw);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(Taps) * nsamp);
+    __shared__ RoiGeom s_g;
+
+    if (tid == 0) {
+        s_g = roi_geometry(rois + (size_t)roi * 6, L);
+        if (levels_out && blockIdx.y == 0) levels_out[roi] = s_g.level;
+    }
+    __syncthreads();
+    const RoiGeom g = s_g;
+    const int H = L.H[g.level], W = L.W[g.level];
+    for (int s = tid; s < nsamp; s += kRoiThreads) {
+        int b = s / spb, q = s % spb;
+        int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
+        float x, y;
+        sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+        s_taps[s] = make_taps(H, W, y, x);
+    }
+    __syncthreads();
+
+    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * L.C + chunk0;
+    const int C = L.C;
+    const int groups = kRoiThreads / Qc;
+    const int cq = tid % Qc, grp = tid / Qc;
+    const float count = (float)max(spb, 1);
+    const int SQ = Q + 1;
+    if (grp < groups) {
+        for (int b = grp; b < nbins; b += groups) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < spb; q++) {
+                const Taps t = s_taps[b * spb + q];
+                float4 v0 = ldg_nc_v4(feat + (size_t)t.o[0] * C + cq * 4);
+                float4 v1 = ldg_nc_v4(feat + (size_t)t.o[1] * C + cq * 4);
+                float4 v2 = ldg_nc_v4(feat + (size_t)t.o[2] * C + cq * 4);
+                float4 v3 = ldg_nc_v4(feat + (size_t)t.o[3] * C + cq * 4);
+                // val = w1*lt + w2*rt + w3*lb + w4*rb ; output_val += val   (:63-65, :138-140)
+                acc.x += t.w[0] * v0.x + t.w[1] * v1.x + t.w[2] * v2.x + t.w[3] * v3.x;
+                acc.y += t.w[0] * v0.y + t.w[1] * v1.y + t.w[2] * v2.y + t.w[3] * v3.y;
+                acc.z += t.w[0] * v0.z + t.w[1] * v1.z + t.w[2] * v2.z + t.w[3] * v3.z;
+                acc.w += t.w[0] * v0.w + t.w[1] * v1.w + t.w[2] * v2.w + t.w[3] * v3.w;
+            }
+            s_stage[(0 * nbins + b) * SQ + cq] = acc.x / count;
+            s_stage[(1 * nbins + b) * SQ + cq] = acc.y / count;
+            s_stage[(2 * nbins + b) * SQ + cq] = acc.z / count;
+            s_stage[(3 * nbins + b) * SQ + cq] = acc.w / count;
+        }
+    }
+    __syncthreads();
+    // coalesced write-out of this chunk's (Qc*4, nbins) block; element e = c_local*nbins + b
+    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;
+    const int total = Qc * 4 * nbins;
+    if (((((size_t)roi * C + chunk0) * nbins) & 3) == 0 && (total & 3) == 0) {
+        for (int e4 = tid; e4 < total / 4; e4 += kRoiThreads) {
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int e = e4 * 4 + k;
+                int c = e / nbins, b = e - c * nbins;
+                v[k] = s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)];
+            }
+            stg_cs_v4(dst + (size_t)e4 * 4, make_float4(v[0], v[1], v[2], v[3]));
+        }
+    } else {
+        for (int e = tid; e < total; e += kRoiThreads) {
+            int c = e / nbins, b = e - c * nbins;
+            dst[e] = s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- backward (fast)
+__global__ void __launch_bounds__(kRoiThreads)
+roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, int K, const float* __restrict__ grad_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int roi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nbins = L.PH * L.PW;
+    const int spb = L.sampling_ratio * L.sampling_ratio;
+    const int nsamp = nbins * spb;
+    const int Q = quads_per_chunk(L.C);
+    const int chunk0 = blockIdx.y * Q * 4;
+    const int Qc = min(Q, (L.C - chunk0) / 4);
+    Taps* s_taps = reinterpret_cast<Taps*>(smem_raw);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(Taps) * nsamp);
+    __shared__ RoiGeom s_g;
+
+    if (tid == 0) s_g = roi_geometry(rois + (size_t)roi * 6, L);
+    // stage this chunk's gradient block: element e = c_local*nbins + b  ->  [k][b][quad]
+    const int C = L.C;
+    const int SQ = Q + 1;
+    const float* __restrict__ src = grad_out + ((size_t)roi * C + chunk0) * nbins;
+    const int total = Qc * 4 * nbins;
+    for (int e = tid; e < total; e += kRoiThreads) {
+        int c = e / nbins, b = e - c * nbins;
+        s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)] = __ldg(src + e);
+    }
+    __syncthreads();
+    const RoiGeom g = s_g;
+    const int H = L.H[g.level], W = L.W[g.level];
+    for (int s = tid; s < nsamp; s += kRoiThreads) {
+        int b = s / spb, q = s % spb;
+        int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
+        float x, y;
+        sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+        s_taps[s] = make_taps(H, W, y, x);
+    }
+    __syncthreads();
+
+    float* __restrict__ gfeat = L.grad[g.level] + (size_t)g.batch * H * W * C + chunk0;
+    const int groups = kRoiThreads / Qc;
+    const int cq = tid % Qc, grp = tid / Qc;
+    const float count = (float)spb;  // no max(.,1) in backward (:246)
+    if (grp < groups) {
+        for (int b = grp; b < nbins; b += groups) {
+            float4 top;
+            top.x = s_stage[(0 * nbins + b) * SQ + cq];
+            top.y = s_stage[(1 * nbins + b) * SQ + cq];
+            top.z = s_stage[(2 * nbins + b) * SQ + cq];
+            top.w = s_stage[(3 * nbins + b) * SQ + cq];
+            for (int q = 0; q < spb; q++) {
+                const Taps t = s_taps[b * spb + q];
+                // out-of-range samples have all-zero weights: skipping them is the reference's `if` (:285)
+                if (t.w[0] == 0.f && t.w[1] == 0.f && t.w[2] == 0.f && t.w[3] == 0.f) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float wk = t.w[k];
+                    float4 gv = make_float4(top.x * wk / count, top.y * wk / count, top.z * wk / count, top.w * wk / count);
+                    red_add_v4(gfeat + (size_t)t.o[k] * C + cq * 4, gv);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- generic path
+// Any pooled size / adaptive sampling grid / channel count; NCHW or NHWC directly.  One thread per
+// output element like the reference, but with the level mapping fused.  Used only when the fast path's
+// preconditions (C % 4 == 0, fixed sampling grid, <= kMaxSamples samples) do not hold.
+struct GenericMaps {
+    const float* feat[RSDET_MAX_LEVELS];
+    float* grad[RSDET_MAX_LEVELS];
+    int channels_last;
+};
+
+__device__ __forceinline__ size_t feat_index(int cl, int n, int c, int pix, int C, int HW) {
+    return cl ? ((size_t)n * HW + pix) * C + c : ((size_t)n * C + c) * HW + pix;
+}
+
+template <bool BACKWARD>
+__global__ void roi_align_generic_kernel(LevelSet L, GenericMaps M, const float* __restrict__ rois, int K,
+                                         float* __restrict__ out_or_gradout, int32_t* __restrict__ levels_out) {
+    const int nbins = L.PH * L.PW;
+    const long long total = (long long)K * L.C * nbins;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int pw = (int)(idx % L.PW), ph = (int)((idx / L.PW) % L.PH);
+        int c = (int)((idx / nbins) % L.C), n = (int)(idx / nbins / L.C);
+        RoiGeom g = roi_geometry(rois + (size_t)n * 6, L);
+        if (!BACKWARD && levels_out && c == 0 && ph == 0 && pw == 0) levels_out[n] = g.level;
+        const int H = L.H[g.level], W = L.W[g.level];
+        if (!BACKWARD) {
+            const float count = (float)max(g.gh * g.gw, 1);
+            float acc = 0.f;
+            for (int iy = 0; iy < g.gh; iy++)
+                for (int ix = 0; ix < g.gw; ix++) {
+                    float x, y;
+                    sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+                    Taps t = make_taps(H, W, y, x);
+                    const float* f = M.feat[g.level];
+                    float v = t.w[0] * f[feat_index(M.channels_last, g.batch, c, t.o[0], L.C, H * W)] +
+                              t.w[1] * f[feat_index(M.channels_last, g.batch, c, t.o[1], L.C, H * W)] +
+                              t.w[2] * f[feat_index(M.channels_last, g.batch, c, t.o[2], L.C, H * W)] +
+                              t.w[3] * f[feat_index(M.channels_last, g.batch, c, t.o[3], L.C, H * W)];
+                    acc += v;
+                }
+            out_or_gradout[idx] = acc / count;
+        } else {
+            const float count = (float)(g.gh * g.gw);
+            const float top = out_or_gradout[idx];
+            for (int iy = 0; iy < g.gh; iy++)
+                for (int ix = 0; ix < g.gw; ix++) {
+                    float x, y;
+                    sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+                    Taps t = make_taps(H, W, y, x);
+                    if (t.w[0] == 0.f && t.w[1] == 0.f && t.w[2] == 0.f && t.w[3] == 0.f) continue;
+                    float* gf = M.grad[g.level];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        atomicAdd(gf + feat_index(M.channels_last, g.batch, c, t.o[k], L.C, H * W), top * t.w[k] / count);
+                }
+        }
+    }
+}
+
+static bool fast_path_ok(const rsdet_roi_align_cfg* c) {
+    return c->channels % 4 == 0 && c->sampling_ratio > 0 &&
+           c->pooled_h * c->pooled_w * c->sampling_ratio * c->sampling_ratio <= kMaxSamples;
+}
+
+static int check_cfg(const rsdet_roi_align_cfg* c) {
+    if (!c) return RSDET_EINVAL;
+    if (c->num_levels < 1 || c->num_levels > RSDET_MAX_LEVELS || c->batch < 1 || c->channels < 1) return RSDET_EINVAL;
+    if (c->pooled_h < 1 || c->pooled_w < 1 || (c->version != 0 && c->version != 1)) return RSDET_EINVAL;
+    for (int l = 0; l < c->num_levels; l++)
+        if (c->height[l] < 1 || c->width[l] < 1) return RSDET_EINVAL;
+    return RSDET_OK;
+}
+
+static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
+    LevelSet L;
+    L.num_levels = c->num_levels; L.batch = c->batch; L.C = c->channels;
+    L.PH = c->pooled_h; L.PW = c->pooled_w; L.sampling_ratio = c->sampling_ratio; L.version = c->version;
+    L.extend_w = c->extend_w; L.extend_h = c->extend_h; L.finest_scale = c->finest_scale;
+    for (int l = 0; l < RSDET_MAX_LEVELS; l++) {
+        L.feat[l] = nullptr; L.grad[l] = nullptr;
+        L.H[l] = l < c->num_levels ? c->height[l] : 1;
+        L.W[l] = l < c->num_levels ? c->width[l] : 1;
+        L.scale[l] = l < c->num_levels ? c->spatial_scale[l] : 1.f;
+    }
+    return L;
+}
+
+static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
+    int nbins = c->pooled_h * c->pooled_w;
+    int nsamp = nbins * c->sampling_ratio * c->sampling_ratio;
+    int Q = quads_per_chunk(c->channels);
+    return sizeof(Taps) * (size_t)nsamp + sizeof(float) * 4 * (size_t)nbins * (Q + 1);
+}
+
+}  // namespace rsdet
+
+using namespace rsdet;
+
+extern "C" size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward) {
+    (void)num_rois; (void)backward;
+    if (check_cfg(cfg) != RSDET_OK) return 0;
+    if (cfg->channels_last || !fast_path_ok(cfg)) return 256;
+    size_t b = 0;
+    for (int l = 0; l < cfg->num_levels; l++)
+        b += ws_bytes<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
+    return b + 256;
+}
+
+extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, const float* const* feats_host, const float* rois,
+                                               int num_rois, float* out, int32_t* levels_out, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != RSDET_OK) return rc;
+    if (num_rois < 0) return RSDET_EINVAL;
+    if (num_rois == 0) return RSDET_OK;
+    if (!feats_host || !rois || !out) return RSDET_EINVAL;
+    for (int l = 0; l < cfg->num_levels; l++)
+        if (!feats_host[l]) return RSDET_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelSet L = make_levels(cfg);
+    if (!fast_path_ok(cfg)) {
+        GenericMaps M;
+        M.channels_last = cfg->channels_last;
+        for (int l = 0; l < RSDET_MAX_LEVELS; l++) { M.feat[l] = l < cfg->num_levels ? feats_host[l] : nullptr; M.grad[l] = nullptr; }
+        long long total = (long long)num_rois * cfg->channels * cfg->pooled_h * cfg->pooled_w;
+        int grid = (int)(ceil_div_ll(total, 256) < (long long)kNumSMs * 16 ? ceil_div_ll(total, 256) : (long long)kNumSMs * 16);
+        roi_align_generic_kernel<false><<<grid, 256, 0, st>>>(L, M, rois, num_rois, out, levels_out);
+        count_launch();
+        return cuda_status();
+    }
+    if (cfg->channels_last) {
+        for (int l = 0; l < cfg->num_levels; l++) L.feat[l] = feats_host[l];
+    } else {
+        if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 0)) return RSDET_EWORKSPACE;
+        Workspace ws(workspace, workspace_bytes);
+        float* dst[RSDET_MAX_LEVELS];
+        for (int l = 0; l < cfg->num_levels; l++) {
+            dst[l] = ws.take<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
+            L.feat[l] = dst[l];
+        }
+        if (!ws.ok()) return RSDET_EWORKSPACE;
+        rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st);
+        if (rc != RSDET_OK) return rc;
+    }
+    size_t smem = fast_smem_bytes(cfg);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
+    int Q = quads_per_chunk(cfg->channels);
+    dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
+    roi_align_fwd_kernel<<<grid, kRoiThreads, smem, st>>>(L, rois, num_rois, out, levels_out);
+    count_launch();
+    return cuda_status();
+}
+
+extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, const float* grad_out, const float* rois,
+                                                int num_rois, float* const* grad_feats_host, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc != RSDET_OK) return rc;
+    if (num_rois < 0 || !grad_feats_host) return RSDET_EINVAL;
+    for (int l = 0; l < cfg->num_levels; l++)
+        if (!grad_feats_host[l]) return RSDET_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelSet L = make_levels(cfg);
+    const bool fast = fast_path_ok(cfg);
+    const bool direct = cfg->channels_last || !fast;  // accumulate straight into the caller's buffers
+    float* acc[RSDET_MAX_LEVELS];
+    if (direct) {
+        for (int l = 0; l < cfg->num_levels; l++) acc[l] = grad_feats_host[l];
+    } else {
+        if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 1)) return RSDET_EWORKSPACE;
+        Workspace ws(workspace, workspace_bytes);
+        for (int l = 0; l < cfg->num_levels; l++)
+            acc[l] = ws.take<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
+        if (!ws.ok()) return RSDET_EWORKSPACE;
+    }
+    for (int l = 0; l < cfg->num_levels; l++) {
+        cudaMemsetAsync(acc[l], 0, sizeof(float) * (size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l], st);
+        L.grad[l] = acc[l];
+    }
+    count_launch(cfg->num_levels);
+    if (num_rois > 0) {
+        if (!grad_out || !rois) return RSDET_EINVAL;
+        if (!fast) {
+            GenericMaps M;
+            M.channels_last = cfg->channels_last;
+            for (int l = 0; l < RSDET_MAX_LEVELS; l++) { M.feat[l] = nullptr; M.grad[l] = l < cfg->num_levels ? acc[l] : nullptr; }
+            long long total = (long long)num_rois * cfg->channels * cfg->pooled_h * cfg->pooled_w;
+            int grid = (int)(ceil_div_ll(total, 256) < (long long)kNumSMs * 16 ? ceil_div_ll(total, 256) : (long long)kNumSMs * 16);
+            roi_align_generic_kernel<true><<<grid, 256, 0, st>>>(L, M, rois, num_rois, const_cast<float*>(grad_out), nullptr);
+        } else {
+            size_t smem = fast_smem_bytes(cfg);
+            static size_t smem_set = 0;
+            if (smem > smem_set) {
+                cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                smem_set = smem;
+            }
+            int Q = quads_per_chunk(cfg->channels);
+            dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
+            roi_align_bwd_kernel<<<grid, kRoiThreads, smem, st>>>(L, rois, num_rois, grad_out);
+        }
+        count_launch();
+    }
+    if (!direct) {
+        rc = launch_transpose(false, acc, grad_feats_host, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st);
+        if (rc != RSDET_OK) return rc;
+    }
+    return cuda_status();
+}
+
+extern "C" int rsdet_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
+    if (!src || !dst || n < 1 || c < 1 || h < 1 || w < 1) return RSDET_EINVAL;
+    const float* s[1] = {src};
+    float* d[1] = {dst};
+    return launch_transpose(true, s, d, &h, &w, 1, n, c, (cudaStream_t)stream);
+}
+
+extern "C" int rsdet_nhwc_to_nchw(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
+    if (!src || !dst || n < 1 || c < 1 || h < 1 || w < 1) return RSDET_EINVAL;
+    const float* s[1] = {src};
+    float* d[1] = {dst};
+    return launch_transpose(false, s, d, &h, &w, 1, n, c, (cudaStream_t)stream);
+}

@@ -1,0 +1,218 @@
+// rotated_iou.cuh -- device-side rotated-rectangle IoU, bit-faithful to the reference's float
+// arithmetic (python/jdet/ops/box_iou_rotated.py:42-310, box_iou_rotated_v1.py:52-77,
+// nms_rotated.py:52-312), restructured for the GPU:
+//
+//  * everything that depends on ONE box (double-precision sin/cos, the four half-extent products,
+//    the area, a bounding radius) is computed once per box by prep_rbox() instead of once per pair;
+//  * pairs whose bounding circles are disjoint return exactly 0 without touching the clipper
+//    (the reference finds no intersection point for them and returns 0.0 as well);
+//  * the 32 IEEE divisions of the edge-edge test are replaced by sign/magnitude comparisons that
+//    decide `0 <= fl(a/b) <= 1` exactly; only edges that really cross pay for the division;
+//  * the <=24 candidate points live in shared memory in a [slot][thread] layout (bank = lane, so the
+//    data-dependent slot index never causes a bank conflict), not in local memory.
+//
+// Translation units that include this header MUST be compiled with -fmad=false: the reference CPU
+// build does not contract a*b+c, and bit-exact keep sets are the parity target.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace rsdet {
+
+// float images of the reference's double-typed tolerances, chosen so that the float comparison
+// decides exactly like the reference's float-vs-double comparison:
+//   x <= 1e-14  <=>  x <= kLe1em14   (largest float <= 1e-14)
+//   x <  1e-6   <=>  x <= kLo1em6    (largest float <  1e-6);   x < -1e-6 <=> x < -kLo1em6
+//   x >  1e-8   <=>  x >  kLo1em8    (largest float <= 1e-8)
+__device__ __forceinline__ float kLe1em14() { return __int_as_float(0x283424dc); }
+__device__ __forceinline__ float kLo1em6() { return __int_as_float(0x358637bd); }
+__device__ __forceinline__ float kLo1em8() { return __int_as_float(0x322bcc77); }
+
+struct __align__(16) RBox {
+    float x, y;    // raw centre
+    float sh, cw;  // (sin/2)*h, (cos/2)*w   (negated for version 1)
+    float ch, sw;  // (cos/2)*h, (sin/2)*w
+    float area;    // w*h
+    float r;       // inflated circumradius; negative => degenerate box (area < 1e-14): IoU is 0
+};
+
+// get_rotated_vertices' per-box part: box_iou_rotated.py:52-62 / box_iou_rotated_v1.py:52-62.
+__device__ __forceinline__ RBox prep_rbox(const float* __restrict__ b, int version) {
+    RBox o;
+    float w = b[2], h = b[3];
+    double theta = (double)b[4];
+    float c2 = (float)cos(theta) * 0.5f;
+    float s2 = (float)sin(theta) * 0.5f;
+    o.x = b[0];
+    o.y = b[1];
+    o.sh = s2 * h;
+    o.cw = c2 * w;
+    o.ch = c2 * h;
+    o.sw = s2 * w;
+    if (version == 1) {  // v1: x + s*h + c*w  ==  x - (-s*h) - (-c*w), negation is exact
+        o.sh = -o.sh;
+        o.cw = -o.cw;
+    }
+    o.area = w * h;
+    float rr = 0.5f * sqrtf(w * w + h * h);
+    rr = rr * 1.0001f + 1e-4f;
+    o.r = ((double)o.area < 1e-14) ? -1e30f : rr;
+    return o;
+}
+
+__device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - bx * ay; }
+__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
+
+// cheap exact-zero test: disjoint bounding circles (also rejects degenerate boxes)
+__device__ __forceinline__ bool rbox_may_overlap(const RBox& a, const RBox& b) {
+    float rs = a.r + b.r;
+    float dx = a.x - b.x, dy = a.y - b.y;
+    return (rs >= 0.f) && !(dx * dx + dy * dy > rs * rs);
+}
+
+// 0 <= fl(n/d) <= 1 decided without dividing (d != 0): exact for IEEE single division, see header.
+__device__ __forceinline__ bool unit_ratio(float n, float d) {
+    return d > 0.f ? (n >= 0.f && n <= d) : (n <= 0.f && n >= d);
+}
+
+// single_box_iou_rotated (box_iou_rotated.py:279-310).  q: this thread's point scratch, element i at
+// q[i * STRIDE]; needs 24 slots.
+template <int STRIDE>
+__device__ float rotated_iou_pair(const RBox& a, const RBox& b, float2* __restrict__ q) {
+    // centre shift to the pair midpoint (:288-296).  x - (x1+x2)/2 is exact in the reference's double
+    // and therefore equals the correctly rounded float subtraction used here.
+    const float hx = (a.x + b.x) * 0.5f, hy = (a.y + b.y) * 0.5f;
+    const float ax = a.x - hx, ay = a.y - hy, bx = b.x - hx, by = b.y - hy;
+
+    float p1x[4], p1y[4], p2x[4], p2y[4];
+    p1x[0] = ax - a.sh - a.cw;  p1y[0] = ay + a.ch - a.sw;
+    p1x[1] = ax + a.sh - a.cw;  p1y[1] = ay - a.ch - a.sw;
+    p1x[2] = 2 * ax - p1x[0];   p1y[2] = 2 * ay - p1y[0];
+    p1x[3] = 2 * ax - p1x[1];   p1y[3] = 2 * ay - p1y[1];
+    p2x[0] = bx - b.sh - b.cw;  p2y[0] = by + b.ch - b.sw;
+    p2x[1] = bx + b.sh - b.cw;  p2y[1] = by - b.ch - b.sw;
+    p2x[2] = 2 * bx - p2x[0];   p2y[2] = 2 * by - p2y[0];
+    p2x[3] = 2 * bx - p2x[1];   p2y[3] = 2 * by - p2y[1];
+
+    float v1x[4], v1y[4], v2x[4], v2y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v1x[i] = p1x[(i + 1) & 3] - p1x[i];  v1y[i] = p1y[(i + 1) & 3] - p1y[i];
+        v2x[i] = p2x[(i + 1) & 3] - p2x[i];  v2y[i] = p2y[(i + 1) & 3] - p2y[i];
+    }
+
+    int num = 0;
+    // edge x edge (:92-113)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float det = cross2(v2x[j], v2y[j], v1x[i], v1y[i]);
+            if (fabsf(det) <= kLe1em14()) continue;
+            float wx = p2x[j] - p1x[i], wy = p2y[j] - p1y[i];
+            float n1 = cross2(v2x[j], v2y[j], wx, wy);
+            float n2 = cross2(v1x[i], v1y[i], wx, wy);
+            if (unit_ratio(n1, det) && unit_ratio(n2, det)) {
+                float t1 = n1 / det;
+                q[num * STRIDE] = make_float2(p1x[i] + v1x[i] * t1, p1y[i] + v1y[i] * t1);
+                num++;
+            }
+        }
+    }
+    // corners of box 1 inside box 2 (:115-136)
+    {
+        float ABx = v2x[0], ABy = v2y[0], DAx = v2x[3], DAy = v2y[3];
+        float ABdotAB = dot2(ABx, ABy, ABx, ABy), ADdotAD = dot2(DAx, DAy, DAx, DAy);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float APx = p1x[i] - p2x[0], APy = p1y[i] - p2y[0];
+            float APdotAB = dot2(APx, APy, ABx, ABy);
+            float APdotAD = -dot2(APx, APy, DAx, DAy);
+            if (APdotAB >= 0 && APdotAD >= 0 && APdotAB <= ABdotAB && APdotAD <= ADdotAD) {
+                q[num * STRIDE] = make_float2(p1x[i], p1y[i]);
+                num++;
+            }
+        }
+    }
+    // corners of box 2 inside box 1 (:138-155)
+    {
+        float ABx = v1x[0], ABy = v1y[0], DAx = v1x[3], DAy = v1y[3];
+        float ABdotAB = dot2(ABx, ABy, ABx, ABy), ADdotAD = dot2(DAx, DAy, DAx, DAy);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float APx = p2x[i] - p1x[0], APy = p2y[i] - p1y[0];
+            float APdotAB = dot2(APx, APy, ABx, ABy);
+            float APdotAD = -dot2(APx, APy, DAx, DAy);
+            if (APdotAB >= 0 && APdotAD >= 0 && APdotAB <= ABdotAB && APdotAD <= ADdotAD) {
+                q[num * STRIDE] = make_float2(p2x[i], p2y[i]);
+                num++;
+            }
+        }
+    }
+    if (num <= 2) return 0.0f / (a.area + b.area - 0.0f);
+
+    // convex_hull_graham (:155-238), CUDA flavour of the sort (:338-351); dist[] is recomputed from
+    // q[] on demand (it is a pure function of the point it travels with).
+    int t = 0;
+    float2 best = q[0];
+    for (int i = 1; i < num; i++) {
+        float2 c = q[i * STRIDE];
+        if (c.y < best.y || (c.y == best.y && c.x < best.x)) { t = i; best = c; }
+    }
+    for (int i = 0; i < num; i++) {
+        float2 c = q[i * STRIDE];
+        q[i * STRIDE] = make_float2(c.x - best.x, c.y - best.y);
+    }
+    {
+        float2 tmp = q[0];
+        q[0] = q[t * STRIDE];
+        q[t * STRIDE] = tmp;
+    }
+    const float e6 = kLo1em6();
+    for (int i = 1; i < num - 1; i++) {
+        float2 qi = q[i * STRIDE];
+        for (int j = i + 1; j < num; j++) {
+            float2 qj = q[j * STRIDE];
+            float cp = cross2(qi.x, qi.y, qj.x, qj.y);
+            bool sw = cp < -e6;
+            if (!sw && fabsf(cp) <= e6) sw = dot2(qi.x, qi.y, qi.x, qi.y) > dot2(qj.x, qj.y, qj.x, qj.y);
+            if (sw) {
+                q[j * STRIDE] = qi;
+                qi = qj;
+            }
+        }
+        q[i * STRIDE] = qi;
+    }
+    int k;
+    for (k = 1; k < num; k++) {
+        float2 c = q[k * STRIDE];
+        if (dot2(c.x, c.y, c.x, c.y) > kLo1em8()) break;
+    }
+    float ia = 0.f;
+    if (k < num) {
+        q[1 * STRIDE] = q[k * STRIDE];
+        int m = 2;
+        for (int i = k + 1; i < num; i++) {
+            float2 c = q[i * STRIDE];
+            while (m > 1) {
+                float2 s0 = q[(m - 2) * STRIDE], s1 = q[(m - 1) * STRIDE];
+                if (cross2(c.x - s0.x, c.y - s0.y, s1.x - s0.x, s1.y - s0.y) >= 0) m--;
+                else break;
+            }
+            q[m * STRIDE] = c;
+            m++;
+        }
+        // polygon_area (:240-252); q[0] is exactly (0,0) so q[i]-q[0] == q[i]
+        if (m > 2) {
+            float2 prev = q[1 * STRIDE];
+            for (int i = 1; i < m - 1; i++) {
+                float2 nxt = q[(i + 1) * STRIDE];
+                ia += fabsf(cross2(prev.x, prev.y, nxt.x, nxt.y));
+                prev = nxt;
+            }
+            ia = ia * 0.5f;
+        }
+    }
+    return ia / (a.area + b.area - ia);
+}
+
+}  // namespace rsdet

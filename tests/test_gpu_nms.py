@@ -1,0 +1,127 @@
+"""GPU parity: nms_rotated / ml_nms_rotated / multiclass_nms_rotated / poly_nms through the jdet mirror
+-> C ABI vs the oracle.  Contract: keep indices bit-exact (pairs inside the 1e-6 band are counted)."""
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+from helpers import band_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_known_answer(cuda):
+    from rs_detection_b200.jdet.ops.nms_rotated import ml_nms_rotated, nms_rotated
+    dets = _t(np.array([[0, 0, 1, 1, 0], [0, 0, 0.5, 0.5, 0.3], [0, 0, 0.9, 0.9, 0]], np.float32))
+    scores = _t(np.array([0.1, 0.2, 0.3], np.float32))
+    labels = _t(np.array([1, 1, 1]))
+    assert nms_rotated(dets, scores, 0.3).tolist() == [2]           # nms_rotated.py:598-603
+    assert ml_nms_rotated(dets, scores, labels, 0.3).tolist() == [2]
+    assert nms_rotated(torch.zeros((0, 5), device="cuda"), torch.zeros((0,), device="cuda"), 0.3).numel() == 0
+
+
+@pytest.mark.parametrize("n,canvas", [(1, 1024), (63, 256), (64, 256), (65, 256), (1000, 1024), (5000, 1024)])
+@pytest.mark.parametrize("thr", [0.1, 0.5])
+def test_nms_rotated_vs_oracle(cuda, oracle, n, canvas, thr):
+    from rs_detection_b200.jdet.ops.nms_rotated import nms_rotated
+    d = W.rotated_boxes(n, 100 + n, canvas=canvas, smin=8, smax=128)
+    s = W.distinct_scores(n, 100 + n)
+    got = nms_rotated(_t(d), _t(s), thr).cpu().numpy()
+    want = oracle.nms_rotated(d, s, thr, ge=False)
+    if n <= 1000:
+        print("band pairs:", band_pairs(oracle.box_iou_rotated(d, d, 0, 1), thr))
+    assert np.array_equal(got, want)
+    assert np.all(np.diff(got) > 0)  # ascending original index (jt.where(keep)[0])
+
+
+def test_nms_cpu_cuda_rule_and_explicit_order(cuda, oracle):
+    from rs_detection_b200.jdet.ops.nms_rotated import nms_rotated_cpu, nms_rotated_cuda
+    n = 800
+    d = W.rotated_boxes(n, 7, canvas=512, smin=16, smax=128)
+    d[100:200] = d[0:100]  # exact duplicates: IoU == 1 -> `>=` and `>` agree; thr 1.0 separates them
+    s = W.distinct_scores(n, 7)
+    order = np.argsort(-s.astype(np.float64), kind="stable").astype(np.int32)
+    for thr in (0.3, 1.0):
+        for fn, ge in ((nms_rotated_cpu, True), (nms_rotated_cuda, False)):
+            got = fn(_t(d), _t(order.astype(np.int64)), thr, box_length=5).cpu().numpy()
+            assert np.array_equal(got, oracle.nms_rotated_keep(d, order, thr, 5, ge, 1)), (thr, ge)
+
+
+@pytest.mark.parametrize("n,ncls", [(3000, 15), (4000, 1), (500, 500)])
+def test_ml_nms_rotated_vs_oracle(cuda, oracle, n, ncls):
+    from rs_detection_b200.jdet.ops.nms_rotated import ml_nms_rotated
+    d = W.rotated_boxes(n, 31, canvas=700, smin=16, smax=128)
+    s = W.distinct_scores(n, 31)
+    lab = np.random.default_rng(1).integers(0, ncls, n)
+    got = ml_nms_rotated(_t(d), _t(s), _t(lab), 0.1).cpu().numpy()
+    assert np.array_equal(got, oracle.ml_nms_rotated(d, s, lab, 0.1))
+
+
+@pytest.mark.parametrize("max_num", [-1, 2000, 50])
+@pytest.mark.parametrize("per_class_boxes", [False, True])
+def test_multiclass_nms_rotated_vs_oracle(cuda, oracle, max_num, per_class_boxes):
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    n, C = 1500, 15
+    sc = W.class_scores(n, C, 3)
+    if per_class_boxes:
+        bb = np.concatenate([W.rotated_boxes(n, 40 + c, smin=16, smax=160) for c in range(C + 1)], 1)
+    else:
+        bb = W.rotated_boxes(n, 40, smin=16, smax=160)
+    fac = np.random.default_rng(9).uniform(0.5, 1.0, n).astype(np.float32)
+    for sf in (None, fac):
+        wd, wl = oracle.multiclass_nms_rotated(bb, sc, 0.05, dict(type='nms_rotated', iou_thr=0.1), max_num, sf)
+        gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 0.05, dict(type='nms_rotated', iou_thr=0.1), max_num,
+                                        None if sf is None else _t(sf))
+        assert gd.shape == wd.shape and gd.shape[1] == 6
+        assert np.array_equal(gd.cpu().numpy(), wd)
+        assert np.array_equal(gl.cpu().numpy(), wl)
+    # nothing above the score threshold -> (0,6), (0,)
+    gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 2.0, dict(iou_thr=0.1), max_num)
+    assert tuple(gd.shape) == (0, 6) and gl.numel() == 0
+
+
+def test_poly_nms_vs_oracle(cuda, oracle):
+    from rs_detection_b200.jdet.ops.nms_poly import multiclass_poly_nms, poly_nms
+    n = 1200
+    pp = oracle.obb2poly(W.rotated_boxes(n, 51, canvas=600, smin=16, smax=128))
+    s = W.distinct_scores(n, 51)
+    b9 = np.concatenate([pp, s[:, None]], 1)
+    for thr in (0.1, 0.5):
+        got = poly_nms(_t(b9), thr).cpu().numpy()
+        want = oracle.poly_nms(b9, thr)
+        assert np.array_equal(got, want)
+    lab = np.random.default_rng(2).integers(0, 15, n)
+    gd, gl = multiclass_poly_nms(_t(pp), _t(s), _t(lab), 0.1)
+    wd, wl = oracle.multiclass_poly_nms(pp, s, lab, 0.1)
+    assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+
+
+def test_large_nms_properties(cuda):
+    """50k boxes: too slow for the CPU oracle; size-independent properties of greedy NMS instead:
+    (a) idempotence, (b) survivors are pairwise below threshold, (c) every suppressed box has a
+    higher-scored survivor above threshold."""
+    from rs_detection_b200 import core
+    from rs_detection_b200._lib import NMS_ROTATED
+    n, thr = 50000, 0.3
+    d = _t(W.rotated_boxes(n, 77, canvas=4096, smin=8, smax=128))
+    s = _t(W.distinct_scores(n, 77))
+    res = core.nms(NMS_ROTATED, d, s, thr)
+    keep = res.sorted_idx
+    k = keep.numel()
+    assert 0 < k < n
+    again = core.nms(NMS_ROTATED, d[keep], s[keep], thr).sorted_idx
+    assert again.numel() == k                                                      # (a)
+    sub = keep[torch.randperm(k, device="cuda")[:3000]]
+    iou = core.box_iou_rotated(d[sub], d[keep], 0)
+    iou[torch.arange(sub.numel(), device="cuda"), torch.searchsorted(keep, sub)] = 0
+    assert float(iou.max()) <= thr                                                 # (b)
+    mask = res.keep_mask
+    supp = torch.nonzero(~mask)[:, 0]
+    supp = supp[torch.randperm(supp.numel(), device="cuda")[:3000]]
+    iou = core.box_iou_rotated(d[supp], d[keep], 0)
+    higher = s[keep][None, :] > s[supp][:, None]
+    assert bool(((iou > thr) & higher).any(1).all())                               # (c)
