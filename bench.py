@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the rotated-box hot path (BASELINE.json configs[1]).
+
+Workload (`config.workload`): Oriented R-CNN (orcnn_van3 config) inference hot path on synthetic
+DOTA-shaped 1024x1024 tiles, 8 tiles per GPU per step, tiles sharded over ranks (weak scaling, no
+data-path collective).  One tile =
+    OrientedSingleRoIExtractor forward: 4000 rotated proposals, 4 FPN levels (stride 4/8/16/32, C=256,
+        fp32 NCHW like Jittor), 7x7 bins, 2x2 samples  ->  (4000,256,7,7)
+    obb2poly on the 4000 decoded boxes (oriented_head.py:304)
+    multiclass_nms_rotated on the (4000 x 10 classes) candidates, score_thr 0.001, iou_thr 0.1,
+        max_num 2000 (the per-class nms_rotated BASELINE.json names)
+The FC head between extractor and NMS is dense GEMM in Jittor (out of scope): its outputs (class
+scores, decoded boxes) are synthetic, random-init-like softmax scores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+`value` : tiles/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
+`e2e`   : tiles/s through the public jdet-mirror API with HOST (pinned) inputs: per tile the pyramid,
+          proposals, boxes and scores are copied H2D and detections + polygons are read back D2H inside
+          the timed region (copies double-buffered against compute on a second stream).
+`roofline`: RoIAlignRotated forward kernel (HBM bound), timed alone (channels-last pyramid resident, one
+          launch per tile) with CUDA events in this same process.
+`cpu_baseline` / `--impl reference`: the reference's own kernel source compiled for the host
+          (oracle/_ref; RoIAlignRotated has no CPU body in the reference, so this is its CUDA source
+          run serially) on all host cores, on a bounded sample (1 tile per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+K_ROIS = 4000
+NUM_CLASSES = 10
+TILES_PER_GPU = 8
+SCORE_THR = 0.001
+IOU_THR = 0.1
+MAX_NUM = 2000
+EXTEND = (1.4, 1.2)
+METRIC = "tiles/s (Oriented R-CNN rotated-box hot path: RoIAlignRotated fwd + obb2poly + per-class nms_rotated)"
+WORKLOAD = ("configs[1]: orcnn_van3 inference hot path, 8 synthetic 1024x1024 tiles/GPU, 4000 rotated proposals/tile, "
+            "4 FPN levels C=256 fp32 NCHW, RoIAlignRotated_v1 7x7x2x2 -> obb2poly -> multiclass_nms_rotated "
+            "(10 classes, score_thr 0.001, iou_thr 0.1, max 2000)")
+
+
+def tile_inputs(seed):
+    """numpy inputs of one tile"""
+    feats = W.fpn_pyramid(1, seed)
+    rois = W.proposals(K_ROIS, seed)
+    boxes = W.rotated_boxes(K_ROIS, seed + 500)                      # decoded detections (synthetic head output)
+    scores = W.class_scores(K_ROIS, NUM_CLASSES, seed, logit_scale=1.0)  # background = column 0
+    return feats, rois, boxes, scores
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ reference arm (CPU)
+_REF_FEATS = None  # set before the worker pool forks, so the 89 MB pyramid is inherited, not pickled
+
+
+def _ref_roi_chunk(args):
+    from oracle import ref as R
+    level, rois, scale = args
+    return R.roi_fwd(_REF_FEATS[level], rois, (7, 7), scale, 2, 1)
+
+
+def _ref_nms_class(args):
+    from oracle import ref as R
+    boxes, scores, thr = args
+    order = np.argsort(-scores.astype(np.float64), kind="stable").astype(np.int32)
+    return R.nms_keep(boxes, order, thr, 5, ge=False)  # the CUDA path's `>` rule
+
+
+def reference_tile(nproc, inputs):
+    """One tile through the reference's own kernel source compiled for the host (oracle/_ref), all cores:
+    RoIs chunked over workers per level, then one NMS task per class (= ml_nms_rotated's label gate)."""
+    global _REF_FEATS
+    from multiprocessing import get_context
+    from oracle import oracle as O
+    feats, rois, boxes, scores = inputs
+    _REF_FEATS = feats
+    r = O.roi_rescale(rois, EXTEND)
+    lv = O.map_roi_levels(r, 4)
+    tasks, slots = [], []
+    for l in range(4):
+        idx = np.nonzero(lv == l)[0]
+        for ch in np.array_split(idx, max(1, min(4 * nproc, len(idx) // 16))):
+            if len(ch):
+                tasks.append((l, r[ch], 1.0 / W.STRIDES[l]))
+                slots.append(ch)
+    out = np.zeros((K_ROIS, W.CHANNELS, 7, 7), np.float32)
+    sc = scores[:, 1:]
+    ntasks = [(boxes[sc[:, c] > SCORE_THR], sc[sc[:, c] > SCORE_THR, c], IOU_THR) for c in range(NUM_CLASSES)]
+    with get_context("fork").Pool(nproc) as pool:
+        nms_async = pool.map_async(_ref_nms_class, ntasks, chunksize=1)
+        for ch, res in zip(slots, pool.map(_ref_roi_chunk, tasks, chunksize=1)):
+            out[ch] = res
+        keeps = nms_async.get()
+    polys = O.obb2poly(boxes)
+    kept = sum(int(k.sum()) for k in keeps)
+    return out, polys, kept
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import ref as R
+    if not R.available("ref_roi_v1"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    nproc = os.cpu_count() or 1
+    inputs = tile_inputs(0)
+    for _ in range(args.warmup_ref):
+        reference_tile(nproc, inputs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_tile(nproc, inputs)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"1 tile per step (the GPU arm runs {TILES_PER_GPU}/GPU), {args.steps} steps, {nproc} worker processes"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": nproc, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ our arm
+def touched_pixels(rois):
+    """U = number of distinct feature pixels the sampling grids touch, numpy restatement of the
+    kernel's geometry; only used to size the algorithmic bytes of the roofline."""
+    from oracle import oracle as O
+    r = O.roi_rescale(rois, EXTEND)
+    lv = O.map_roi_levels(r, 4)
+    total = 0
+    for l, s in enumerate(W.STRIDES):
+        rr = r[lv == l]
+        if not len(rr):
+            continue
+        H = Wd = W.TILE // s
+        sc = np.float32(1.0 / s)
+        cx, cy = rr[:, 1] * sc - 0.5, rr[:, 2] * sc - 0.5
+        rw, rh = np.maximum(rr[:, 3] * sc, 1), np.maximum(rr[:, 4] * sc, 1)
+        g = (np.arange(14) + 0.5) / 14.0 - 0.5
+        xx = rw[:, None, None] * g[None, None, :]
+        yy = rh[:, None, None] * g[None, :, None]
+        c, sn = np.cos(rr[:, 5])[:, None, None], np.sin(rr[:, 5])[:, None, None]
+        x = xx * c + yy * sn + cx[:, None, None]
+        y = yy * c - xx * sn + cy[:, None, None]
+        ok = (y >= -1) & (y <= H) & (x >= -1) & (x <= Wd)
+        x0 = np.clip(np.floor(np.maximum(x, 0)), 0, Wd - 1).astype(np.int64)
+        y0 = np.clip(np.floor(np.maximum(y, 0)), 0, H - 1).astype(np.int64)
+        x1, y1 = np.minimum(x0 + 1, Wd - 1), np.minimum(y0 + 1, H - 1)
+        m = np.zeros(H * Wd, bool)
+        for yy_, xx_ in ((y0, x0), (y0, x1), (y1, x0), (y1, x1)):
+            m[(yy_ * Wd + xx_)[ok]] = True
+        total += int(m.sum())
+    return total
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from rs_detection_b200 import _lib, core
+    from rs_detection_b200.jdet.models.roi_extractors.oriented_single_level import OrientedSingleRoIExtractor
+    from rs_detection_b200.jdet.ops.bbox_transforms import obb2poly
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+
+    _lib.load()
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    shapes = W.fpn_shapes()
+    scales = [1.0 / s for s in W.STRIDES]
+    cfg = core.make_roi_cfg(shapes, scales, 7, 2, 1, EXTEND, 56.0)
+    cfg_cl = core.make_roi_cfg(shapes, scales, 7, 2, 1, EXTEND, 56.0, channels_last=True)
+    tiles_np = [tile_inputs(1000 * rank + t) for t in range(TILES_PER_GPU)]
+    tiles = [([torch.from_numpy(f).to(dev) for f in fs], torch.from_numpy(r).to(dev), torch.from_numpy(b).to(dev),
+              torch.from_numpy(s).to(dev)) for fs, r, b, s in tiles_np]
+    out_buf = torch.empty((K_ROIS, W.CHANNELS, 7, 7), dtype=torch.float32, device=dev)
+
+    def device_step():
+        for feats, rois, boxes, scores in tiles:
+            core.roi_align_rotated_forward(cfg, feats, rois, out=out_buf)
+            core.obb2poly(boxes)
+            core.multiclass_nms_rotated(boxes, scores, SCORE_THR, IOU_THR, MAX_NUM)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * TILES_PER_GPU * args.steps / (ms_total * 1e-3)
+
+    # ---- component timings (same tiles, same process): per-kernel CUDA events
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(args.steps, 3)
+    ms_ext = timed(lambda: [core.roi_align_rotated_forward(cfg, f, r, out=out_buf) for f, r, _, _ in tiles], reps) / TILES_PER_GPU
+    ms_nms = timed(lambda: [core.multiclass_nms_rotated(b, s, SCORE_THR, IOU_THR, MAX_NUM) for _, _, b, s in tiles], reps) / TILES_PER_GPU
+    feats_cl = [[core.nchw_to_nhwc(f) for f in fs] for fs, _, _, _ in tiles]
+    ms_fwd_kernel = timed(lambda: [core.roi_align_rotated_forward(cfg_cl, fcl, t[1], out=out_buf) for fcl, t in zip(feats_cl, tiles)],
+                          reps) / TILES_PER_GPU
+    # training-side figures (config 3): fwd+bwd on 512 sampled RoIs, IoU 512x2000 + assignment
+    rois512 = tiles[0][1][:512].contiguous()
+    gout = torch.randn((512, W.CHANNELS, 7, 7), device=dev)
+    ms_fb = timed(lambda: (core.roi_align_rotated_forward(cfg, tiles[0][0], rois512),
+                           core.roi_align_rotated_backward(cfg, gout, rois512, shapes)), reps)
+    gt = torch.from_numpy(W.jittered_copies(tiles_np[0][1][:, 1:], 512, 3)).to(dev)
+    props = tiles[0][1][:2000, 1:].contiguous()
+    ms_iou = timed(lambda: core.assign_wrt_overlaps(core.box_iou_rotated(gt, props, 1, True), 0.5, 0.5, 0.5, False), reps)
+    del feats_cl
+
+    # ---- roofline of the dominant HBM kernel: roi_align_fwd_kernel (one launch per tile)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    U = float(np.mean([touched_pixels(t[1]) for t in tiles_np[:2]]))
+    algo_bytes = 4.0 * K_ROIS * W.CHANNELS * 49 + 24.0 * K_ROIS + 4.0 * W.CHANNELS * U
+    achieved = algo_bytes / (ms_fwd_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "roi_align_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": ms_fwd_kernel, "touched_pixels": U}
+    prof = os.path.join(ROOT, "profiles", "roi_fwd_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = float(json.load(open(prof))["dram_bytes_per_launch"])
+        except Exception:
+            pass
+
+    # ---- end-to-end through the public API with host buffers
+    ext = OrientedSingleRoIExtractor(dict(type='ROIAlignRotated_v1', output_size=7, sampling_ratio=2), W.CHANNELS,
+                                     list(W.STRIDES), extend_factor=EXTEND)
+    pinned = [([torch.from_numpy(f).pin_memory() for f in fs], torch.from_numpy(r).pin_memory(), torch.from_numpy(b).pin_memory(),
+               torch.from_numpy(s).pin_memory()) for fs, r, b, s in tiles_np]
+    h2d_bytes = sum(sum(f.numel() for f in fs) * 4 + (r.numel() + b.numel() + s.numel()) * 4 for fs, r, b, s in pinned)
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [([torch.empty(s, device=dev) for s in shapes], torch.empty((K_ROIS, 6), device=dev),
+              torch.empty((K_ROIS, 5), device=dev), torch.empty((K_ROIS, NUM_CLASSES + 1), device=dev)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    d2h = [0]
+
+    def e2e_step():
+        comp = torch.cuda.current_stream()
+        for e in freed:
+            e.record(comp)
+        results = []
+
+        def upload(i):
+            sl = slots[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                fs, r, b, s = pinned[i]
+                for d, h in zip(sl[0], fs):
+                    d.copy_(h, non_blocking=True)
+                sl[1].copy_(r, non_blocking=True); sl[2].copy_(b, non_blocking=True); sl[3].copy_(s, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        upload(0)
+        nbytes = 0
+        for i in range(TILES_PER_GPU):
+            if i + 1 < TILES_PER_GPU:
+                upload(i + 1)
+            sl = slots[i % 2]
+            comp.wait_event(ready[i % 2])
+            feats_roi = ext(sl[0], sl[1])
+            polys = obb2poly(sl[2])
+            dets, labels = multiclass_nms_rotated(sl[2], sl[3], SCORE_THR, dict(type='nms_rotated', iou_thr=IOU_THR), MAX_NUM)
+            freed[i % 2].record(comp)
+            dh, lh, ph = dets.cpu(), labels.cpu(), polys.cpu()  # detections + polygons back to the host
+            nbytes += dh.numel() * 4 + lh.numel() * 4 + ph.numel() * 4
+            results.append((dh.shape[0], float(feats_roi[0, 0, 0, 0])))
+        d2h[0] = nbytes
+        return results
+
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    barrier()
+    ms_e2e = max_over_ranks(a.elapsed_time(b))
+    e2e_val = world * TILES_PER_GPU * args.steps / (ms_e2e * 1e-3)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref as R
+        nproc = os.cpu_count() or 1
+        if R.available("ref_roi_v1"):
+            t0 = time.perf_counter()
+            reference_tile(nproc, tiles_np[0])
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": 1.0 / dt, "unit": "tiles/s", "cores": nproc, "kind": "reference",
+                            "sample": "1 tile (4000 RoIs + 40k NMS candidates) through oracle/_ref = the reference's "
+                                      "kernel source compiled for the host; RoI chunks / classes over all cores"}
+        else:
+            cpu_baseline = {"value": None, "unit": "tiles/s", "cores": nproc, "kind": "reference",
+                            "sample": "oracle/_ref not built"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tiles_per_gpu": TILES_PER_GPU, "rois_per_tile": K_ROIS,
+                       "nms_candidates_per_tile": K_ROIS * NUM_CLASSES,
+                       "l2_policy": "inputs larger than L2 (8 pyramids = 713 MB per GPU cycled every step)"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h[0]),
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "components": {
+                "roi_extractor_fwd_ms_per_tile": ms_ext, "roi_extractor_fwd_rois_per_s": K_ROIS / (ms_ext * 1e-3),
+                "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel,
+                "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
+                "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
+                "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup_ref = min(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
