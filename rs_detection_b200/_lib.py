@@ -110,9 +110,10 @@ _workspaces: dict = {}
 
 
 def workspace(nbytes: int, tag: str = "default") -> torch.Tensor:
-    """Cached per-(device, tag) scratch buffer, grown geometrically; contents are undefined."""
+    """Cached per-(device, stream, tag) scratch buffer, grown geometrically; contents are undefined.
+    Keyed by the current stream so that tiles processed on different streams never share scratch."""
     dev = torch.cuda.current_device()
-    key = (dev, tag)
+    key = (dev, torch.cuda.current_stream().cuda_stream, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         size = max(int(nbytes * 1.25) + 4096, 1 << 20)

@@ -32,7 +32,6 @@ __global__ void __launch_bounds__(kIouThreads)
 box_iou_tiles_kernel(const RBox* __restrict__ rows, int n1, const RBox* __restrict__ cols, int n2, float* __restrict__ out) {
     __shared__ RBox s_row[kTile];
     __shared__ RBox s_col[kTile];
-    __shared__ float s_cx[kTile], s_cy[kTile], s_cr[kTile];
     __shared__ unsigned short s_queue[kTile * kTile];
     __shared__ float2 s_pts[24 * kIouThreads];
     __shared__ int s_count;
@@ -51,30 +50,33 @@ box_iou_tiles_kernel(const RBox* __restrict__ rows, int n1, const RBox* __restri
         } else {
             int c = tid - kTile;
             if (c < nc) {
-                RBox b = cols[c0 + c];
-                s_col[c] = b;
-                s_cx[c] = b.x; s_cy[c] = b.y; s_cr[c] = b.r;
+                s_col[c] = cols[c0 + c];
             }
         }
         if (tid == 0) s_count = 0;
         __syncthreads();
 
-        // phase 1: reject test, zero stores, queue the candidates
-        for (int p = tid; p < kTile * kTile; p += kIouThreads) {
-            int r = p >> 6, c = p & 63;
-            bool cand = false;
-            if (r < nr && c < nc) {
-                float rs = s_row[r].r + s_cr[c];
-                float dx = s_row[r].x - s_cx[c], dy = s_row[r].y - s_cy[c];
-                cand = (rs >= 0.f) && !(dx * dx + dy * dy > rs * rs);
-                if (!cand) out[(size_t)(r0 + r) * n2 + c0 + c] = 0.f;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+        // phase 1: exact-zero filters (bounding circles, then separating axes in both box frames); zero
+        // stores are coalesced (a warp covers 32 consecutive columns of one row); survivors are queued.
+        {
+            const int c = tid & 63, rhalf = tid >> 6;
+            RBox colbox;
+            if (c < nc) colbox = s_col[c];
+#pragma unroll 2
+            for (int k = 0; k < 32; k++) {
+                const int r = 2 * k + rhalf;
+                bool cand = false;
+                if (r < nr && c < nc) {
+                    cand = rbox_may_overlap(s_row[r], colbox) && rbox_inter_upper_bound(s_row[r], colbox) > 0.f;
+                    if (!cand) out[(size_t)(r0 + r) * n2 + c0 + c] = 0.f;
+                }
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 6) | c);
+                }
             }
         }
         __syncthreads();

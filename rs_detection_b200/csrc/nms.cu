@@ -38,6 +38,7 @@ namespace rsdet {
 constexpr int kNmsThreads = 128;
 constexpr int kReduceThreads = 256;
 constexpr size_t kCubTempBytes = 8u << 20;
+constexpr int kFastSegs = 2048;  // segment starts collected with atomics + one in-CTA bitonic sort
 
 // ----------------------------------------------------------------------------- predicates
 struct PolyBox { float p[8]; };
@@ -49,7 +50,10 @@ template <> struct Traits<RSDET_NMS_ROTATED> {
     using Box = RBox; using Raw = float; using Thr = float;
     static constexpr int kRow = 5; static constexpr bool kScratch = true;
     __device__ static Box prep(const Raw* r) { return prep_rbox(r, 0); }
-    __device__ static bool candidate(const Box& a, const Box& b) { return rbox_may_overlap(a, b); }
+    // bounding circles, then the oriented-frame upper bound of the IoU (exact decisions, see rotated_iou.cuh)
+    __device__ static bool candidate(const Box& a, const Box& b, Thr thr) {
+        return rbox_may_overlap(a, b) && !rbox_iou_below(a, b, thr);
+    }
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2* q) {
         return rotated_iou_pair<kNmsThreads>(a, b, q) > thr;
     }
@@ -63,7 +67,7 @@ template <> struct Traits<RSDET_NMS_POLY> {
     using Box = PolyBox; using Raw = float; using Thr = float;
     static constexpr int kRow = 8; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; for (int i = 0; i < 8; i++) b.p[i] = r[i]; return b; }
-    __device__ static bool candidate(const Box&, const Box&) { return true; }  // see poly_iou.cuh
+    __device__ static bool candidate(const Box&, const Box&, Thr) { return true; }  // see poly_iou.cuh
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return poly_iou_f32(a.p, b.p) > thr; }
 };
 template <> struct Traits<RSDET_NMS_MERGE> {
@@ -80,7 +84,7 @@ template <> struct Traits<RSDET_NMS_MERGE> {
         b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2;
         return b;
     }
-    __device__ static bool candidate(const Box& a, const Box& b) { return merge_hbb_overlap(a, b); }
+    __device__ static bool candidate(const Box& a, const Box& b, Thr) { return merge_hbb_overlap(a, b); }
     // survivors are `iou <= thr` (result_merge.py:118)
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return !(iou_poly_d(a, b) <= thr); }
 };
@@ -88,7 +92,7 @@ template <> struct Traits<RSDET_NMS_HBB> {
     using Box = HBox; using Raw = double; using Thr = double;
     static constexpr int kRow = 4; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
-    __device__ static bool candidate(const Box& a, const Box& b) {
+    __device__ static bool candidate(const Box& a, const Box& b, Thr) {
         return fmin(a.x2, b.x2) > fmax(a.x1, b.x1) && fmin(a.y2, b.y2) > fmax(a.y1, b.y1);
     }
     // merge.py:21-25: survivors are `iou < thresh`
@@ -102,7 +106,7 @@ template <> struct Traits<RSDET_NMS_HBB> {
 
 // ----------------------------------------------------------------------------- segment table
 struct SegTable {
-    int* hdr;              // [0]=nseg [1]=n_eff [2]=tile counter  (+ [4..5] total tiles as long long)
+    int* hdr;              // [0]=nseg [1]=n_eff [2]=tile counter [3]=#boundaries  (+ [4..5] total tiles as long long)
     int* seg_start;        // nseg+1
     long long* tile_pref;  // nseg+1
     long long* mask_off;   // nseg+1 (in 64-bit words)
@@ -129,25 +133,44 @@ __global__ void make_keys_kernel(const ScoreT* __restrict__ scores, int n_max, K
     idx[i] = i;
 }
 
+// label_bits == 32: arbitrary int32 labels (sign-flipped key).  label_bits < 32: the caller guarantees
+// 0 <= label, and every label >= 2^bits-1 (the dead-row marker) collapses onto the all-ones key, so the
+// radix sort needs ceil(bits/8) passes instead of 4.
 __global__ void label_keys_kernel(const int32_t* __restrict__ labels, const int* __restrict__ idx, int n_max,
-                                  const int* __restrict__ n_dev, uint32_t* __restrict__ lkeys) {
+                                  const int* __restrict__ n_dev, int label_bits, uint32_t* __restrict__ lkeys) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_max) return;
     int n = n_dev ? min(*n_dev, n_max) : n_max;
-    lkeys[p] = p < n ? ((uint32_t)labels[idx[p]] ^ 0x80000000u) : 0xffffffffu;
+    uint32_t key;
+    if (label_bits >= 32) key = p < n ? ((uint32_t)labels[idx[p]] ^ 0x80000000u) : 0xffffffffu;
+    else {
+        const uint32_t top = (1u << label_bits) - 1u;
+        key = p < n ? min((uint32_t)labels[idx[p]], top) : top;
+    }
+    lkeys[p] = key;
 }
 
 template <int KIND>
 __global__ void prep_sorted_kernel(const typename Traits<KIND>::Raw* __restrict__ dets, const int32_t* __restrict__ labels,
                                    const int* __restrict__ idx, int n_max, const int* __restrict__ n_dev,
-                                   typename Traits<KIND>::Box* __restrict__ boxes, int32_t* __restrict__ label_sorted) {
+                                   typename Traits<KIND>::Box* __restrict__ boxes, int32_t* __restrict__ label_sorted,
+                                   int* __restrict__ hdr, int* __restrict__ starts_unsorted) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_max) return;
     int n = n_dev ? min(*n_dev, n_max) : n_max;
     if (p >= n) return;
     int src = idx[p];
     boxes[p] = Traits<KIND>::prep(dets + (size_t)src * Traits<KIND>::kRow);
-    if (labels) label_sorted[p] = labels[src];
+    bool boundary = p == 0;
+    if (labels) {
+        int l = labels[src];
+        label_sorted[p] = l;
+        if (p > 0) boundary = labels[idx[p - 1]] != l;
+    }
+    if (boundary) {  // collect segment starts (unordered); segment_table_kernel sorts them
+        int k = atomicAdd(&hdr[3], 1);
+        if (k < kFastSegs) starts_unsorted[k] = p;
+    }
 }
 
 // exclusive scan of one long long per thread across a 1024-thread CTA; returns the CTA total via *total
@@ -177,20 +200,45 @@ __device__ long long block_excl_scan(long long v, long long* s_warp, long long* 
 
 __global__ void __launch_bounds__(1024)
 segment_table_kernel(const int32_t* __restrict__ label_sorted, int n_max, const int* __restrict__ n_dev, double thr,
-                     const double* __restrict__ thr_per_label, int num_thr, SegTable tb) {
+                     const double* __restrict__ thr_per_label, int num_thr, SegTable tb,
+                     const int* __restrict__ starts_unsorted) {
     __shared__ long long s_warp[32];
+    __shared__ int s_sort[kFastSegs];
     const int tid = threadIdx.x;
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
-    const int chunk = ceil_div(n > 0 ? n : 1, 1024);
-    const int p0 = min(n, tid * chunk), p1 = min(n, p0 + chunk);
-    int cnt = 0;
-    for (int p = p0; p < p1; p++)
-        cnt += (p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1]);
-    long long total;
-    int off = (int)block_excl_scan(cnt, s_warp, &total);
-    const int nseg = (int)total;
-    for (int p = p0; p < p1; p++)
-        if ((p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1])) tb.seg_start[off++] = p;
+    int nseg;
+    const int nb = tb.hdr[3];  // boundaries found by prep_sorted_kernel
+    if (nb <= kFastSegs) {
+        // few segments (the normal case: classes): sort the collected starts in shared memory
+        for (int i = tid; i < kFastSegs; i += 1024) s_sort[i] = i < nb ? starts_unsorted[i] : 0x7fffffff;
+        __syncthreads();
+        for (int k = 2; k <= kFastSegs; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < kFastSegs; i += 1024) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        int a = s_sort[i], b = s_sort[ixj];
+                        bool up = (i & k) == 0;
+                        if ((a > b) == up) { s_sort[i] = b; s_sort[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        nseg = nb;
+        for (int i = tid; i < nb; i += 1024) tb.seg_start[i] = s_sort[i];
+    } else {
+        // many segments: ordered compaction by a chunked scan over the sorted labels
+        const int chunk = ceil_div(n > 0 ? n : 1, 1024);
+        const int p0 = min(n, tid * chunk), p1 = min(n, p0 + chunk);
+        int cnt = 0;
+        for (int p = p0; p < p1; p++)
+            cnt += (p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1]);
+        long long total;
+        int off = (int)block_excl_scan(cnt, s_warp, &total);
+        nseg = (int)total;
+        for (int p = p0; p < p1; p++)
+            if ((p == 0) || (label_sorted && label_sorted[p] != label_sorted[p - 1])) tb.seg_start[off++] = p;
+    }
     if (tid == 0) tb.seg_start[nseg] = n;
     __syncthreads();
     long long carry_t = 0, carry_w = 0;
@@ -277,17 +325,25 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
         if (tid == 0) s_count = 0;
         __syncthreads();
 
+        // phase 1: each thread owns ONE column box (registers) and sweeps 32 rows; a warp reads the same
+        // row box at a time (shared-memory broadcast), so the filter runs without bank conflicts.
         const bool diag = rb == cb;
-        for (int p = tid; p < 64 * 64; p += kNmsThreads) {
-            int r = p >> 6, c = p & 63;
-            bool cand = r < nr && c < nc && (!diag || c > r);
-            if (cand) cand = Tr::candidate(s_row[r], s_col[c]);
-            unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+        {
+            const int c = tid & 63, rhalf = tid >> 6;
+            Box colbox;
+            if (c < nc) colbox = s_col[c];
+#pragma unroll 2
+            for (int k = 0; k < 32; k++) {
+                const int r = 2 * k + rhalf;
+                bool cand = r < nr && c < nc && (!diag || c > r);
+                if (cand) cand = Tr::candidate(s_row[r], colbox, thr);
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 6) | c);
+                }
             }
         }
         __syncthreads();
@@ -304,10 +360,16 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
 }
 
 // ----------------------------------------------------------------------------- greedy scan
-__global__ void __launch_bounds__(kReduceThreads)
+// One CTA per segment walks its 64-row blocks in score order.  Per block: (1) thread 0 resolves the 64
+// rows against the already-accumulated `remv` word and the block's diagonal words (all 64 words are
+// pulled into registers first, so the dependent chain is pure ALU); (2) all 256 threads OR the
+// suppression words of the KEPT rows into the shared-memory `remv` vector (64 column lanes x 4 row
+// groups, merged with shared-memory atomics).  The next block's diagonal words are prefetched while (1)
+// and (2) run.
+__global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted) {
     extern __shared__ unsigned long long s_remv[];
-    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_diag[2][64];
     __shared__ unsigned long long s_keep;
     const int tid = threadIdx.x;
     const int nseg = tb.hdr[0];
@@ -318,35 +380,45 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
         const unsigned long long* m = mask + tb.mask_off[s];
         __syncthreads();
         for (int j = tid; j < T; j += kReduceThreads) s_remv[j] = 0ull;
+        if (tid < 64) s_diag[0][tid] = tid < min(64, ns) ? m[(long long)tid * T] : 0ull;
         __syncthreads();
         for (int b = 0; b < T; b++) {
             const int nr = min(64, ns - b * 64);
-            if (tid < 64) s_diag[tid] = tid < nr ? m[(long long)(b * 64 + tid) * T + b] : 0ull;
-            __syncthreads();
+            unsigned long long diag_next = 0ull;
+            if (tid >= 64 && tid < 128 && b + 1 < T) {  // warp 2/3 prefetch the next diagonal
+                const int i = tid - 64;
+                if (i < min(64, ns - (b + 1) * 64)) diag_next = m[(long long)((b + 1) * 64 + i) * T + (b + 1)];
+            }
             if (tid == 0) {
                 unsigned long long d[64];
 #pragma unroll
-                for (int i = 0; i < 64; i++) d[i] = s_diag[i];
+                for (int i = 0; i < 64; i++) d[i] = s_diag[b & 1][i];
                 unsigned long long r = s_remv[b], kb = 0ull;
-                if (nr < 64) r |= ~0ull << nr;  // rows past the segment end are "removed"
+                if (nr < 64) r |= ~0ull << nr;  // rows past the segment end count as removed
 #pragma unroll
                 for (int i = 0; i < 64; i++) {
-                    bool alive = !((r >> i) & 1ull);
-                    if (alive) { kb |= 1ull << i; r |= d[i]; }
+                    const bool alive = ((r >> i) & 1ull) == 0ull;
+                    kb |= alive ? (1ull << i) : 0ull;
+                    r |= alive ? d[i] : 0ull;
                 }
                 s_keep = kb;
             }
             __syncthreads();
             const unsigned long long kb = s_keep;
             if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            if (tid >= 64 && tid < 128) s_diag[(b + 1) & 1][tid - 64] = diag_next;
             if (kb) {
-                for (int j = b + 1 + tid; j < T; j += kReduceThreads) {
-                    unsigned long long acc = 0ull;
-                    const unsigned long long* col = m + (long long)(b * 64) * T + j;
-#pragma unroll 8
-                    for (int i = 0; i < 64; i++)
-                        if ((kb >> i) & 1ull) acc |= col[(long long)i * T];
-                    s_remv[j] |= acc;
+                const int jj = tid & 63, rg = tid >> 6;
+                const unsigned kb16 = (unsigned)((kb >> (rg * 16)) & 0xffffull);
+                if (kb16) {
+                    for (int j = b + 1 + jj; j < T; j += 64) {
+                        unsigned long long acc = 0ull;
+                        const unsigned long long* col = m + (long long)(b * 64 + rg * 16) * T + j;
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if ((kb16 >> i) & 1u) acc |= col[(long long)i * T];
+                        if (acc) atomicOr(&s_remv[j], acc);
+                    }
                 }
             }
             __syncthreads();
@@ -387,6 +459,7 @@ struct NmsArgs {
     int64_t* keep_sorted_idx;
     int64_t* keep_score_idx;
     int32_t* num_keep;
+    int label_bits = 32;
 };
 
 static size_t box_bytes(int kind) {
@@ -410,18 +483,19 @@ size_t nms_ws_bytes(int kind, int n) {
     b += ws_bytes<unsigned long long>(N * ((N + 63) / 64));            // mask (worst case: one segment)
     b += 3 * ws_bytes<uint8_t>(N);                                     // keep_sorted, keep_mask tmp, flags
     b += 2 * ws_bytes<int64_t>(N);                                     // vals, scratch index output
-    b += ws_bytes<int>(64);                                            // scratch count
+    b += ws_bytes<int>(64) + ws_bytes<int>(kFastSegs);                 // scratch count, unordered segment starts
     b += align256(kCubTempBytes + 16 * N);
     return b;
 }
 
 template <int KIND>
 static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
-                        unsigned long long* mask, cudaStream_t st, bool mask_phase) {
+                        unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted) {
     using Tr = Traits<KIND>;
     if (!mask_phase) {
         prep_sorted_kernel<KIND><<<ceil_div(a.n_max, 256), 256, 0, st>>>((const typename Tr::Raw*)a.dets, a.labels, idx, a.n_max,
-                                                                        a.n_dev, (typename Tr::Box*)boxes, label_sorted);
+                                                                        a.n_dev, (typename Tr::Box*)boxes, label_sorted,
+                                                                        tb.hdr, starts_unsorted);
     } else {
         long long T = (a.n_max + 63) / 64;
         long long tiles = T * (T + 1) / 2;
@@ -432,13 +506,13 @@ static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* 
 }
 
 static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
-                          unsigned long long* mask, cudaStream_t st, bool mask_phase) {
+                          unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted) {
     switch (a.kind) {
-        case RSDET_NMS_ROTATED: launch_kind<RSDET_NMS_ROTATED>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
-        case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
-        case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
-        case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
-        default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase); break;
+        case RSDET_NMS_ROTATED: launch_kind<RSDET_NMS_ROTATED>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
     }
 }
 
@@ -479,6 +553,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     int64_t* vals = ws.take<int64_t>(N);
     int64_t* idx_scratch = ws.take<int64_t>(N);
     int* cnt_scratch = ws.take<int>(64);
+    int* starts_unsorted = ws.take<int>(kFastSegs);
     size_t cub_bytes = kCubTempBytes + 16 * N;
     void* cub_tmp = ws.take<char>(cub_bytes);
     if (!ws.ok()) return RSDET_EWORKSPACE;
@@ -510,23 +585,26 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     // 2. stable sort by label -> segments
     const int* idx_ls = idx_score;
     if (a.labels) {
-        label_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.labels, idx_score, n, a.n_dev, lkA);
+        const int lbits = a.label_bits >= 1 && a.label_bits < 32 ? a.label_bits : 32;
+        label_keys_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a.labels, idx_score, n, a.n_dev, lbits, lkA);
         cudaMemcpyAsync(idxC, idx_score, sizeof(int) * N, cudaMemcpyDeviceToDevice, st);
         cub::DoubleBuffer<uint32_t> dk(lkA, lkB);
         cub::DoubleBuffer<int> dv(idxC, idxD);
         size_t need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, lbits, st);
         if (need > cub_bytes) return RSDET_EWORKSPACE;
-        cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, lbits, st);
         idx_ls = dv.Current();
         count_launch(5);
     }
     // 3. per-box preprocessing in sorted order, segment table
-    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, false);
-    segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr, tb);
+    cudaMemsetAsync(tb.hdr, 0, 64 * sizeof(int), st);
+    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, false, starts_unsorted);
+    segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr, tb,
+                                             starts_unsorted);
     count_launch();
     // 4. suppression mask over the upper-triangular tiles of every segment
-    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true);
+    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true, starts_unsorted);
     // 5. greedy scan
     {
         size_t smem = sizeof(unsigned long long) * ((N + 63) / 64);
@@ -674,6 +752,8 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
                                                         score_factors, cbox, cscore, clabel, n_valid);
     count_launch();
     NmsArgs a{RSDET_NMS_ROTATED, cbox, cscore, clabel, cap, n_valid, (double)iou_thr, nullptr, 0, nullptr, nullptr, kidx, nkeep};
+    a.label_bits = 1;
+    while ((1 << a.label_bits) - 1 < num_classes) a.label_bits++;  // classes 0..C-1, dead rows -> all ones
     int rc = nms_run(a, sub, sub_bytes, st);
     if (rc != RSDET_OK) return rc;
     mc_output_kernel<<<ceil_div(cap, 256), 256, 0, st>>>(kidx, nkeep, max_num, cbox, cscore, clabel, out_dets, out_labels,

@@ -215,25 +215,87 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 //   stage  : [4][nbins][Q+1] floats   (k = channel within quad, Q = quads per CTA chunk)
 __host__ __device__ inline int quads_per_chunk(int C) { return (C / 4) < 64 ? (C / 4) : 64; }
 
+// ---------------------------------------------------------------------------------- processing order
+// RoIs are independent, so the ORDER in which CTAs take them is free.  A one-CTA counting sort buckets
+// them by (level, 128-pixel image cell): CTAs that run at the same time then read the same few MB of
+// one feature level, which keeps the gather inside L2 (the 200 MB output stream would otherwise push
+// the 89 MB pyramid out between re-reads).  Output positions are untouched (roi index = output row).
+constexpr int kCellShift = 7;   // 128-pixel cells in image coordinates
+constexpr int kCellsPerAxis = 16;
+constexpr int kBuckets = RSDET_MAX_LEVELS * kCellsPerAxis * kCellsPerAxis;
+
+__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, int K, int* __restrict__ order,
+                                                         int32_t* __restrict__ levels_out) {
+    __shared__ int s_hist[kBuckets];
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBuckets; i += 1024) s_hist[i] = 0;
+    __syncthreads();
+    auto bucket_of = [&](int i, int& lvl) {
+        const float* r = rois + (size_t)i * 6;
+        RoiGeom g = roi_geometry(r, L);
+        lvl = g.level;
+        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
+        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
+        // boustrophedon rows: neighbouring buckets are neighbouring cells
+        if (cy & 1) cx = kCellsPerAxis - 1 - cx;
+        return (g.level * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+    };
+    for (int i = tid; i < K; i += 1024) {
+        int lvl;
+        int bkt = bucket_of(i, lvl);
+        if (levels_out) levels_out[i] = lvl;
+        atomicAdd(&s_hist[bkt], 1);
+    }
+    __syncthreads();
+    // exclusive scan of kBuckets (=2048) counters: 2 per thread
+    int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1];
+    int sum = a0 + a1, x = sum;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    int excl = (w ? s_warp[w - 1] : 0) + x - sum;
+    s_hist[2 * tid] = excl;
+    s_hist[2 * tid + 1] = excl + a0;
+    __syncthreads();
+    for (int i = tid; i < K; i += 1024) {
+        int lvl;
+        int bkt = bucket_of(i, lvl);
+        order[atomicAdd(&s_hist[bkt], 1)] = i;
+    }
+}
+
 // ---------------------------------------------------------------------------------- forward (fast)
+// QPT = channel quads per thread (2 when the CTA covers 256 channels: the tap record is read once per 8
+// channels instead of once per 4).
+template <int QPT>
 __global__ void __launch_bounds__(kRoiThreads)
-roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
+roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K, float* __restrict__ out,
+                     int32_t* __restrict__ levels_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int roi = blockIdx.x;
+    const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x;
     const int nbins = L.PH * L.PW;
     const int spb = L.sampling_ratio * L.sampling_ratio;  // samples per bin (fast path: fixed grid)
     const int nsamp = nbins * spb;
-    const int Q = quads_per_chunk(L.C);
+    const int C = L.C;
+    const int Q = quads_per_chunk(C);
     const int chunk0 = blockIdx.y * Q * 4;                 // first channel of this chunk
-    const int Qc = min(Q, (L.C - chunk0) / 4);             // quads in this chunk
+    const int Qc = min(Q, (C - chunk0) / 4);               // quads in this chunk
     Taps* s_taps = reinterpret_cast<Taps*>(smem_raw);
     float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(Taps) * nsamp);
     __shared__ RoiGeom s_g;
 
     if (tid == 0) {
         s_g = roi_geometry(rois + (size_t)roi * 6, L);
-        if (levels_out && blockIdx.y == 0) levels_out[roi] = s_g.level;
+        if (levels_out && !order && blockIdx.y == 0) levels_out[roi] = s_g.level;
     }
     __syncthreads();
     const RoiGeom g = s_g;
@@ -243,57 +305,61 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, int K, float* _
         int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
         float x, y;
         sample_xy(g, L.version, ph, pw, iy, ix, x, y);
-        s_taps[s] = make_taps(H, W, y, x);
+        Taps t = make_taps(H, W, y, x);
+        t.o[0] *= C; t.o[1] *= C; t.o[2] *= C; t.o[3] *= C;  // element offsets of the pixel rows
+        s_taps[s] = t;
     }
     __syncthreads();
 
-    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * L.C + chunk0;
-    const int C = L.C;
-    const int groups = kRoiThreads / Qc;
-    const int cq = tid % Qc, grp = tid / Qc;
+    const int lanes = Qc / QPT;                            // threads per bin group
+    const int groups = kRoiThreads / lanes;
+    const int cq = tid % lanes, grp = tid / lanes;
+    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + cq * 4;
     const float count = (float)max(spb, 1);
     const int SQ = Q + 1;
     if (grp < groups) {
         for (int b = grp; b < nbins; b += groups) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 acc[QPT];
+#pragma unroll
+            for (int u = 0; u < QPT; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int q = 0; q < spb; q++) {
                 const Taps t = s_taps[b * spb + q];
-                float4 v0 = ldg_nc_v4(feat + (size_t)t.o[0] * C + cq * 4);
-                float4 v1 = ldg_nc_v4(feat + (size_t)t.o[1] * C + cq * 4);
-                float4 v2 = ldg_nc_v4(feat + (size_t)t.o[2] * C + cq * 4);
-                float4 v3 = ldg_nc_v4(feat + (size_t)t.o[3] * C + cq * 4);
+                float4 v[QPT][4];
+#pragma unroll
+                for (int u = 0; u < QPT; u++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[u][k] = ldg_nc_v4(feat + t.o[k] + u * lanes * 4);
                 // val = w1*lt + w2*rt + w3*lb + w4*rb ; output_val += val   (:63-65, :138-140)
-                acc.x += t.w[0] * v0.x + t.w[1] * v1.x + t.w[2] * v2.x + t.w[3] * v3.x;
-                acc.y += t.w[0] * v0.y + t.w[1] * v1.y + t.w[2] * v2.y + t.w[3] * v3.y;
-                acc.z += t.w[0] * v0.z + t.w[1] * v1.z + t.w[2] * v2.z + t.w[3] * v3.z;
-                acc.w += t.w[0] * v0.w + t.w[1] * v1.w + t.w[2] * v2.w + t.w[3] * v3.w;
+#pragma unroll
+                for (int u = 0; u < QPT; u++) {
+                    acc[u].x += t.w[0] * v[u][0].x + t.w[1] * v[u][1].x + t.w[2] * v[u][2].x + t.w[3] * v[u][3].x;
+                    acc[u].y += t.w[0] * v[u][0].y + t.w[1] * v[u][1].y + t.w[2] * v[u][2].y + t.w[3] * v[u][3].y;
+                    acc[u].z += t.w[0] * v[u][0].z + t.w[1] * v[u][1].z + t.w[2] * v[u][2].z + t.w[3] * v[u][3].z;
+                    acc[u].w += t.w[0] * v[u][0].w + t.w[1] * v[u][1].w + t.w[2] * v[u][2].w + t.w[3] * v[u][3].w;
+                }
             }
-            s_stage[(0 * nbins + b) * SQ + cq] = acc.x / count;
-            s_stage[(1 * nbins + b) * SQ + cq] = acc.y / count;
-            s_stage[(2 * nbins + b) * SQ + cq] = acc.z / count;
-            s_stage[(3 * nbins + b) * SQ + cq] = acc.w / count;
+#pragma unroll
+            for (int u = 0; u < QPT; u++) {
+                const int qd = cq + u * lanes;
+                s_stage[(0 * nbins + b) * SQ + qd] = acc[u].x / count;
+                s_stage[(1 * nbins + b) * SQ + qd] = acc[u].y / count;
+                s_stage[(2 * nbins + b) * SQ + qd] = acc[u].z / count;
+                s_stage[(3 * nbins + b) * SQ + qd] = acc[u].w / count;
+            }
         }
     }
     __syncthreads();
-    // coalesced write-out of this chunk's (Qc*4, nbins) block; element e = c_local*nbins + b
+    // coalesced write-out of this chunk's (Qc*4, nbins) block: element e = c_local*nbins + b.  (c, b) are
+    // advanced incrementally (no div/mod); consecutive lanes read consecutive b -> stride SQ (odd) in shared
+    // memory, conflict-free, and store 128 contiguous bytes per warp with a streaming hint.
     float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;
     const int total = Qc * 4 * nbins;
-    if (((((size_t)roi * C + chunk0) * nbins) & 3) == 0 && (total & 3) == 0) {
-        for (int e4 = tid; e4 < total / 4; e4 += kRoiThreads) {
-            float v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int e = e4 * 4 + k;
-                int c = e / nbins, b = e - c * nbins;
-                v[k] = s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)];
-            }
-            stg_cs_v4(dst + (size_t)e4 * 4, make_float4(v[0], v[1], v[2], v[3]));
-        }
-    } else {
-        for (int e = tid; e < total; e += kRoiThreads) {
-            int c = e / nbins, b = e - c * nbins;
-            dst[e] = s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)];
-        }
+    const int dc = kRoiThreads / nbins, db = kRoiThreads % nbins;
+    int c = tid / nbins, b = tid % nbins;
+    for (int e = tid; e < total; e += kRoiThreads) {
+        __stcs(dst + e, s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)]);
+        c += dc; b += db;
+        if (b >= nbins) { b -= nbins; c++; }
     }
 }
 
@@ -421,6 +487,8 @@ __global__ void roi_align_generic_kernel(LevelSet L, GenericMaps M, const float*
 }
 
 static bool fast_path_ok(const rsdet_roi_align_cfg* c) {
+    for (int l = 0; l < c->num_levels; l++)  // tap offsets are 32-bit element offsets inside one image
+        if ((long long)c->height[l] * c->width[l] * c->channels >= (1ll << 31)) return false;
     return c->channels % 4 == 0 && c->sampling_ratio > 0 &&
            c->pooled_h * c->pooled_w * c->sampling_ratio * c->sampling_ratio <= kMaxSamples;
 }
@@ -460,10 +528,10 @@ static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
 using namespace rsdet;
 
 extern "C" size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward) {
-    (void)num_rois; (void)backward;
+    (void)backward;
     if (check_cfg(cfg) != RSDET_OK) return 0;
-    if (cfg->channels_last || !fast_path_ok(cfg)) return 256;
-    size_t b = 0;
+    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1);  // processing order
+    if (cfg->channels_last || !fast_path_ok(cfg)) return b + 256;
     for (int l = 0; l < cfg->num_levels; l++)
         b += ws_bytes<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
     return b + 256;
@@ -491,11 +559,12 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         count_launch();
         return cuda_status();
     }
+    if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 0)) return RSDET_EWORKSPACE;
+    Workspace ws(workspace, workspace_bytes);
+    int* order_ws = ws.take<int>(num_rois);
     if (cfg->channels_last) {
         for (int l = 0; l < cfg->num_levels; l++) L.feat[l] = feats_host[l];
     } else {
-        if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 0)) return RSDET_EWORKSPACE;
-        Workspace ws(workspace, workspace_bytes);
         float* dst[RSDET_MAX_LEVELS];
         for (int l = 0; l < cfg->num_levels; l++) {
             dst[l] = ws.take<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
@@ -508,12 +577,23 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     size_t smem = fast_smem_bytes(cfg);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
+    }
+    // locality order (needs the int[K] slot at the end of the workspace; skipped for tiny calls)
+    int* order = nullptr;
+    if (num_rois >= 256 && order_ws) {
+        order = order_ws;
+        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, levels_out);
+        count_launch();
     }
     int Q = quads_per_chunk(cfg->channels);
     dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
-    roi_align_fwd_kernel<<<grid, kRoiThreads, smem, st>>>(L, rois, num_rois, out, levels_out);
+    if (cfg->channels % 256 == 0)
+        roi_align_fwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, out, levels_out);
+    else
+        roi_align_fwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, out, levels_out);
     count_launch();
     return cuda_status();
 }

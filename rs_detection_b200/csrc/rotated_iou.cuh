@@ -33,6 +33,8 @@ struct __align__(16) RBox {
     float ch, sw;  // (cos/2)*h, (sin/2)*w
     float area;    // w*h
     float r;       // inflated circumradius; negative => degenerate box (area < 1e-14): IoU is 0
+    float ax, ay;  // unit vector of the width axis (cos, +-sin) -- filters only, never the exact path
+    float hw, hh;  // |w|/2, |h|/2                             -- filters only
 };
 
 // get_rotated_vertices' per-box part: box_iou_rotated.py:52-62 / box_iou_rotated_v1.py:52-62.
@@ -56,7 +58,50 @@ __device__ __forceinline__ RBox prep_rbox(const float* __restrict__ b, int versi
     float rr = 0.5f * sqrtf(w * w + h * h);
     rr = rr * 1.0001f + 1e-4f;
     o.r = ((double)o.area < 1e-14) ? -1e30f : rr;
+    o.ax = 2.f * c2;
+    o.ay = version == 1 ? -2.f * s2 : 2.f * s2;
+    o.hw = 0.5f * fabsf(w);
+    o.hh = 0.5f * fabsf(h);
     return o;
+}
+
+// Conservative geometric bounds used to skip the exact clipper.  In the frame of box A, box B is
+// enclosed by an axis-aligned box of half extents (ex, ey); the overlap of that box with A bounds the
+// true intersection from above.  `slack` (a small length) absorbs the float error of the filter itself.
+//   returns an UPPER bound of the intersection area, <= 0 when the boxes are certainly disjoint.
+__device__ __forceinline__ float rbox_inter_upper_bound(const RBox& a, const RBox& b) {
+    const float dx = b.x - a.x, dy = b.y - a.y;
+    const float cosd = fabsf(a.ax * b.ax + a.ay * b.ay);
+    const float sind = fabsf(a.ax * b.ay - a.ay * b.ax);
+    const float slack = 1e-3f * (a.r + b.r);
+    float ub = fminf(a.area, b.area);
+    {   // frame of A
+        float px = dx * a.ax + dy * a.ay, py = dy * a.ax - dx * a.ay;
+        float ex = b.hw * cosd + b.hh * sind + slack, ey = b.hw * sind + b.hh * cosd + slack;
+        float ox = fminf(a.hw, px + ex) - fmaxf(-a.hw, px - ex);
+        float oy = fminf(a.hh, py + ey) - fmaxf(-a.hh, py - ey);
+        if (ox <= 0.f || oy <= 0.f) return 0.f;
+        ub = fminf(ub, ox * oy);
+    }
+    {   // frame of B
+        float px = -(dx * b.ax + dy * b.ay), py = -(dy * b.ax - dx * b.ay);
+        float ex = a.hw * cosd + a.hh * sind + slack, ey = a.hw * sind + a.hh * cosd + slack;
+        float ox = fminf(b.hw, px + ex) - fmaxf(-b.hw, px - ex);
+        float oy = fminf(b.hh, py + ey) - fmaxf(-b.hh, py - ey);
+        if (ox <= 0.f || oy <= 0.f) return 0.f;
+        ub = fminf(ub, ox * oy);
+    }
+    return ub;
+}
+
+// true when IoU(a,b) certainly stays below `thr` (with a 1e-4 guard band, two orders of magnitude above
+// the float error of the reference's IoU): the pair cannot suppress, whatever the clipper would return.
+__device__ __forceinline__ bool rbox_iou_below(const RBox& a, const RBox& b, float thr) {
+    float ub = rbox_inter_upper_bound(a, b);
+    if (ub <= 0.f) return true;
+    ub *= 1.001f;
+    float un = a.area + b.area - ub;
+    return ub < (thr - 1e-4f) * un;
 }
 
 __device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - bx * ay; }
