@@ -499,7 +499,7 @@ static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* 
     } else {
         long long T = (a.n_max + 63) / 64;
         long long tiles = T * (T + 1) / 2;
-        int grid = (int)(tiles < (long long)kNumSMs * 4 ? tiles : (long long)kNumSMs * 4);
+        int grid = (int)(tiles < (long long)kNumSMs * 5 ? tiles : (long long)kNumSMs * 5);  // 5 CTAs/SM fit (39 KB smem, 91 regs)
         mask_tiles_kernel<KIND><<<grid, kNmsThreads, 0, st>>>((const typename Tr::Box*)boxes, tb, mask);
     }
     count_launch();
