@@ -25,6 +25,8 @@
 //
 // Sample coordinates are computed with explicitly un-contracted IEEE operations in the reference's
 // order: the validity test `y < -1 || y > H` is discontinuous, so coordinates must not drift.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rsdet {
@@ -193,6 +195,12 @@ __device__ __forceinline__ Taps make_taps(int H, int W, float y, float x) {
     return t;
 }
 
+// base + off*16 as ONE mad.wide.u32 (the compiler otherwise builds the 64-bit address in 4 instructions)
+__device__ __forceinline__ const float* tap_ptr(const float4* base, unsigned off16) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(off16), "l"((unsigned long long)base));
+    return reinterpret_cast<const float*>(a);
+}
 __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
@@ -273,10 +281,15 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
 }
 
 // ---------------------------------------------------------------------------------- forward (fast)
-// QPT = channel quads per thread (2 when the CTA covers 256 channels: the tap record is read once per 8
-// channels instead of once per 4).
+// One CTA per (RoI, chunk of up to 64 channel quads).  Measured on B200 (profiles/README.md): the kernel
+// is bound by L1 load wavefronts -- every bilinear tap is a 512-byte warp load and a RoI issues 784 of
+// them per 128 channels, ~9x its own output -- not by HBM.  So the sampling grid is not only computed
+// once per RoI (phase A1) but also MERGED per bin (phase A2): taps of the bin's samples that land on the
+// same pixel are summed into one (offset, weight) entry and zero-weight taps are dropped; on the
+// benchmark proposals 16 taps collapse to ~9 loads.  Offsets are kept in 16-byte units so that one
+// mad.wide forms each address; with QPT = 2 the second channel quad is an immediate +512 B.
 template <int QPT>
-__global__ void __launch_bounds__(kRoiThreads)
+__global__ void __launch_bounds__(kRoiThreads, 4)
 roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K, float* __restrict__ out,
                      int32_t* __restrict__ levels_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,12 +298,18 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     const int nbins = L.PH * L.PW;
     const int spb = L.sampling_ratio * L.sampling_ratio;  // samples per bin (fast path: fixed grid)
     const int nsamp = nbins * spb;
+    const int cap = 4 * spb;                               // taps per bin before merging
     const int C = L.C;
     const int Q = quads_per_chunk(C);
     const int chunk0 = blockIdx.y * Q * 4;                 // first channel of this chunk
     const int Qc = min(Q, (C - chunk0) / 4);               // quads in this chunk
-    Taps* s_taps = reinterpret_cast<Taps*>(smem_raw);
-    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(Taps) * nsamp);
+    // smem: [merged lists: nbins*cap int2][counts: nbins int, padded][staging [c][bin] | phase-A temporaries]
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    int* s_off = reinterpret_cast<int*>(s_stage);          // [nbins*cap] raw tap offsets (float4 units)
+    float* s_w = s_stage + nbins * cap;                    // [nbins*cap] raw tap weights
+    float* s_wsum = s_stage + 2 * nbins * cap;             // [nbins*cap] merged weight of leaders, 0 otherwise
     __shared__ RoiGeom s_g;
 
     if (tid == 0) {
@@ -300,66 +319,111 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     __syncthreads();
     const RoiGeom g = s_g;
     const int H = L.H[g.level], W = L.W[g.level];
+    const int C4 = C >> 2;
+    // A1: one thread per sample
     for (int s = tid; s < nsamp; s += kRoiThreads) {
         int b = s / spb, q = s % spb;
         int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
         float x, y;
         sample_xy(g, L.version, ph, pw, iy, ix, x, y);
-        Taps t = make_taps(H, W, y, x);
-        t.o[0] *= C; t.o[1] *= C; t.o[2] *= C; t.o[3] *= C;  // element offsets of the pixel rows
-        s_taps[s] = t;
+        const Taps t = make_taps(H, W, y, x);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            s_off[s * 4 + k] = t.o[k] * C4;
+            s_w[s * 4 + k] = t.w[k];
+        }
+    }
+    __syncthreads();
+    // A2a: one thread per tap: a tap is a LEADER if its weight is non-zero and no earlier tap of the bin
+    // hits the same pixel; a leader collects the weights of its later duplicates (fixed order).
+    const int ntaps = nbins * cap;
+    for (int t = tid; t < ntaps; t += kRoiThreads) {
+        const int b = t / cap, j = t - b * cap;
+        const int* ob = s_off + b * cap;
+        const float* wb = s_w + b * cap;
+        const int o = ob[j];
+        float w = wb[j];
+        bool leader = w != 0.f;
+        for (int i = 0; i < j && leader; i++) leader = !(ob[i] == o && wb[i] != 0.f);
+        if (leader)
+            for (int i = j + 1; i < cap; i++)
+                if (ob[i] == o) w += wb[i];
+        s_wsum[t] = leader ? w : 0.f;
+    }
+    __syncthreads();
+    // A2b: compaction (position = number of leaders before me in my bin)
+    for (int t = tid; t < ntaps; t += kRoiThreads) {
+        const int b = t / cap, j = t - b * cap;
+        const float* ws = s_wsum + b * cap;
+        const float w = ws[j];
+        int pos = 0;
+        for (int i = 0; i < j; i++) pos += ws[i] != 0.f;
+        if (w != 0.f) s_list[b * cap + pos] = make_int2(s_off[t], __float_as_int(w));
+        if (j == cap - 1) s_cnt[b] = pos + (w != 0.f);
     }
     __syncthreads();
 
-    const int lanes = Qc / QPT;                            // threads per bin group
+    const int lanes = QPT == 2 ? 32 : Qc;                  // threads per bin group
     const int groups = kRoiThreads / lanes;
     const int cq = tid % lanes, grp = tid / lanes;
-    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + cq * 4;
-    const float count = (float)max(spb, 1);
-    const int SQ = Q + 1;
+    const float4* __restrict__ feat =
+        reinterpret_cast<const float4*>(L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0) + cq;
+    const bool pow2 = (spb & (spb - 1)) == 0;
+    const float count = (float)max(spb, 1), inv_count = 1.f / count;
     if (grp < groups) {
         for (int b = grp; b < nbins; b += groups) {
             float4 acc[QPT];
 #pragma unroll
             for (int u = 0; u < QPT; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < spb; q++) {
-                const Taps t = s_taps[b * spb + q];
+            const int2* lp = s_list + b * cap;
+            const int cnt = s_cnt[b];
+            for (int e = 0; e < cnt; e += 4) {
+                int2 en[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) en[k] = lp[min(e + k, cnt - 1)];  // warp-uniform broadcast reads
                 float4 v[QPT][4];
 #pragma unroll
-                for (int u = 0; u < QPT; u++)
+                for (int k = 0; k < 4; k++)
+                    if (e + k < cnt) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) v[u][k] = ldg_nc_v4(feat + t.o[k] + u * lanes * 4);
-                // val = w1*lt + w2*rt + w3*lb + w4*rb ; output_val += val   (:63-65, :138-140)
+                        for (int u = 0; u < QPT; u++) v[u][k] = ldg_nc_v4(tap_ptr(feat, (unsigned)en[k].x) + u * 128);
+                    }
 #pragma unroll
-                for (int u = 0; u < QPT; u++) {
-                    acc[u].x += t.w[0] * v[u][0].x + t.w[1] * v[u][1].x + t.w[2] * v[u][2].x + t.w[3] * v[u][3].x;
-                    acc[u].y += t.w[0] * v[u][0].y + t.w[1] * v[u][1].y + t.w[2] * v[u][2].y + t.w[3] * v[u][3].y;
-                    acc[u].z += t.w[0] * v[u][0].z + t.w[1] * v[u][1].z + t.w[2] * v[u][2].z + t.w[3] * v[u][3].z;
-                    acc[u].w += t.w[0] * v[u][0].w + t.w[1] * v[u][1].w + t.w[2] * v[u][2].w + t.w[3] * v[u][3].w;
-                }
+                for (int k = 0; k < 4; k++)
+                    if (e + k < cnt) {
+                        const float wt = __int_as_float(en[k].y);
+#pragma unroll
+                        for (int u = 0; u < QPT; u++) {
+                            acc[u].x = fmaf(wt, v[u][k].x, acc[u].x);
+                            acc[u].y = fmaf(wt, v[u][k].y, acc[u].y);
+                            acc[u].z = fmaf(wt, v[u][k].z, acc[u].z);
+                            acc[u].w = fmaf(wt, v[u][k].w, acc[u].w);
+                        }
+                    }
             }
+            // phase-A temporaries (aliasing the staging area) died at the barrier above
 #pragma unroll
             for (int u = 0; u < QPT; u++) {
-                const int qd = cq + u * lanes;
-                s_stage[(0 * nbins + b) * SQ + qd] = acc[u].x / count;
-                s_stage[(1 * nbins + b) * SQ + qd] = acc[u].y / count;
-                s_stage[(2 * nbins + b) * SQ + qd] = acc[u].z / count;
-                s_stage[(3 * nbins + b) * SQ + qd] = acc[u].w / count;
+                // output_val /= count (:143); a power-of-two count makes the reciprocal multiply exact
+                if (pow2) { acc[u].x *= inv_count; acc[u].y *= inv_count; acc[u].z *= inv_count; acc[u].w *= inv_count; }
+                else { acc[u].x /= count; acc[u].y /= count; acc[u].z /= count; acc[u].w /= count; }
+                const int c0 = (cq + u * 32) * 4;
+                s_stage[(c0 + 0) * nbins + b] = acc[u].x;
+                s_stage[(c0 + 1) * nbins + b] = acc[u].y;
+                s_stage[(c0 + 2) * nbins + b] = acc[u].z;
+                s_stage[(c0 + 3) * nbins + b] = acc[u].w;
             }
         }
     }
     __syncthreads();
-    // coalesced write-out of this chunk's (Qc*4, nbins) block: element e = c_local*nbins + b.  (c, b) are
-    // advanced incrementally (no div/mod); consecutive lanes read consecutive b -> stride SQ (odd) in shared
-    // memory, conflict-free, and store 128 contiguous bytes per warp with a streaming hint.
+    // the staged block IS the output block of this (roi, chunk): straight coalesced copy, streaming stores
     float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;
     const int total = Qc * 4 * nbins;
-    const int dc = kRoiThreads / nbins, db = kRoiThreads % nbins;
-    int c = tid / nbins, b = tid % nbins;
-    for (int e = tid; e < total; e += kRoiThreads) {
-        __stcs(dst + e, s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)]);
-        c += dc; b += db;
-        if (b >= nbins) { b -= nbins; c++; }
+    if ((((size_t)roi * C + chunk0) * nbins & 3) == 0 && (total & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(s_stage);
+        for (int e = tid; e < total / 4; e += kRoiThreads) stg_cs_v4(dst + (size_t)e * 4, s4[e]);
+    } else {
+        for (int e = tid; e < total; e += kRoiThreads) __stcs(dst + e, s_stage[e]);
     }
 }
 
@@ -516,11 +580,18 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
     return L;
 }
 
+static size_t fwd_smem_bytes(const rsdet_roi_align_cfg* c) {
+    size_t nbins = (size_t)c->pooled_h * c->pooled_w;
+    size_t ntaps = nbins * 4 * c->sampling_ratio * c->sampling_ratio;
+    size_t stage = sizeof(float) * 4 * nbins * quads_per_chunk(c->channels), tmp = 12 * ntaps;
+    return 8 * ntaps + ((nbins * 4 + 15) & ~(size_t)15) + (stage > tmp ? stage : tmp);
+}
+
 static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
     int nbins = c->pooled_h * c->pooled_w;
     int nsamp = nbins * c->sampling_ratio * c->sampling_ratio;
     int Q = quads_per_chunk(c->channels);
-    return sizeof(Taps) * (size_t)nsamp + sizeof(float) * 4 * (size_t)nbins * (Q + 1);
+    return sizeof(Taps) * (size_t)nsamp + sizeof(float) * 4 * (size_t)nbins * (Q + 1);  // backward layout is the larger
 }
 
 }  // namespace rsdet
@@ -574,21 +645,21 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st);
         if (rc != RSDET_OK) return rc;
     }
-    size_t smem = fast_smem_bytes(cfg);
+    size_t smem = fwd_smem_bytes(cfg);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         smem_set = smem;
     }
-    // locality order (needs the int[K] slot at the end of the workspace; skipped for tiny calls)
+    // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
     int* order = nullptr;
     if (num_rois >= 256 && order_ws) {
         order = order_ws;
         roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, levels_out);
         count_launch();
     }
-    int Q = quads_per_chunk(cfg->channels);
+    const int Q = quads_per_chunk(cfg->channels);
     dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
     if (cfg->channels % 256 == 0)
         roi_align_fwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, out, levels_out);
