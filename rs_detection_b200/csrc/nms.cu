@@ -160,7 +160,7 @@ __global__ void prep_sorted_kernel(const typename Traits<KIND>::Raw* __restrict_
     int n = n_dev ? min(*n_dev, n_max) : n_max;
     if (p >= n) return;
     int src = idx[p];
-    boxes[p] = Traits<KIND>::prep(dets + (size_t)src * Traits<KIND>::kRow);
+    if (boxes) boxes[p] = Traits<KIND>::prep(dets + (size_t)src * Traits<KIND>::kRow);
     bool boundary = p == 0;
     if (labels) {
         int l = labels[src];
@@ -426,6 +426,164 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
     }
 }
 
+// ----------------------------------------------------------------------------- shared-box mode
+// multiclass_nms_rotated with class-agnostic boxes (multi_bboxes is (n,5): every class scores the SAME n
+// boxes -- `reg_class_agnostic=True` in the orcnn configs, and every single-stage head).  The reference
+// expands to n*C candidates and evaluates IoU per class; but IoU(a,b) does not depend on the class, so
+// the pairwise decisions are computed ONCE per box pair into a directed n x n bit matrix
+// (ov[a][b] = "a, as the higher-scored box, suppresses b") and each class's greedy scan reads it through
+// its own score order.  C x fewer clipper calls (10x on FAIR1M, 15x on DOTA).
+//
+// Orientation: the reference evaluates single_box_iou_rotated(higher, lower) and its float result is not
+// exactly symmetric, and which box is "higher" differs per class.  The canonical evaluation is
+// (lower index, higher index); the reverse orientation is recomputed only when the IoU lies within 1e-5
+// of the threshold, otherwise both directions take the same decision.
+__global__ void prep_shared_kernel(const float* __restrict__ boxes, int n, RBox* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = prep_rbox(boxes + (size_t)i * 5, 0);
+}
+
+template <bool GE>
+__global__ void __launch_bounds__(kNmsThreads)
+ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long long* __restrict__ ov, int* __restrict__ counter) {
+    __shared__ RBox s_row[64];
+    __shared__ RBox s_col[64];
+    __shared__ unsigned short s_queue[64 * 64];
+    __shared__ float2 s_pts[24 * kNmsThreads];
+    __shared__ int s_count;
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int T = (n + 63) >> 6;
+    const int total = T * (T + 1) / 2;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(counter, 1);
+        __syncthreads();
+        const int u = s_tile;
+        if (u >= total) break;
+        int rb = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)u)) * 0.5);
+        rb = max(0, min(rb, T - 1));
+        while (rb > 0 && rb * T - rb * (rb - 1) / 2 > u) rb--;
+        while ((rb + 1) * T - (rb + 1) * rb / 2 <= u) rb++;
+        const int cb = rb + (u - (rb * T - rb * (rb - 1) / 2));
+        const int nr = min(64, n - rb * 64), nc = min(64, n - cb * 64);
+        if (tid < 64) { if (tid < nr) s_row[tid] = boxes[rb * 64 + tid]; }
+        else if (tid - 64 < nc) s_col[tid - 64] = boxes[cb * 64 + tid - 64];
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const bool diag = rb == cb;
+        {
+            const int c = tid & 63, rhalf = tid >> 6;
+            RBox colbox;
+            if (c < nc) colbox = s_col[c];
+#pragma unroll 2
+            for (int k = 0; k < 32; k++) {
+                const int r = 2 * k + rhalf;
+                bool cand = r < nr && c < nc && (!diag || c > r);
+                if (cand) cand = rbox_may_overlap(s_row[r], colbox) && !rbox_iou_below(s_row[r], colbox, thr);
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 6) | c);
+                }
+            }
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int qi = tid; qi < cnt; qi += kNmsThreads) {
+            const int p = s_queue[qi];
+            const int r = p >> 6, c = p & 63;
+            const int a = rb * 64 + r, b = cb * 64 + c;
+            const float iou_ab = rotated_iou_pair<kNmsThreads>(s_row[r], s_col[c], s_pts + tid);
+            const bool d_ab = GE ? iou_ab >= thr : iou_ab > thr;
+            bool d_ba = d_ab;
+            if (fabsf(iou_ab - thr) <= 1e-5f) {
+                const float iou_ba = rotated_iou_pair<kNmsThreads>(s_col[c], s_row[r], s_pts + tid);
+                d_ba = GE ? iou_ba >= thr : iou_ba > thr;
+            }
+            if (d_ab) atomicOr(&ov[(size_t)a * T + (b >> 6)], 1ull << (b & 63));
+            if (d_ba) atomicOr(&ov[(size_t)b * T + (a >> 6)], 1ull << (a & 63));
+        }
+    }
+}
+
+// greedy scan of one class through the shared matrix: `remv` lives in ORIGINAL box-index space (a kept
+// box ORs its whole matrix row; bits that land on already-decided boxes are harmless), the 64x64
+// diagonal block of the class order is gathered bit by bit (256 threads, warp ballots).
+__global__ void __launch_bounds__(kReduceThreads, 1)
+reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov,
+                 int n_boxes, uint8_t* __restrict__ keep_sorted) {
+    extern __shared__ unsigned long long s_remv[];
+    __shared__ int s_box2[2][64];  // double-buffered: the OR phase of block b overlaps the loads of block b+1
+    __shared__ unsigned int s_diag32[128];
+    __shared__ unsigned int s_rem32[2];
+    __shared__ unsigned long long s_keep;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nseg = tb.hdr[0];
+    const int T = (n_boxes + 63) >> 6;
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int st = tb.seg_start[s];
+        const int ns = tb.seg_start[s + 1] - st;
+        const int nblk = (ns + 63) >> 6;
+        __syncthreads();
+        for (int j = tid; j < T; j += kReduceThreads) s_remv[j] = 0ull;
+        for (int b = 0; b < nblk; b++) {
+            const int nr = min(64, ns - b * 64);
+            int* s_box = s_box2[b & 1];
+            if (tid < 64) s_box[tid] = tid < nr ? idx_ls[st + b * 64 + tid] / cand_per_box : -1;
+            __syncthreads();  // also orders the previous block's OR phase before the reads below
+            if (tid < 64) {
+                const int a = s_box[tid];
+                const bool rem = a < 0 || ((s_remv[a >> 6] >> (a & 63)) & 1ull);
+                const unsigned m = __ballot_sync(0xffffffffu, rem);
+                if (lane == 0) s_rem32[tid >> 5] = m;
+            }
+#pragma unroll 4
+            for (int it = 0; it < 16; it++) {
+                const int idx = it * kReduceThreads + tid;
+                const int i = idx >> 6, j = idx & 63;
+                bool bit = false;
+                if (i < nr && j < nr && j > i) {
+                    const int a = s_box[i], c = s_box[j];
+                    bit = (ov[(size_t)a * T + (c >> 6)] >> (c & 63)) & 1ull;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) s_diag32[idx >> 5] = m;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long r = (unsigned long long)s_rem32[0] | ((unsigned long long)s_rem32[1] << 32), kb = 0ull;
+#pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    const bool alive = ((r >> i) & 1ull) == 0ull;
+                    const unsigned long long d = (unsigned long long)s_diag32[2 * i] | ((unsigned long long)s_diag32[2 * i + 1] << 32);
+                    kb |= alive ? (1ull << i) : 0ull;
+                    r |= alive ? d : 0ull;
+                }
+                s_keep = kb;
+            }
+            __syncthreads();
+            const unsigned long long kb = s_keep;
+            if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            if (kb && b + 1 < nblk) {
+                const int jj = tid & 63, rg = tid >> 6;
+                const unsigned kb16 = (unsigned)((kb >> (rg * 16)) & 0xffffull);
+                if (kb16) {
+                    for (int w = jj; w < T; w += 64) {
+                        unsigned long long acc = 0ull;
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if ((kb16 >> i) & 1u) acc |= ov[(size_t)s_box[rg * 16 + i] * T + w];
+                        if (acc) atomicOr(&s_remv[w], acc);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- outputs
 __global__ void scatter_keep_kernel(const uint8_t* __restrict__ keep_sorted, const int* __restrict__ idx, int n_max,
                                     const int* __restrict__ n_dev, uint8_t* __restrict__ keep_mask) {
@@ -460,6 +618,10 @@ struct NmsArgs {
     int64_t* keep_score_idx;
     int32_t* num_keep;
     int label_bits = 32;
+    // shared-box mode (multiclass with class-agnostic boxes): candidate e refers to box e / cand_per_box
+    const float* shared_boxes = nullptr;
+    int n_shared = 0;
+    int cand_per_box = 1;
 };
 
 static size_t box_bytes(int kind) {
@@ -598,11 +760,35 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         count_launch(5);
     }
     // 3. per-box preprocessing in sorted order, segment table
+    const bool shared = a.shared_boxes != nullptr;
+    if (shared && (a.kind > RSDET_NMS_ROTATED_GE || a.n_shared <= 0 || a.n_shared > n)) return RSDET_EINVAL;
     cudaMemsetAsync(tb.hdr, 0, 64 * sizeof(int), st);
-    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, false, starts_unsorted);
+    dispatch_kind(a, idx_ls, shared ? nullptr : boxes, label_sorted, tb, mask, st, false, starts_unsorted);
     segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr, tb,
                                              starts_unsorted);
     count_launch();
+    if (shared) {
+        // 4'. one directed decision matrix for all classes, 5'. per-class scans through it
+        const int nb = a.n_shared, Tov = (nb + 63) / 64;
+        RBox* sb = (RBox*)boxes;
+        prep_shared_kernel<<<ceil_div(nb, 256), 256, 0, st>>>(a.shared_boxes, nb, sb);
+        cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * Tov, st);
+        cudaMemsetAsync(cnt_scratch + 32, 0, sizeof(int), st);
+        long long tiles = (long long)Tov * (Tov + 1) / 2;
+        int grid = (int)(tiles < (long long)kNumSMs * 5 ? tiles : (long long)kNumSMs * 5);
+        if (a.kind == RSDET_NMS_ROTATED_GE)
+            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, cnt_scratch + 32);
+        else
+            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, cnt_scratch + 32);
+        size_t smem = sizeof(unsigned long long) * (size_t)Tov;
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr2 = true;
+        }
+        reduce_ov_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, idx_ls, a.cand_per_box, mask, nb, keep_sorted);
+        count_launch(5);
+    } else {
     // 4. suppression mask over the upper-triangular tiles of every segment
     dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true, starts_unsorted);
     // 5. greedy scan
@@ -615,6 +801,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         }
         reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted);
         count_launch();
+    }
     }
     // 6. outputs
     uint8_t* km = a.keep_mask ? a.keep_mask : keep_tmp;
@@ -754,6 +941,11 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
     NmsArgs a{RSDET_NMS_ROTATED, cbox, cscore, clabel, cap, n_valid, (double)iou_thr, nullptr, 0, nullptr, nullptr, kidx, nkeep};
     a.label_bits = 1;
     while ((1 << a.label_bits) - 1 < num_classes) a.label_bits++;  // classes 0..C-1, dead rows -> all ones
+    if (bbox_dim == 5) {  // class-agnostic boxes: pairwise decisions are shared by all classes
+        a.shared_boxes = multi_bboxes;
+        a.n_shared = n;
+        a.cand_per_box = num_classes;
+    }
     int rc = nms_run(a, sub, sub_bytes, st);
     if (rc != RSDET_OK) return rc;
     mc_output_kernel<<<ceil_div(cap, 256), 256, 0, st>>>(kidx, nkeep, max_num, cbox, cscore, clabel, out_dets, out_labels,
