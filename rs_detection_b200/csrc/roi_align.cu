@@ -280,46 +280,24 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     }
 }
 
-// ---------------------------------------------------------------------------------- forward (fast)
-// One CTA per (RoI, chunk of up to 64 channel quads).  Measured on B200 (profiles/README.md): the kernel
-// is bound by L1 load wavefronts -- every bilinear tap is a 512-byte warp load and a RoI issues 784 of
-// them per 128 channels, ~9x its own output -- not by HBM.  So the sampling grid is not only computed
-// once per RoI (phase A1) but also MERGED per bin (phase A2): taps of the bin's samples that land on the
-// same pixel are summed into one (offset, weight) entry and zero-weight taps are dropped; on the
-// benchmark proposals 16 taps collapse to ~9 loads.  Offsets are kept in 16-byte units so that one
-// mad.wide forms each address; with QPT = 2 the second channel quad is an immediate +512 B.
-template <int QPT>
-__global__ void __launch_bounds__(kRoiThreads, 4)
-roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K, float* __restrict__ out,
-                     int32_t* __restrict__ levels_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int roi = order ? order[blockIdx.x] : blockIdx.x;
+// ---------------------------------------------------------------------------------- tap lists
+// Shared by forward and backward.  Measured on B200 (profiles/README.md): the gather is bound by L2
+// round trips and L1 load wavefronts -- every bilinear tap is a 512-byte warp load and a RoI issues 784
+// of them per 128 channels, ~9x its own output -- not by HBM.  So the sampling grid is computed once per
+// RoI (A1) AND merged per bin (A2): taps of the bin's samples that land on the same pixel are summed
+// into one (offset, weight) entry and zero-weight taps are dropped; on the benchmark proposals 16 taps
+// collapse to ~9.  Offsets are in 16-byte units of the channels-last map (one mad.wide per address).
+//   s_list [nbins*cap] int2 {offset, weight bits}, s_cnt [nbins], tmp: 3*nbins*cap words of scratch.
+__device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet& L, int H, int W, int2* s_list, int* s_cnt,
+                                                float* tmp) {
     const int tid = threadIdx.x;
     const int nbins = L.PH * L.PW;
-    const int spb = L.sampling_ratio * L.sampling_ratio;  // samples per bin (fast path: fixed grid)
-    const int nsamp = nbins * spb;
-    const int cap = 4 * spb;                               // taps per bin before merging
-    const int C = L.C;
-    const int Q = quads_per_chunk(C);
-    const int chunk0 = blockIdx.y * Q * 4;                 // first channel of this chunk
-    const int Qc = min(Q, (C - chunk0) / 4);               // quads in this chunk
-    // smem: [merged lists: nbins*cap int2][counts: nbins int, padded][staging [c][bin] | phase-A temporaries]
-    int2* s_list = reinterpret_cast<int2*>(smem_raw);
-    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
-    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
-    int* s_off = reinterpret_cast<int*>(s_stage);          // [nbins*cap] raw tap offsets (float4 units)
-    float* s_w = s_stage + nbins * cap;                    // [nbins*cap] raw tap weights
-    float* s_wsum = s_stage + 2 * nbins * cap;             // [nbins*cap] merged weight of leaders, 0 otherwise
-    __shared__ RoiGeom s_g;
-
-    if (tid == 0) {
-        s_g = roi_geometry(rois + (size_t)roi * 6, L);
-        if (levels_out && !order && blockIdx.y == 0) levels_out[roi] = s_g.level;
-    }
-    __syncthreads();
-    const RoiGeom g = s_g;
-    const int H = L.H[g.level], W = L.W[g.level];
-    const int C4 = C >> 2;
+    const int spb = L.sampling_ratio * L.sampling_ratio;
+    const int nsamp = nbins * spb, cap = 4 * spb, ntaps = nbins * cap;
+    const int C4 = L.C >> 2;
+    int* s_off = reinterpret_cast<int*>(tmp);
+    float* s_w = tmp + ntaps;
+    float* s_wsum = tmp + 2 * ntaps;
     // A1: one thread per sample
     for (int s = tid; s < nsamp; s += kRoiThreads) {
         int b = s / spb, q = s % spb;
@@ -336,7 +314,6 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     __syncthreads();
     // A2a: one thread per tap: a tap is a LEADER if its weight is non-zero and no earlier tap of the bin
     // hits the same pixel; a leader collects the weights of its later duplicates (fixed order).
-    const int ntaps = nbins * cap;
     for (int t = tid; t < ntaps; t += kRoiThreads) {
         const int b = t / cap, j = t - b * cap;
         const int* ob = s_off + b * cap;
@@ -362,6 +339,39 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
         if (j == cap - 1) s_cnt[b] = pos + (w != 0.f);
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------- forward (fast)
+// One CTA per (RoI, chunk of up to 64 channel quads), thread = (channel quad(s), bin group).  QPT = 2:
+// the second channel quad is an immediate +512 B off the same address.
+template <int QPT>
+__global__ void __launch_bounds__(kRoiThreads, 4)
+roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K, float* __restrict__ out,
+                     int32_t* __restrict__ levels_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int roi = order ? order[blockIdx.x] : blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nbins = L.PH * L.PW;
+    const int spb = L.sampling_ratio * L.sampling_ratio;  // samples per bin (fast path: fixed grid)
+    const int cap = 4 * spb;                               // taps per bin before merging
+    const int C = L.C;
+    const int Q = quads_per_chunk(C);
+    const int chunk0 = blockIdx.y * Q * 4;                 // first channel of this chunk
+    const int Qc = min(Q, (C - chunk0) / 4);               // quads in this chunk
+    // smem: [merged lists: nbins*cap int2][counts: nbins int, padded][staging [c][bin] | phase-A scratch]
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    __shared__ RoiGeom s_g;
+
+    if (tid == 0) {
+        s_g = roi_geometry(rois + (size_t)roi * 6, L);
+        if (levels_out && !order && blockIdx.y == 0) levels_out[roi] = s_g.level;
+    }
+    __syncthreads();
+    const RoiGeom g = s_g;
+    const int H = L.H[g.level], W = L.W[g.level];
+    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage);   // the scratch is dead after its final barrier
 
     const int lanes = QPT == 2 ? 32 : Qc;                  // threads per bin group
     const int groups = kRoiThreads / lanes;
@@ -401,7 +411,6 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
                         }
                     }
             }
-            // phase-A temporaries (aliasing the staging area) died at the barrier above
 #pragma unroll
             for (int u = 0; u < QPT; u++) {
                 // output_val /= count (:143); a power-of-two count makes the reciprocal multiply exact
@@ -428,63 +437,75 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
 }
 
 // ---------------------------------------------------------------------------------- backward (fast)
-__global__ void __launch_bounds__(kRoiThreads)
-roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, int K, const float* __restrict__ grad_out) {
+// Same CTA shape and tap lists.  The RoI's (C,7,7) gradient block is copied into shared memory as it
+// lies in memory (coalesced 16-byte loads); every merged tap becomes ONE 16-byte vector reduction per
+// channel quad (red.global.add.v4.f32) into the channels-last accumulator.
+template <int QPT>
+__global__ void __launch_bounds__(kRoiThreads, 4)
+roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K,
+                     const float* __restrict__ grad_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int roi = blockIdx.x;
+    const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x;
     const int nbins = L.PH * L.PW;
     const int spb = L.sampling_ratio * L.sampling_ratio;
-    const int nsamp = nbins * spb;
-    const int Q = quads_per_chunk(L.C);
+    const int cap = 4 * spb;
+    const int C = L.C;
+    const int Q = quads_per_chunk(C);
     const int chunk0 = blockIdx.y * Q * 4;
-    const int Qc = min(Q, (L.C - chunk0) / 4);
-    Taps* s_taps = reinterpret_cast<Taps*>(smem_raw);
-    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(Taps) * nsamp);
+    const int Qc = min(Q, (C - chunk0) / 4);
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
     if (tid == 0) s_g = roi_geometry(rois + (size_t)roi * 6, L);
-    // stage this chunk's gradient block: element e = c_local*nbins + b  ->  [k][b][quad]
-    const int C = L.C;
-    const int SQ = Q + 1;
-    const float* __restrict__ src = grad_out + ((size_t)roi * C + chunk0) * nbins;
-    const int total = Qc * 4 * nbins;
-    for (int e = tid; e < total; e += kRoiThreads) {
-        int c = e / nbins, b = e - c * nbins;
-        s_stage[((c & 3) * nbins + b) * SQ + (c >> 2)] = __ldg(src + e);
-    }
     __syncthreads();
     const RoiGeom g = s_g;
     const int H = L.H[g.level], W = L.W[g.level];
-    for (int s = tid; s < nsamp; s += kRoiThreads) {
-        int b = s / spb, q = s % spb;
-        int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
-        float x, y;
-        sample_xy(g, L.version, ph, pw, iy, ix, x, y);
-        s_taps[s] = make_taps(H, W, y, x);
+    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage);
+
+    // stage this chunk's gradient block [c_local][bin] (= memory order)
+    const float* __restrict__ src = grad_out + ((size_t)roi * C + chunk0) * nbins;
+    const int total = Qc * 4 * nbins;
+    if ((((size_t)roi * C + chunk0) * nbins & 3) == 0 && (total & 3) == 0) {
+        float4* s4 = reinterpret_cast<float4*>(s_stage);
+        for (int e = tid; e < total / 4; e += kRoiThreads) s4[e] = ldg_cs_v4(src + (size_t)e * 4);
+    } else {
+        for (int e = tid; e < total; e += kRoiThreads) s_stage[e] = __ldg(src + e);
     }
     __syncthreads();
 
-    float* __restrict__ gfeat = L.grad[g.level] + (size_t)g.batch * H * W * C + chunk0;
-    const int groups = kRoiThreads / Qc;
-    const int cq = tid % Qc, grp = tid / Qc;
-    const float count = (float)spb;  // no max(.,1) in backward (:246)
+    const int lanes = QPT == 2 ? 32 : Qc;
+    const int groups = kRoiThreads / lanes;
+    const int cq = tid % lanes, grp = tid / lanes;
+    float4* __restrict__ gfeat = reinterpret_cast<float4*>(L.grad[g.level] + (size_t)g.batch * H * W * C + chunk0) + cq;
+    const bool pow2 = (spb & (spb - 1)) == 0;
+    const float count = (float)spb, inv_count = 1.f / count;  // no max(.,1) in backward (:246)
     if (grp < groups) {
         for (int b = grp; b < nbins; b += groups) {
-            float4 top;
-            top.x = s_stage[(0 * nbins + b) * SQ + cq];
-            top.y = s_stage[(1 * nbins + b) * SQ + cq];
-            top.z = s_stage[(2 * nbins + b) * SQ + cq];
-            top.w = s_stage[(3 * nbins + b) * SQ + cq];
-            for (int q = 0; q < spb; q++) {
-                const Taps t = s_taps[b * spb + q];
-                // out-of-range samples have all-zero weights: skipping them is the reference's `if` (:285)
-                if (t.w[0] == 0.f && t.w[1] == 0.f && t.w[2] == 0.f && t.w[3] == 0.f) continue;
+            float4 top[QPT];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float wk = t.w[k];
-                    float4 gv = make_float4(top.x * wk / count, top.y * wk / count, top.z * wk / count, top.w * wk / count);
-                    red_add_v4(gfeat + (size_t)t.o[k] * C + cq * 4, gv);
+            for (int u = 0; u < QPT; u++) {
+                const int c0 = (cq + u * 32) * 4;
+                top[u].x = s_stage[(c0 + 0) * nbins + b];
+                top[u].y = s_stage[(c0 + 1) * nbins + b];
+                top[u].z = s_stage[(c0 + 2) * nbins + b];
+                top[u].w = s_stage[(c0 + 3) * nbins + b];
+            }
+            const int2* lp = s_list + b * cap;
+            const int cnt = s_cnt[b];
+            for (int e = 0; e < cnt; e++) {
+                const int2 en = lp[e];
+                const float wk = __int_as_float(en.y);
+                float* dst = const_cast<float*>(tap_ptr(reinterpret_cast<const float4*>(gfeat), (unsigned)en.x));
+#pragma unroll
+                for (int u = 0; u < QPT; u++) {
+                    // g = top * w / count (:280-283); exact reciprocal when count is a power of two
+                    float4 gv;
+                    if (pow2) gv = make_float4(top[u].x * wk * inv_count, top[u].y * wk * inv_count, top[u].z * wk * inv_count, top[u].w * wk * inv_count);
+                    else gv = make_float4(top[u].x * wk / count, top[u].y * wk / count, top[u].z * wk / count, top[u].w * wk / count);
+                    red_add_v4(dst + u * 128, gv);
                 }
             }
         }
@@ -682,11 +703,12 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
     const bool fast = fast_path_ok(cfg);
     const bool direct = cfg->channels_last || !fast;  // accumulate straight into the caller's buffers
     float* acc[RSDET_MAX_LEVELS];
+    if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 1)) return RSDET_EWORKSPACE;
+    Workspace ws(workspace, workspace_bytes);
+    int* order_ws = ws.take<int>(num_rois > 0 ? num_rois : 1);
     if (direct) {
         for (int l = 0; l < cfg->num_levels; l++) acc[l] = grad_feats_host[l];
     } else {
-        if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 1)) return RSDET_EWORKSPACE;
-        Workspace ws(workspace, workspace_bytes);
         for (int l = 0; l < cfg->num_levels; l++)
             acc[l] = ws.take<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
         if (!ws.ok()) return RSDET_EWORKSPACE;
@@ -706,15 +728,23 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
             int grid = (int)(ceil_div_ll(total, 256) < (long long)kNumSMs * 16 ? ceil_div_ll(total, 256) : (long long)kNumSMs * 16);
             roi_align_generic_kernel<true><<<grid, 256, 0, st>>>(L, M, rois, num_rois, const_cast<float*>(grad_out), nullptr);
         } else {
-            size_t smem = fast_smem_bytes(cfg);
+            size_t smem = fwd_smem_bytes(cfg);
             static size_t smem_set = 0;
             if (smem > smem_set) {
-                cudaFuncSetAttribute(roi_align_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(roi_align_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(roi_align_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 smem_set = smem;
+            }
+            int* order = nullptr;
+            if (num_rois >= 256) {
+                order = order_ws;
+                roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, nullptr);
+                count_launch();
             }
             int Q = quads_per_chunk(cfg->channels);
             dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
-            roi_align_bwd_kernel<<<grid, kRoiThreads, smem, st>>>(L, rois, num_rois, grad_out);
+            if (cfg->channels % 256 == 0) roi_align_bwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, grad_out);
+            else roi_align_bwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, grad_out);
         }
         count_launch();
     }
