@@ -360,23 +360,52 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
 }
 
 // ----------------------------------------------------------------------------- greedy scan
-// One CTA per segment walks its 64-row blocks in score order.  Per block: (1) thread 0 resolves the 64
-// rows against the already-accumulated `remv` word and the block's diagonal words (all 64 words are
-// pulled into registers first, so the dependent chain is pure ALU); (2) all 256 threads OR the
-// suppression words of the KEPT rows into the shared-memory `remv` vector (64 column lanes x 4 row
-// groups, merged with shared-memory atomics).  The next block's diagonal words are prefetched while (1)
-// and (2) run.
+// Small label groups (< kCoopMinBlocks 64-row blocks): one CTA per group walks its blocks in score
+// order.  Per block: (1) thread 0 resolves the 64 rows against the accumulated `remv` word and the block's
+// diagonal words (pulled into registers first, so the dependent chain is pure ALU); (2) all 256 threads
+// OR the suppression words of the KEPT rows into the shared-memory `remv` vector (64 column lanes x 4
+// row groups, merged with shared-memory atomics).  The next diagonal is prefetched meanwhile.
+//
+// Large groups (a 100k-box single-class NMS has 1563 dependent blocks and ~0.5 GB of kept-row words to
+// OR): kCoopCtas co-resident CTAs share ONE group.  Column block j belongs to CTA j % kCoopCtas, which keeps
+// that slice of `remv` in its shared memory.  The owner of block b resolves it and publishes the 64 keep
+// bits through global memory (word + flag, release/acquire by __threadfence); every CTA ORs the kept rows
+// into its own columns.  Only "publish -> next owner's one-column OR -> resolve" is on the critical path
+// (~2 us per block instead of the ~25 us a single CTA needs to sweep 64 x 1563 words).
+constexpr int kCoopMinBlocks = 128;
+constexpr int kCoopCtas = 64;
+
+__device__ __forceinline__ unsigned long long resolve_block(const unsigned long long* __restrict__ diag, unsigned long long r, int nr) {
+    unsigned long long d[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) d[i] = diag[i];
+    unsigned long long kb = 0ull;
+    if (nr < 64) r |= ~0ull << nr;  // rows past the group end count as removed
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        const bool alive = ((r >> i) & 1ull) == 0ull;
+        kb |= alive ? (1ull << i) : 0ull;
+        r |= alive ? d[i] : 0ull;
+    }
+    return kb;
+}
+
 __global__ void __launch_bounds__(kReduceThreads, 1)
-reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted) {
+reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted,
+              unsigned long long* __restrict__ pub_keep, int* __restrict__ pub_flag) {
     extern __shared__ unsigned long long s_remv[];
     __shared__ unsigned long long s_diag[2][64];
     __shared__ unsigned long long s_keep;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int nseg = tb.hdr[0];
-    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+    // ---- phase 1: small groups, one CTA each
+    int small_rank = 0;
+    for (int s = 0; s < nseg; s++) {
         const int st = tb.seg_start[s];
         const int ns = tb.seg_start[s + 1] - st;
         const int T = (ns + 63) >> 6;
+        if (T >= kCoopMinBlocks) continue;
+        if ((small_rank++ % (int)gridDim.x) != (int)blockIdx.x) continue;
         const unsigned long long* m = mask + tb.mask_off[s];
         __syncthreads();
         for (int j = tid; j < T; j += kReduceThreads) s_remv[j] = 0ull;
@@ -385,24 +414,11 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
         for (int b = 0; b < T; b++) {
             const int nr = min(64, ns - b * 64);
             unsigned long long diag_next = 0ull;
-            if (tid >= 64 && tid < 128 && b + 1 < T) {  // warp 2/3 prefetch the next diagonal
+            if (tid >= 64 && tid < 128 && b + 1 < T) {  // warps 2/3 prefetch the next diagonal
                 const int i = tid - 64;
                 if (i < min(64, ns - (b + 1) * 64)) diag_next = m[(long long)((b + 1) * 64 + i) * T + (b + 1)];
             }
-            if (tid == 0) {
-                unsigned long long d[64];
-#pragma unroll
-                for (int i = 0; i < 64; i++) d[i] = s_diag[b & 1][i];
-                unsigned long long r = s_remv[b], kb = 0ull;
-                if (nr < 64) r |= ~0ull << nr;  // rows past the segment end count as removed
-#pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    const bool alive = ((r >> i) & 1ull) == 0ull;
-                    kb |= alive ? (1ull << i) : 0ull;
-                    r |= alive ? d[i] : 0ull;
-                }
-                s_keep = kb;
-            }
+            if (tid == 0) s_keep = resolve_block(s_diag[b & 1], s_remv[b], nr);
             __syncthreads();
             const unsigned long long kb = s_keep;
             if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
@@ -418,6 +434,72 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
                         for (int i = 0; i < 16; i++)
                             if ((kb16 >> i) & 1u) acc |= col[(long long)i * T];
                         if (acc) atomicOr(&s_remv[j], acc);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- phase 2: large groups, kCoopCtas CTAs per group
+    const int G = min(kCoopCtas, (int)gridDim.x), k = blockIdx.x;
+    if (k >= G) return;
+    int large_rank = 0;
+    for (int s = 0; s < nseg; s++) {
+        const int st = tb.seg_start[s];
+        const int ns = tb.seg_start[s + 1] - st;
+        const int T = (ns + 63) >> 6;
+        if (T < kCoopMinBlocks) continue;
+        const unsigned long long* m = mask + tb.mask_off[s];
+        const int pub0 = (st >> 6) + large_rank++;  // unique publication slots for this group's blocks
+        const int nloc = (T + G - 1) / G;          // my slice of remv: column j -> s_remv[j / G]
+        __syncthreads();
+        for (int j = tid; j < nloc; j += kReduceThreads) s_remv[j] = 0ull;
+        __syncthreads();
+        for (int b = 0; b < T; b++) {
+            const int nr = min(64, ns - b * 64);
+            const bool own = (b % G) == k, own_next = ((b + 1) % G) == k && b + 1 < T;
+            // loads that do not depend on the keep bits are issued before waiting for them
+            unsigned long long pre = 0ull;
+            if (own && tid < 64) { if (tid < nr) pre = m[(long long)(b * 64 + tid) * T + b]; s_diag[0][tid] = pre; }
+            if (own_next && tid >= 64 && tid < 128) { const int i = tid - 64; if (i < nr) pre = m[(long long)(b * 64 + i) * T + (b + 1)]; }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long kb;
+                if (own) {
+                    kb = resolve_block(s_diag[0], s_remv[b / G], nr);
+                    pub_keep[pub0 + b] = kb;
+                    __threadfence();
+                    *(volatile int*)(pub_flag + pub0 + b) = 1;
+                } else {
+                    while (*(volatile int*)(pub_flag + pub0 + b) == 0) { }
+                    __threadfence();
+                    kb = *(volatile unsigned long long*)(pub_keep + pub0 + b);
+                }
+                s_keep = kb;
+            }
+            __syncthreads();
+            const unsigned long long kb = s_keep;
+            if (own && tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            // critical path first: the next owner folds block b into column b+1 (words already in registers)
+            if (own_next && tid >= 64 && tid < 128) {
+                unsigned long long w = ((kb >> (tid - 64)) & 1ull) ? pre : 0ull;
+                unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)w), hi = __reduce_or_sync(0xffffffffu, (unsigned)(w >> 32));
+                if (lane == 0 && (lo | hi)) atomicOr(&s_remv[(b + 1) / G], ((unsigned long long)hi << 32) | lo);
+            }
+            // then my other columns j > b (j % G == k), 16 column lanes x 16 row groups of 4
+            if (kb) {
+                int j0 = b + 1 + ((k - (b + 1)) % G + G) % G;
+                if (own_next) j0 += G;
+                const int cl = tid & 15, rg = tid >> 4;
+                const unsigned kb4 = (unsigned)((kb >> (rg * 4)) & 0xfull);
+                if (kb4) {
+                    for (int j = j0 + cl * G; j < T; j += 16 * G) {
+                        unsigned long long acc = 0ull;
+                        const unsigned long long* col = m + (long long)(b * 64 + rg * 4) * T + j;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if ((kb4 >> i) & 1u) acc |= col[(long long)i * T];
+                        if (acc) atomicOr(&s_remv[j / G], acc);
                     }
                 }
             }
@@ -646,6 +728,7 @@ size_t nms_ws_bytes(int kind, int n) {
     b += 3 * ws_bytes<uint8_t>(N);                                     // keep_sorted, keep_mask tmp, flags
     b += 2 * ws_bytes<int64_t>(N);                                     // vals, scratch index output
     b += ws_bytes<int>(64) + ws_bytes<int>(kFastSegs);                 // scratch count, unordered segment starts
+    b += ws_bytes<unsigned long long>(2 * N / 64 + 8) + ws_bytes<int>(2 * N / 64 + 8);  // published keep words + flags
     b += align256(kCubTempBytes + 16 * N);
     return b;
 }
@@ -716,6 +799,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     int64_t* idx_scratch = ws.take<int64_t>(N);
     int* cnt_scratch = ws.take<int>(64);
     int* starts_unsorted = ws.take<int>(kFastSegs);
+    unsigned long long* pub_keep = ws.take<unsigned long long>(2 * N / 64 + 8);
+    int* pub_flag = ws.take<int>(2 * N / 64 + 8);
     size_t cub_bytes = kCubTempBytes + 16 * N;
     void* cub_tmp = ws.take<char>(cub_bytes);
     if (!ws.ok()) return RSDET_EWORKSPACE;
@@ -799,7 +884,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
             cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
-        reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted);
+        if ((N + 63) / 64 >= (size_t)kCoopMinBlocks) cudaMemsetAsync(pub_flag, 0, sizeof(int) * (2 * N / 64 + 8), st);
+        reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag);
         count_launch();
     }
     }

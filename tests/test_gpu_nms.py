@@ -24,7 +24,8 @@ def test_known_answer(cuda):
     assert nms_rotated(torch.zeros((0, 5), device="cuda"), torch.zeros((0,), device="cuda"), 0.3).numel() == 0
 
 
-@pytest.mark.parametrize("n,canvas", [(1, 1024), (63, 256), (64, 256), (65, 256), (1000, 1024), (5000, 1024)])
+@pytest.mark.parametrize("n,canvas", [(1, 1024), (63, 256), (64, 256), (65, 256), (1000, 1024), (5000, 1024),
+                                      (9000, 2048)])  # 9000 boxes = 141 blocks: the multi-CTA cooperative scan
 @pytest.mark.parametrize("thr", [0.1, 0.5])
 def test_nms_rotated_vs_oracle(cuda, oracle, n, canvas, thr):
     from rs_detection_b200.jdet.ops.nms_rotated import nms_rotated
@@ -51,7 +52,7 @@ def test_nms_cpu_cuda_rule_and_explicit_order(cuda, oracle):
             assert np.array_equal(got, oracle.nms_rotated_keep(d, order, thr, 5, ge, 1)), (thr, ge)
 
 
-@pytest.mark.parametrize("n,ncls", [(3000, 15), (4000, 1), (500, 500)])
+@pytest.mark.parametrize("n,ncls", [(3000, 15), (4000, 1), (500, 500), (20000, 2)])
 def test_ml_nms_rotated_vs_oracle(cuda, oracle, n, ncls):
     from rs_detection_b200.jdet.ops.nms_rotated import ml_nms_rotated
     d = W.rotated_boxes(n, 31, canvas=700, smin=16, smax=128)
