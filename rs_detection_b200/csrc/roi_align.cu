@@ -25,6 +25,8 @@
 //
 // Sample coordinates are computed with explicitly un-contracted IEEE operations in the reference's
 // order: the validity test `y < -1 || y > H` is discontinuous, so coordinates must not drift.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -288,13 +290,14 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
 // into one (offset, weight) entry and zero-weight taps are dropped; on the benchmark proposals 16 taps
 // collapse to ~9.  Offsets are in 16-byte units of the channels-last map (one mad.wide per address).
 //   s_list [nbins*cap] int2 {offset, weight bits}, s_cnt [nbins], tmp: 3*nbins*cap words of scratch.
+//   unit/base: stored offset = base + pixel * unit (unit = C/4 for float4 addressing, 1 for TMA row indices)
 __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet& L, int H, int W, int2* s_list, int* s_cnt,
-                                                float* tmp) {
+                                                float* tmp, int unit, int base) {
     const int tid = threadIdx.x;
     const int nbins = L.PH * L.PW;
     const int spb = L.sampling_ratio * L.sampling_ratio;
     const int nsamp = nbins * spb, cap = 4 * spb, ntaps = nbins * cap;
-    const int C4 = L.C >> 2;
+    const int C4 = unit;
     int* s_off = reinterpret_cast<int*>(tmp);
     float* s_w = tmp + ntaps;
     float* s_wsum = tmp + 2 * ntaps;
@@ -307,7 +310,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         const Taps t = make_taps(H, W, y, x);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            s_off[s * 4 + k] = t.o[k] * C4;
+            s_off[s * 4 + k] = base + t.o[k] * C4;
             s_w[s * 4 + k] = t.w[k];
         }
     }
@@ -371,7 +374,7 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     __syncthreads();
     const RoiGeom g = s_g;
     const int H = L.H[g.level], W = L.W[g.level];
-    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage);   // the scratch is dead after its final barrier
+    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);   // the scratch is dead after its final barrier
 
     const int lanes = QPT == 2 ? 32 : Qc;                  // threads per bin group
     const int groups = kRoiThreads / lanes;
@@ -436,6 +439,177 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     }
 }
 
+// ---------------------------------------------------------------------------------- forward (TMA gather4)
+// Same decomposition (one CTA per RoI, merged tap lists, warp = bin group), but the feature rows are no
+// longer pulled through the LSU into registers: each group of 4 merged taps is ONE Blackwell
+// `cp.async.bulk.tensor.2d ... tile::gather4` (4 arbitrary pixel rows x 256 channels = 4 KB) issued by a
+// single lane into a per-warp ring in shared memory and tracked by an mbarrier.  What this buys: bytes in
+// flight are bounded by shared memory (8 warps x 3 stages x 4 KB = 96 KB per CTA, 2 CTAs per SM) instead
+// of by the register file (8 x 16 B per thread), so the L2 round trips (~1 us loaded) overlap instead of
+// serialising; address generation and the 784 x 64 vector loads per RoI leave the instruction stream.
+// Results stay in registers until the ring is idle, then the ring is reused as the [c][bin] staging area.
+constexpr int kTmaStages = 3;
+#ifndef RSDET_BULK_ROWS
+#define RSDET_BULK_ROWS 0
+#endif
+constexpr bool kBulkRows = RSDET_BULK_ROWS != 0;
+constexpr int kTmaMaxSlots = 8;  // bins per warp (ceil(nbins / 8) <= 8 -> nbins <= 64)
+
+struct TmaMaps { CUtensorMap m[RSDET_MAX_LEVELS]; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kRoiThreads, 2)
+roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const float* __restrict__ rois,
+                         const int* __restrict__ order, int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int roi = order ? order[blockIdx.x] : blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbins = L.PH * L.PW;
+    const int spb = L.sampling_ratio * L.sampling_ratio;
+    const int cap = 4 * spb;
+    const int C = L.C;                                     // == 256 * gridDim.y
+    const int chunk0 = blockIdx.y * 256;
+    // smem: [ring 8 warps x kTmaStages x 4 KB | staging [256][nbins] | phase-A scratch][lists][counts][mbarriers]
+    const size_t ring_bytes = (size_t)8 * kTmaStages * 4096;
+    const size_t big = max(ring_bytes, max((size_t)256 * nbins * 4, (size_t)12 * nbins * cap));
+    float* s_stage = reinterpret_cast<float*>(smem_raw);
+    int2* s_list = reinterpret_cast<int2*>(smem_raw + big);
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + big + sizeof(int2) * nbins * cap);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + big + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    __shared__ RoiGeom s_g;
+
+    if (tid == 0) {
+        s_g = roi_geometry(rois + (size_t)roi * 6, L);
+        if (levels_out && !order && blockIdx.y == 0) levels_out[roi] = s_g.level;
+    }
+    if (tid < 8 * kTmaStages) mbar_init(s_bar + tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const RoiGeom g = s_g;
+    const int H = L.H[g.level], W = L.W[g.level];
+    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, 1, g.batch * H * W);  // entries = global pixel-row index
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // scratch (generic writes) -> TMA writes
+
+    const CUtensorMap* map = &maps.m[g.level];
+    unsigned char* ring = smem_raw + (size_t)warp * kTmaStages * 4096;
+    unsigned long long* bar = s_bar + warp * kTmaStages;
+    const bool pow2 = (spb & (spb - 1)) == 0;
+    const float count = (float)max(spb, 1), inv_count = 1.f / count;
+
+    // issue cursor (warp-uniform): next (bin, first entry) to fetch
+    int ib = warp, ie = 0, istage = 0, inflight = 0;
+    auto issue = [&]() {
+        while (ib < nbins && ie >= s_cnt[ib]) { ib += 8; ie = 0; }
+        if (ib >= nbins) return;
+        if (kBulkRows) {
+            // variant: four 1-D bulk copies (one per pixel row) instead of one gather4
+            const int cnt = s_cnt[ib];
+            const int nrow = min(4, cnt - ie);
+            if (lane == 0) mbar_expect_tx(bar + istage, 1024u * nrow);
+            __syncwarp();
+            if (lane < nrow) {
+                const int r = s_list[ib * cap + ie + lane].x;
+                const float* src = L.feat[g.level] + (size_t)r * C + chunk0;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(ring + istage * 4096 + lane * 1024)), "l"(src), "r"(1024u), "r"(smem_u32(bar + istage)) : "memory");
+            }
+        } else if (lane == 0) {
+            const int cnt = s_cnt[ib];
+            const int2* lp = s_list + ib * cap;
+            const int r0 = lp[ie].x, r1 = lp[min(ie + 1, cnt - 1)].x, r2 = lp[min(ie + 2, cnt - 1)].x, r3 = lp[min(ie + 3, cnt - 1)].x;
+            mbar_expect_tx(bar + istage, 4096u);
+            tma_gather4(ring + istage * 4096, map, chunk0, r0, r1, r2, r3, bar + istage);
+        }
+        ie += 4;
+        istage = istage + 1 == kTmaStages ? 0 : istage + 1;
+        inflight++;
+    };
+#pragma unroll
+    for (int d = 0; d < kTmaStages; d++) issue();
+
+    float4 res[kTmaMaxSlots][2];
+    int cstage = 0;
+    unsigned phase = 0;  // bit s = parity to wait for on stage s
+#pragma unroll
+    for (int slot = 0; slot < kTmaMaxSlots; slot++) {
+        const int b = warp + 8 * slot;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (b < nbins) {
+            const int cnt = s_cnt[b];
+            const int2* lp = s_list + b * cap;
+            for (int e = 0; e < cnt; e += 4) {
+                float wt[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) wt[k] = e + k < cnt ? __int_as_float(lp[e + k].y) : 0.f;
+                mbar_wait(bar + cstage, (phase >> cstage) & 1u);
+                const float4* row = reinterpret_cast<const float4*>(ring + cstage * 4096) + lane;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (kBulkRows && e + k >= cnt) continue;  // that row was not fetched
+                    const float4 v0 = row[k * 64], v1 = row[k * 64 + 32];
+                    a0.x = fmaf(wt[k], v0.x, a0.x); a0.y = fmaf(wt[k], v0.y, a0.y); a0.z = fmaf(wt[k], v0.z, a0.z); a0.w = fmaf(wt[k], v0.w, a0.w);
+                    a1.x = fmaf(wt[k], v1.x, a1.x); a1.y = fmaf(wt[k], v1.y, a1.y); a1.z = fmaf(wt[k], v1.z, a1.z); a1.w = fmaf(wt[k], v1.w, a1.w);
+                }
+                phase ^= 1u << cstage;
+                cstage = cstage + 1 == kTmaStages ? 0 : cstage + 1;
+                inflight--;
+                __syncwarp();  // every lane has read the stage before lane 0 hands it back to the TMA unit
+                issue();
+            }
+            if (pow2) { a0.x *= inv_count; a0.y *= inv_count; a0.z *= inv_count; a0.w *= inv_count;
+                        a1.x *= inv_count; a1.y *= inv_count; a1.z *= inv_count; a1.w *= inv_count; }
+            else { a0.x /= count; a0.y /= count; a0.z /= count; a0.w /= count;
+                   a1.x /= count; a1.y /= count; a1.z /= count; a1.w /= count; }
+        }
+        res[slot][0] = a0;
+        res[slot][1] = a1;
+    }
+    __syncthreads();  // all rings idle: reuse them as the staging area
+#pragma unroll
+    for (int slot = 0; slot < kTmaMaxSlots; slot++) {
+        const int b = warp + 8 * slot;
+        if (b < nbins) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int c0 = (lane + u * 32) * 4;
+                s_stage[(c0 + 0) * nbins + b] = res[slot][u].x;
+                s_stage[(c0 + 1) * nbins + b] = res[slot][u].y;
+                s_stage[(c0 + 2) * nbins + b] = res[slot][u].z;
+                s_stage[(c0 + 3) * nbins + b] = res[slot][u].w;
+            }
+        }
+    }
+    __syncthreads();
+    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;
+    const int total = 256 * nbins;
+    if ((((size_t)roi * C + chunk0) * nbins & 3) == 0 && (total & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(s_stage);
+        for (int e = tid; e < total / 4; e += kRoiThreads) stg_cs_v4(dst + (size_t)e * 4, s4[e]);
+    } else {
+        for (int e = tid; e < total; e += kRoiThreads) __stcs(dst + e, s_stage[e]);
+    }
+}
+
 // ---------------------------------------------------------------------------------- backward (fast)
 // Same CTA shape and tap lists.  The RoI's (C,7,7) gradient block is copied into shared memory as it
 // lies in memory (coalesced 16-byte loads); every merged tap becomes ONE 16-byte vector reduction per
@@ -463,7 +637,7 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     __syncthreads();
     const RoiGeom g = s_g;
     const int H = L.H[g.level], W = L.W[g.level];
-    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage);
+    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);
 
     // stage this chunk's gradient block [c_local][bin] (= memory order)
     const float* __restrict__ src = grad_out + ((size_t)roi * C + chunk0) * nbins;
@@ -615,6 +789,57 @@ static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
     return sizeof(Taps) * (size_t)nsamp + sizeof(float) * 4 * (size_t)nbins * (Q + 1);  // backward layout is the larger
 }
 
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (librsdet links no libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D view [N*H*W pixel rows][C] of a channels-last map; box = one row of 256 channels (gather4 fetches 4 rows)
+static bool make_row_map(CUtensorMap* m, const float* base, long long rows, int C) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(float)};
+    cuuint32_t box[2] = {256u, 1u};
+    cuuint32_t estr[2] = {1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static size_t tma_smem_bytes(const rsdet_roi_align_cfg* c) {
+    size_t nbins = (size_t)c->pooled_h * c->pooled_w, cap = 4 * (size_t)c->sampling_ratio * c->sampling_ratio;
+    size_t big = (size_t)8 * kTmaStages * 4096;
+    if (256 * nbins * 4 > big) big = 256 * nbins * 4;
+    if (12 * nbins * cap > big) big = 12 * nbins * cap;
+    return big + 8 * nbins * cap + ((nbins * 4 + 15) & ~(size_t)15) + 8 * 8 * kTmaStages + 64;
+}
+
+static bool tma_path_ok(const rsdet_roi_align_cfg* c) {
+    // Opt-in (RSDET_ROI_TMA=1): measured 308 us per 4000-RoI tile against 200 us for the register path on
+    // B200 (profiles/README.md, "TMA gather4 experiment") -- correct, but two 105 KB CTAs per SM expose the
+    // tap-list and write-out phases that four 57 KB CTAs overlap.  Kept for the round-2 persistent-CTA rework.
+    const char* e = getenv("RSDET_ROI_TMA");
+    if (!(e && e[0] == '1')) return false;
+    if (c->channels % 256 != 0 || c->pooled_h * c->pooled_w > 8 * kTmaMaxSlots) return false;
+    for (int l = 0; l < c->num_levels; l++)
+        if ((long long)c->batch * c->height[l] * c->width[l] >= (1ll << 31)) return false;
+    return tma_smem_bytes(c) <= 110 * 1024 && encode_tiled_fn() != nullptr;
+}
+
 }  // namespace rsdet
 
 using namespace rsdet;
@@ -679,6 +904,25 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         order = order_ws;
         roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, levels_out);
         count_launch();
+    }
+    if (tma_path_ok(cfg)) {
+        TmaMaps maps;
+        bool ok = true;
+        for (int l = 0; l < cfg->num_levels && ok; l++)
+            ok = make_row_map(&maps.m[l], L.feat[l], (long long)cfg->batch * cfg->height[l] * cfg->width[l], cfg->channels);
+        for (int l = cfg->num_levels; l < RSDET_MAX_LEVELS; l++) maps.m[l] = maps.m[0];
+        if (ok) {
+            const size_t tsmem = tma_smem_bytes(cfg);
+            static size_t tsmem_set = 0;
+            if (tsmem > tsmem_set) {
+                cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+                tsmem_set = tsmem;
+            }
+            dim3 tgrid(num_rois, cfg->channels / 256);
+            roi_align_fwd_tma_kernel<<<tgrid, kRoiThreads, tsmem, st>>>(L, maps, rois, order, num_rois, out, levels_out);
+            count_launch();
+            return cuda_status();
+        }
     }
     const int Q = quads_per_chunk(cfg->channels);
     dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
