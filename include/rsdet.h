@@ -153,6 +153,21 @@ int rsdet_iou_poly_pairs(const double* polys1, const double* polys2, int n, doub
  * polys (n,8) fp64 in-tile coords; offs (n,3) fp64 [x, y, rate] per row. */
 int rsdet_poly2origpoly(const double* polys, const double* offs, int n, double* out, void* stream);
 
+/* ---------------------------------------------------------------- head tail fusion
+ * models/roi_heads/oriented_head.py:498-536 (get_bboxes) + :279-305 (get_results), with
+ * OrientedDeltaXYWHTCoder.decode (models/boxes/coder.py:477-514), regular_theta / regular_obb
+ * (ops/bbox_transforms.py:501-519) and obb2poly (:612-623): softmax over (k, C+1) logits (background =
+ * LAST column), delta decode against rois5 (k,5) [cx,cy,w,h,theta], optional division of cx,cy,w,h by
+ * scale_factor4_host (NULL = rescale False), `score > score_thresh`, polygon conversion and compaction
+ * in row-major (roi, class) order.  bbox_pred is (k,5) when reg_class_agnostic else (k,5*C).
+ * means5_host / stds5_host / scale_factor4_host are HOST arrays (config constants).
+ * out_dets (k*C, 9) [x1..y4, score], out_labels int64 (k*C), out_count int32 (1, device). */
+size_t rsdet_oriented_head_results_workspace_bytes(int k);
+int rsdet_oriented_head_results(const float* rois5, const float* cls_score, const float* bbox_pred, int k, int num_classes,
+                                int reg_class_agnostic, const float* means5_host, const float* stds5_host, float wh_ratio_clip,
+                                const float* scale_factor4_host, float score_thresh, int apply_softmax, float* out_dets,
+                                int64_t* out_labels, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* counters for bench.py's `gpu_launches`: number of kernels this library has launched so far */
 unsigned long long rsdet_launch_count(void);
 

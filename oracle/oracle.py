@@ -383,3 +383,66 @@ def poly2origpoly(poly, x, y, rate):
     p[..., 0::2] = (p[..., 0::2] + x) / float(rate)
     p[..., 1::2] = (p[..., 1::2] + y) / float(rate)
     return p
+
+
+# ----------------------------------------------------------------------------- head tail
+def regular_theta(theta, mode='180', start=-np.pi / 2):
+    """python/jdet/ops/bbox_transforms.py:501-507 (float32; `%` taken as floor-mod like numpy)."""
+    cycle = np.float32(2 * np.pi if mode == '360' else np.pi)
+    t = theta.astype(np.float32) - np.float32(start)
+    t = np.mod(t, cycle).astype(np.float32)
+    return t + np.float32(start)
+
+
+def regular_obb(obb):
+    """python/jdet/ops/bbox_transforms.py:509-519."""
+    x, y, w, h, th = [obb[..., i] for i in range(5)]
+    wide = w > h
+    w_r = np.where(wide, w, h)
+    h_r = np.where(wide, h, w)
+    th_r = regular_theta(np.where(wide, th, th + np.float32(np.pi / 2)).astype(np.float32))
+    return np.stack([x, y, w_r, h_r, th_r], -1).astype(np.float32)
+
+
+def delta_xywht_decode(bboxes, pred, means, stds, wh_ratio_clip=16 / 1000):
+    """OrientedDeltaXYWHTCoder.decode, python/jdet/models/boxes/coder.py:477-514.  bboxes (K,5), pred (K,5m)."""
+    b, p = _c32(bboxes), _c32(pred)
+    m = p.shape[1] // 5
+    d = p.reshape(-1, m, 5) * np.asarray(stds, np.float32) + np.asarray(means, np.float32)
+    dx, dy, dw, dh, dt = [d[..., i] for i in range(5)]
+    mr = np.float32(np.abs(np.log(wh_ratio_clip)))
+    dw, dh = np.clip(dw, -mr, mr), np.clip(dh, -mr, mr)
+    px, py, pw, ph, pt = [b[:, i:i + 1] for i in range(5)]
+    gx = dx * pw * np.cos(-pt) - dy * ph * np.sin(-pt) + px
+    gy = dx * pw * np.sin(-pt) + dy * ph * np.cos(-pt) + py
+    gw, gh = pw * np.exp(dw), ph * np.exp(dh)
+    gt = regular_theta((dt + pt).astype(np.float32))
+    out = regular_obb(np.stack([gx, gy, gw, gh, gt], -1).astype(np.float32))
+    return out.reshape(p.shape[0], -1)
+
+
+def oriented_head_get_bboxes(rois, cls_score, bbox_pred, scale_factor=None, means=(0., 0., 0., 0., 0.),
+                             stds=(0.1, 0.1, 0.2, 0.2, 0.1), score_thresh=0.05):
+    """OrientedHead.get_bboxes + get_results (start 'obb' -> end 'obb'),
+    python/jdet/models/roi_heads/oriented_head.py:498-536, 279-305.  rois (K,6); returns (dets (M,9), labels (M,))."""
+    s = _c32(cls_score)
+    e = np.exp(s - s.max(1, keepdims=True))
+    scores = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    bboxes = delta_xywht_decode(_c32(rois)[:, 1:], bbox_pred, means, stds)
+    K = scores.shape[0]
+    C_ = scores.shape[1] - 1
+    if scale_factor is not None:
+        sf = np.asarray([scale_factor] * 4 if np.isscalar(scale_factor) else scale_factor, np.float32)
+        bb = bboxes.reshape(K, -1, 5).copy()
+        bb[..., :4] = bb[..., :4] / sf
+        bboxes = bb.reshape(K, -1)
+    if bboxes.shape[1] > 5:
+        bb = bboxes.reshape(K, -1, 5)
+    else:
+        bb = np.broadcast_to(bboxes[:, None], (K, C_, 5))
+    sc = scores[:, :-1]
+    valid = sc > np.float32(score_thresh)
+    if not valid.any():
+        return np.zeros((0, 9), np.float32), np.zeros((0,), np.int64)
+    dets = np.concatenate([obb2poly(bb[valid]), sc[valid][:, None]], 1)
+    return dets.astype(np.float32), np.nonzero(valid)[1].astype(np.int64)

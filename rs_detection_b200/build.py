@@ -26,6 +26,7 @@ UNITS = {
     "box_iou.cu": ["-fmad=false"],
     "nms.cu": ["-fmad=false"],
     "transforms.cu": ["-fmad=false"],
+    "head.cu": ["-fmad=false"],
     "roi_align.cu": ["-DRSDET_BULK_ROWS=" + os.environ.get("RSDET_BULK_ROWS", "0")],
 }
 

@@ -254,6 +254,33 @@ def roi_align_rotated_backward(cfg: RoiAlignCfg, grad_out: torch.Tensor, rois: t
     return grads
 
 
+def oriented_head_results(rois5: torch.Tensor, cls_score: torch.Tensor, bbox_pred: torch.Tensor, num_classes: int,
+                          reg_class_agnostic: bool, means, stds, score_thresh: float, scale_factor=None,
+                          wh_ratio_clip: float = 16 / 1000, apply_softmax: bool = True):
+    """-> (dets (cap,9), labels (cap,) int64, count (1,) int32), all on device (no sync)."""
+    r, s, d = _f32(rois5), _f32(cls_score), _f32(bbox_pred)
+    k = r.shape[0]
+    cap = max(k * num_classes, 1)
+    dev = r.device
+    dets = torch.empty((cap, 9), dtype=torch.float32, device=dev)
+    labels = torch.empty((cap,), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if k == 0:
+        return dets, labels, cnt
+    L = load()
+    m5 = (C.c_float * 5)(*[float(v) for v in means])
+    s5 = (C.c_float * 5)(*[float(v) for v in stds])
+    sf = None
+    if scale_factor is not None:
+        sfv = [float(scale_factor)] * 4 if isinstance(scale_factor, (int, float)) else [float(v) for v in scale_factor]
+        sf = (C.c_float * 4)(*sfv)
+    ws = workspace(L.rsdet_oriented_head_results_workspace_bytes(k), "head")
+    check(L.rsdet_oriented_head_results(ptr(r), ptr(s), ptr(d), k, int(num_classes), int(reg_class_agnostic), m5, s5,
+                                        float(wh_ratio_clip), sf, float(score_thresh), int(apply_softmax), ptr(dets),
+                                        ptr(labels), ptr(cnt), ptr(ws), ws.numel(), stream_ptr()), "oriented_head_results")
+    return dets, labels, cnt
+
+
 def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x)
     n, c, h, w = x.shape
