@@ -21,7 +21,7 @@ def test_head_tail_vs_oracle(cuda, oracle, agnostic, C, thr, scale):
         rng = np.random.default_rng(seed)
         cls = (rng.standard_normal((K, C + 1)) * 2.0).astype(np.float32)
         e0 = np.exp(cls - cls.max(1, keepdims=True))
-        if int((np.abs((e0 / e0.sum(1, keepdims=True))[:, :-1] - thr) < 1e-6).sum()) == 0:
+        if int((np.abs((e0 / e0.sum(1, keepdims=True))[:, :-1] - thr) < 1e-5 * thr).sum()) == 0:
             break
     rois = W.proposals(K, C)
     pred = (rng.standard_normal((K, 5 if agnostic else 5 * C)) * 0.8).astype(np.float32)
@@ -31,8 +31,8 @@ def test_head_tail_vs_oracle(cuda, oracle, agnostic, C, thr, scale):
     wd, wl = oracle.oriented_head_get_bboxes(rois, cls, pred, scale, score_thresh=thr)
     # candidates whose softmax score sits within 1e-6 of the threshold may flip with exp() ulps
     e = np.exp(cls - cls.max(1, keepdims=True)); sc = e / e.sum(1, keepdims=True)
-    near = int((np.abs(sc[:, :-1] - thr) < 1e-6).sum())
-    print(f"C={C} agnostic={agnostic}: {wd.shape[0]} detections, {near} scores within 1e-6 of the threshold")
+    near = int((np.abs(sc[:, :-1] - thr) < 1e-5 * thr).sum())  # expf/exp differ by ulps: band relative to thr
+    print(f"C={C} agnostic={agnostic}: {wd.shape[0]} detections, {near} scores within 1e-5*thr of the threshold")
     assert near == 0
     assert gd.shape == wd.shape and wd.shape[0] > 1000
     assert np.array_equal(gl.cpu().numpy(), wl)

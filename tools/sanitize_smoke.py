@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family, meant to run under compute-sanitizer (memcheck / racecheck /
+initcheck): python tools/sanitize_smoke.py"""
+import os, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import workloads as W
+from rs_detection_b200 import core
+from rs_detection_b200._lib import NMS_HBB, NMS_MERGE, NMS_POLY, NMS_ROTATED, NMS_ROTATED_GE
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+n = 700
+b = W.rotated_boxes(n, 1, canvas=300, smin=8, smax=96)
+s = W.distinct_scores(n, 1)
+lab = np.random.default_rng(0).integers(0, 5, n).astype(np.int32)
+core.box_iou_rotated(t(b[:100]), t(b), 1, True)
+core.assign_wrt_overlaps(core.box_iou_rotated(t(b[:37]), t(b), 0), 0.5, (0.1, 0.4), 0.3, True, True, t(lab[:37]))
+for kind in (NMS_ROTATED, NMS_ROTATED_GE):
+    core.nms(kind, t(b), t(s), 0.3, labels=t(lab), want_score=True).count
+core.nms(NMS_ROTATED, t(W.rotated_boxes(9000, 2, canvas=2048, smin=8, smax=96)), t(W.distinct_scores(9000, 2)), 0.3).count  # coop scan
+p = core.obb2poly(t(b)); core.obb2hbb(t(b)); core.poly2hbb(p)
+core.nms(NMS_POLY, p[:300], t(s[:300]), 0.2, want_score=True).count
+sc = W.merge_scene(num_objects=150, scene=1500, seed=2)
+core.nms(NMS_MERGE, t(sc["polys"]), t(sc["scores"]), 0.1, labels=t(sc["labels"].astype(np.int32)), thr_per_label=t(np.full(10, 0.2)), want_score=True).count
+core.iou_poly_pairs(t(sc["polys"][:50]), t(sc["polys"][1:51]))
+hb = np.concatenate([np.random.default_rng(1).uniform(0, 100, (200, 2))] * 2, 1); hb[:, 2:] += 20
+core.nms(NMS_HBB, t(hb), t(W.distinct_scores(200, 3).astype(np.float64)), 0.5, want_score=True).count
+core.multiclass_nms_rotated(t(b), t(W.class_scores(n, 6, 1)), 0.05, 0.1, 100)[2].item()
+core.multiclass_nms_rotated(t(np.concatenate([b] * 7, 1)), t(W.class_scores(n, 6, 1)), 0.05, 0.1, -1)[2].item()
+for C in (256, 24, 6):
+    shapes = W.fpn_shapes(2, tile=256, channels=C)
+    feats = [torch.randn(sh, device="cuda") for sh in shapes]
+    rois = t(W.proposals(300, 4, batch=2, canvas=256))
+    cfg = core.make_roi_cfg(shapes, [1 / s_ for s_ in W.STRIDES], 7, 2, 1, (1.4, 1.2))
+    out = core.roi_align_rotated_forward(cfg, feats, rois)
+    core.roi_align_rotated_backward(cfg, torch.randn_like(out), rois, shapes)
+cfg = core.make_roi_cfg([(1, 8, 32, 32)], [0.25], (3, 5), 0, 0)
+out = core.roi_align_rotated_forward(cfg, [torch.randn((1, 8, 32, 32), device="cuda")], t(W.proposals(40, 5, canvas=128)))
+core.roi_align_rotated_backward(cfg, torch.randn_like(out), t(W.proposals(40, 5, canvas=128)), [(1, 8, 32, 32)])
+core.oriented_head_results(t(b), torch.randn((n, 11), device="cuda"), torch.randn((n, 5), device="cuda") * 0.1, 10, True, [0.] * 5, [0.1, 0.1, 0.2, 0.2, 0.1], 0.05, 1.5)[2].item()
+torch.cuda.synchronize()
+print("sanitize smoke done")
