@@ -44,6 +44,7 @@ struct LevelSet {
     int num_levels, batch, C;
     int PH, PW, sampling_ratio, version;
     float extend_w, extend_h, finest_scale;
+    int dbg_skip_main;  // profiling aid (RSDET_ROI_DBG_SKIP_MAIN=1): tap lists are built, then treated as empty
 };
 
 // ---------------------------------------------------------------------------------- transposes
@@ -225,6 +226,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 //   stage  : [4][nbins][Q+1] floats   (k = channel within quad, Q = quads per CTA chunk)
 __host__ __device__ inline int quads_per_chunk(int C) { return (C / 4) < 64 ? (C / 4) : 64; }
 
+// ---------------------------------------------------------------------------------- per-RoI geometry
+// sin/cos/log2/sqrt and six divisions per RoI: done by K parallel threads here instead of by thread 0 of
+// every RoI's CTA (a ~1.5 us serial chain in front of each CTA's barrier).
+__global__ void roi_geometry_kernel(LevelSet L, const float* __restrict__ rois, int K, RoiGeom* __restrict__ geoms,
+                                    int32_t* __restrict__ levels_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    RoiGeom g = roi_geometry(rois + (size_t)i * 6, L);
+    geoms[i] = g;
+    if (levels_out) levels_out[i] = g.level;
+}
+
 // ---------------------------------------------------------------------------------- processing order
 // RoIs are independent, so the ORDER in which CTAs take them is free.  A one-CTA counting sort buckets
 // them by (level, 128-pixel image cell): CTAs that run at the same time then read the same few MB of
@@ -234,8 +247,8 @@ constexpr int kCellShift = 7;   // 128-pixel cells in image coordinates
 constexpr int kCellsPerAxis = 16;
 constexpr int kBuckets = RSDET_MAX_LEVELS * kCellsPerAxis * kCellsPerAxis;
 
-__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, int K, int* __restrict__ order,
-                                                         int32_t* __restrict__ levels_out) {
+__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, const RoiGeom* __restrict__ geoms,
+                                                         int K, int* __restrict__ order, int32_t* __restrict__ levels_out) {
     __shared__ int s_hist[kBuckets];
     __shared__ int s_warp[32];
     const int tid = threadIdx.x;
@@ -243,13 +256,12 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     __syncthreads();
     auto bucket_of = [&](int i, int& lvl) {
         const float* r = rois + (size_t)i * 6;
-        RoiGeom g = roi_geometry(r, L);
-        lvl = g.level;
+        lvl = geoms[i].level;
         int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
         int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
         // boustrophedon rows: neighbouring buckets are neighbouring cells
         if (cy & 1) cx = kCellsPerAxis - 1 - cx;
-        return (g.level * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
     };
     for (int i = tid; i < K; i += 1024) {
         int lvl;
@@ -315,6 +327,38 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         }
     }
     __syncthreads();
+    if (cap == 16 || cap == 4) {
+        // A2 (fast): cap lanes per bin, everything in registers.  Each lane walks the cap lanes of its bin with
+        // warp shuffles (uniform trip count): it is a LEADER if no earlier live lane hits the same pixel, and it
+        // sums the weights of all live lanes on its pixel in lane order; a ballot of the leaders gives each
+        // one its slot in the bin's compacted list.
+        const int lane = tid & 31;
+        const int rounds = (ntaps + kRoiThreads - 1) / kRoiThreads;
+        for (int rd = 0; rd < rounds; rd++) {
+            const int t = rd * kRoiThreads + tid;
+            const bool in = t < ntaps;
+            const int b = in ? t / cap : 0, j = in ? t - b * cap : 0;
+            const int o = in ? s_off[t] : -1;
+            const float w = in ? s_w[t] : 0.f;
+            const bool live = in && w != 0.f;
+            const int seg = lane & ~(cap - 1);                        // first lane of my bin inside the warp
+            bool leader = live;
+            float wsum = 0.f;
+            for (int i = 0; i < cap; i++) {                           // same trip count on every lane
+                const int oi = __shfl_sync(0xffffffffu, o, seg + i);
+                const float wi = __shfl_sync(0xffffffffu, w, seg + i);
+                const bool same = live && wi != 0.f && oi == o;
+                if (same && i < (lane - seg)) leader = false;
+                if (same) wsum += wi;
+            }
+            const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+            const unsigned segmask = ((1u << cap) - 1u) << seg;       // cap is 4 or 16 here
+            if (leader) s_list[b * cap + __popc(leaders & segmask & ((1u << lane) - 1u))] = make_int2(o, __float_as_int(wsum));
+            if (in && j == 0) s_cnt[b] = __popc(leaders & segmask);
+        }
+        __syncthreads();
+        return;
+    }
     // A2a: one thread per tap: a tap is a LEADER if its weight is non-zero and no earlier tap of the bin
     // hits the same pixel; a leader collects the weights of its later duplicates (fixed order).
     for (int t = tid; t < ntaps; t += kRoiThreads) {
@@ -349,8 +393,8 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
 // the second channel quad is an immediate +512 B off the same address.
 template <int QPT>
 __global__ void __launch_bounds__(kRoiThreads, 4)
-roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K, float* __restrict__ out,
-                     int32_t* __restrict__ levels_out) {
+roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, const RoiGeom* __restrict__ geoms,
+                     int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x;
@@ -367,14 +411,17 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
-    if (tid == 0) {
-        s_g = roi_geometry(rois + (size_t)roi * 6, L);
-        if (levels_out && !order && blockIdx.y == 0) levels_out[roi] = s_g.level;
+    if (!geoms) {
+        if (tid == 0) {
+            s_g = roi_geometry(rois + (size_t)roi * 6, L);
+            if (levels_out && blockIdx.y == 0) levels_out[roi] = s_g.level;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const RoiGeom g = s_g;
+    const RoiGeom g = geoms ? geoms[roi] : s_g;
     const int H = L.H[g.level], W = L.W[g.level];
-    build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);   // the scratch is dead after its final barrier
+    if (L.dbg_skip_main < 2) build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);   // the scratch is dead after its final barrier
+    if (L.dbg_skip_main) { for (int b = tid; b < nbins; b += kRoiThreads) s_cnt[b] = 0; __syncthreads(); }
 
     const int lanes = QPT == 2 ? 32 : Qc;                  // threads per bin group
     const int groups = kRoiThreads / lanes;
@@ -508,6 +555,7 @@ roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const
     const RoiGeom g = s_g;
     const int H = L.H[g.level], W = L.W[g.level];
     build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, 1, g.batch * H * W);  // entries = global pixel-row index
+    if (L.dbg_skip_main) { for (int b = tid; b < nbins; b += kRoiThreads) s_cnt[b] = 0; __syncthreads(); }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // scratch (generic writes) -> TMA writes
 
     const CUtensorMap* map = &maps.m[g.level];
@@ -616,8 +664,8 @@ roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const
 // channel quad (red.global.add.v4.f32) into the channels-last accumulator.
 template <int QPT>
 __global__ void __launch_bounds__(kRoiThreads, 4)
-roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, int K,
-                     const float* __restrict__ grad_out) {
+roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, const RoiGeom* __restrict__ geoms,
+                     int K, const float* __restrict__ grad_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x;
@@ -633,9 +681,11 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
-    if (tid == 0) s_g = roi_geometry(rois + (size_t)roi * 6, L);
-    __syncthreads();
-    const RoiGeom g = s_g;
+    if (!geoms) {
+        if (tid == 0) s_g = roi_geometry(rois + (size_t)roi * 6, L);
+        __syncthreads();
+    }
+    const RoiGeom g = geoms ? geoms[roi] : s_g;
     const int H = L.H[g.level], W = L.W[g.level];
     build_tap_lists(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);
 
@@ -766,6 +816,7 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
     L.num_levels = c->num_levels; L.batch = c->batch; L.C = c->channels;
     L.PH = c->pooled_h; L.PW = c->pooled_w; L.sampling_ratio = c->sampling_ratio; L.version = c->version;
     L.extend_w = c->extend_w; L.extend_h = c->extend_h; L.finest_scale = c->finest_scale;
+    { const char* e = getenv("RSDET_ROI_DBG_SKIP_MAIN"); L.dbg_skip_main = e ? atoi(e) : 0; }
     for (int l = 0; l < RSDET_MAX_LEVELS; l++) {
         L.feat[l] = nullptr; L.grad[l] = nullptr;
         L.H[l] = l < c->num_levels ? c->height[l] : 1;
@@ -847,7 +898,7 @@ using namespace rsdet;
 extern "C" size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward) {
     (void)backward;
     if (check_cfg(cfg) != RSDET_OK) return 0;
-    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1);  // processing order
+    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1) + ws_bytes<RoiGeom>(num_rois > 0 ? num_rois : 1);  // order, geometry
     if (cfg->channels_last || !fast_path_ok(cfg)) return b + 256;
     for (int l = 0; l < cfg->num_levels; l++)
         b += ws_bytes<float>((size_t)cfg->batch * cfg->channels * cfg->height[l] * cfg->width[l]);
@@ -879,6 +930,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 0)) return RSDET_EWORKSPACE;
     Workspace ws(workspace, workspace_bytes);
     int* order_ws = ws.take<int>(num_rois);
+    RoiGeom* geoms = ws.take<RoiGeom>(num_rois);
     if (cfg->channels_last) {
         for (int l = 0; l < cfg->num_levels; l++) L.feat[l] = feats_host[l];
     } else {
@@ -899,10 +951,12 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         smem_set = smem;
     }
     // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
+    roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, levels_out);
+    count_launch();
     int* order = nullptr;
     if (num_rois >= 256 && order_ws) {
         order = order_ws;
-        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, levels_out);
+        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
         count_launch();
     }
     if (tma_path_ok(cfg)) {
@@ -927,9 +981,9 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     const int Q = quads_per_chunk(cfg->channels);
     dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
     if (cfg->channels % 256 == 0)
-        roi_align_fwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, out, levels_out);
+        roi_align_fwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, geoms, num_rois, out, nullptr);
     else
-        roi_align_fwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, out, levels_out);
+        roi_align_fwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, geoms, num_rois, out, nullptr);
     count_launch();
     return cuda_status();
 }
@@ -950,6 +1004,7 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
     if (workspace_bytes < rsdet_roi_align_rotated_workspace_bytes(cfg, num_rois, 1)) return RSDET_EWORKSPACE;
     Workspace ws(workspace, workspace_bytes);
     int* order_ws = ws.take<int>(num_rois > 0 ? num_rois : 1);
+    RoiGeom* geoms = ws.take<RoiGeom>(num_rois > 0 ? num_rois : 1);
     if (direct) {
         for (int l = 0; l < cfg->num_levels; l++) acc[l] = grad_feats_host[l];
     } else {
@@ -979,16 +1034,18 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
                 cudaFuncSetAttribute(roi_align_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 smem_set = smem;
             }
+            roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, nullptr);
+            count_launch();
             int* order = nullptr;
             if (num_rois >= 256) {
                 order = order_ws;
-                roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, num_rois, order, nullptr);
+                roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
                 count_launch();
             }
             int Q = quads_per_chunk(cfg->channels);
             dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
-            if (cfg->channels % 256 == 0) roi_align_bwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, grad_out);
-            else roi_align_bwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, num_rois, grad_out);
+            if (cfg->channels % 256 == 0) roi_align_bwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, geoms, num_rois, grad_out);
+            else roi_align_bwd_kernel<1><<<grid, kRoiThreads, smem, st>>>(L, rois, order, geoms, num_rois, grad_out);
         }
         count_launch();
     }
