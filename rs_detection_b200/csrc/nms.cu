@@ -272,6 +272,40 @@ segment_table_kernel(const int32_t* __restrict__ label_sorted, int n_max, const 
     }
 }
 
+// segment table straight from per-class live counts (multiclass path): empty classes are skipped
+__global__ void __launch_bounds__(1024)
+segments_from_counts_kernel(const int* __restrict__ counts, int C, double thr, SegTable tb) {
+    __shared__ long long s_warp[32];
+    const int tid = threadIdx.x;
+    long long carry_n = 0, carry_s = 0, carry_t = 0, carry_w = 0;
+    for (int base = 0; base < C; base += 1024) {
+        const int c = base + tid;
+        const long long ns = c < C ? counts[c] : 0;
+        const long long T = (ns + 63) / 64;
+        long long tn, ts, tt, tw;
+        const long long en = block_excl_scan(ns, s_warp, &tn);
+        const long long es = block_excl_scan(ns > 0 ? 1 : 0, s_warp, &ts);
+        const long long et = block_excl_scan(T * (T + 1) / 2, s_warp, &tt);
+        const long long ew = block_excl_scan(ns * T, s_warp, &tw);
+        if (ns > 0) {
+            const int sidx = (int)(carry_s + es);
+            tb.seg_start[sidx] = (int)(carry_n + en);
+            tb.tile_pref[sidx] = carry_t + et;
+            tb.mask_off[sidx] = carry_w + ew;
+            tb.seg_thr[sidx] = thr;
+        }
+        carry_n += tn; carry_s += ts; carry_t += tt; carry_w += tw;
+    }
+    if (tid == 0) {
+        const int nseg = (int)carry_s;
+        tb.seg_start[nseg] = (int)carry_n;
+        tb.tile_pref[nseg] = carry_t;
+        tb.mask_off[nseg] = carry_w;
+        tb.hdr[0] = nseg; tb.hdr[1] = (int)carry_n; tb.hdr[2] = 0;
+        *(long long*)(tb.hdr + 4) = carry_t;
+    }
+}
+
 // ----------------------------------------------------------------------------- mask tiles
 template <int KIND>
 __global__ void __launch_bounds__(kNmsThreads)
@@ -704,6 +738,10 @@ struct NmsArgs {
     const float* shared_boxes = nullptr;
     int n_shared = 0;
     int cand_per_box = 1;
+    // labels are class ids 0..num_classes-1 whose live counts are already known on the device: the segment
+    // table is an exclusive scan of the counts (no boundary search over the sorted labels)
+    const int* class_counts = nullptr;
+    int num_classes = 0;
 };
 
 static size_t box_bytes(int kind) {
@@ -847,10 +885,14 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     // 3. per-box preprocessing in sorted order, segment table
     const bool shared = a.shared_boxes != nullptr;
     if (shared && (a.kind > RSDET_NMS_ROTATED_GE || a.n_shared <= 0 || a.n_shared > n)) return RSDET_EINVAL;
-    cudaMemsetAsync(tb.hdr, 0, 64 * sizeof(int), st);
-    dispatch_kind(a, idx_ls, shared ? nullptr : boxes, label_sorted, tb, mask, st, false, starts_unsorted);
-    segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr, tb,
-                                             starts_unsorted);
+    if (a.class_counts && shared) {
+        segments_from_counts_kernel<<<1, 1024, 0, st>>>(a.class_counts, a.num_classes, a.thr, tb);
+    } else {
+        cudaMemsetAsync(tb.hdr, 0, 64 * sizeof(int), st);
+        dispatch_kind(a, idx_ls, shared ? nullptr : boxes, label_sorted, tb, mask, st, false, starts_unsorted);
+        segment_table_kernel<<<1, 1024, 0, st>>>(a.labels ? label_sorted : nullptr, n, a.n_dev, a.thr, a.thr_per_label, a.num_thr,
+                                                 tb, starts_unsorted);
+    }
     count_launch();
     if (shared) {
         // 4'. one directed decision matrix for all classes, 5'. per-class scans through it
@@ -920,9 +962,18 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
 // ----------------------------------------------------------------------------- multiclass_nms_rotated
 // nms_rotated.py:562-575: expand (n, C) candidates in row-major order; invalid ones get score -inf and
 // label INT_MAX so that both sorts push them behind the *n_valid live rows.
+constexpr int kMcHist = 1024;  // classes counted through a shared-memory histogram
+
 __global__ void mc_expand_kernel(const float* __restrict__ bboxes, int bbox_dim, const float* __restrict__ scores, int n, int C,
                                  float score_thr, const float* __restrict__ factors, float* __restrict__ cbox,
-                                 float* __restrict__ cscore, int32_t* __restrict__ clabel, int* __restrict__ n_valid) {
+                                 float* __restrict__ cscore, int32_t* __restrict__ clabel, int* __restrict__ n_valid,
+                                 int* __restrict__ class_counts) {
+    __shared__ int s_hist[kMcHist];
+    const bool hist = class_counts != nullptr && C <= kMcHist;
+    if (hist) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     bool in = e < n * C;
     int i = in ? e / C : 0, c = in ? e % C : 0;
@@ -938,6 +989,12 @@ __global__ void mc_expand_kernel(const float* __restrict__ bboxes, int bbox_dim,
     }
     unsigned m = __ballot_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, __popc(m));
+    if (hist) {
+        if (valid) atomicAdd(&s_hist[c], 1);
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&class_counts[i], s_hist[i]);
+    }
 }
 
 // nms_rotated.py:577-596: kept candidates arrive in descending-score order; apply the max_num slice.
@@ -992,7 +1049,7 @@ extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const i
 extern "C" size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes) {
     size_t cap = (size_t)(n > 0 ? n : 1) * (size_t)(num_classes > 0 ? num_classes : 1);
     return ws_bytes<float>(cap * 5) + ws_bytes<float>(cap) + ws_bytes<int32_t>(cap) + ws_bytes<int>(64) +
-           ws_bytes<int64_t>(cap) + ws_bytes<int32_t>(64) + nms_ws_bytes(RSDET_NMS_ROTATED, (int)cap);
+           ws_bytes<int64_t>(cap) + ws_bytes<int32_t>(64) + ws_bytes<int>(kMcHist) + nms_ws_bytes(RSDET_NMS_ROTATED, (int)cap);
 }
 
 extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_dim, const float* multi_scores, int n,
@@ -1018,11 +1075,15 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
     int* n_valid = ws.take<int>(64);
     int64_t* kidx = ws.take<int64_t>(cap);
     int32_t* nkeep = ws.take<int32_t>(64);
+    int* class_counts = ws.take<int>(kMcHist);
     void* sub = ws.base + ws.used;
     size_t sub_bytes = workspace_bytes - ws.used;
+    const bool use_counts = bbox_dim == 5 && num_classes <= kMcHist;
     cudaMemsetAsync(n_valid, 0, sizeof(int), st);
+    if (use_counts) cudaMemsetAsync(class_counts, 0, sizeof(int) * num_classes, st);
     mc_expand_kernel<<<ceil_div(cap, 256), 256, 0, st>>>(multi_bboxes, bbox_dim, multi_scores, n, num_classes, score_thr,
-                                                        score_factors, cbox, cscore, clabel, n_valid);
+                                                        score_factors, cbox, cscore, clabel, n_valid,
+                                                        use_counts ? class_counts : nullptr);
     count_launch();
     NmsArgs a{RSDET_NMS_ROTATED, cbox, cscore, clabel, cap, n_valid, (double)iou_thr, nullptr, 0, nullptr, nullptr, kidx, nkeep};
     a.label_bits = 1;
@@ -1031,6 +1092,7 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
         a.shared_boxes = multi_bboxes;
         a.n_shared = n;
         a.cand_per_box = num_classes;
+        if (use_counts) { a.class_counts = class_counts; a.num_classes = num_classes; }
     }
     int rc = nms_run(a, sub, sub_bytes, st);
     if (rc != RSDET_OK) return rc;
