@@ -48,7 +48,7 @@ struct LevelSet {
 };
 
 // ---------------------------------------------------------------------------------- transposes
-// (N, C, HW) <-> (N, HW, C), 32x32 tiles through padded shared memory.
+// (N, C, HW) <-> (N, HW, C), 64x64 tiles through padded shared memory.
 struct TransposeJob {
     const float* src[RSDET_MAX_LEVELS];
     float* dst[RSDET_MAX_LEVELS];
@@ -57,44 +57,59 @@ struct TransposeJob {
     int num_levels, N, C;
 };
 
+// 64(channels) x 64(pixels) tiles, 16-byte global accesses on both sides: a thread reads a float4 along the
+// source's contiguous dimension, scatters it into a padded shared tile, and writes a float4 along the
+// destination's contiguous dimension.  Falls back to scalar accesses at ragged edges / unaligned bases.
 template <bool TO_NHWC>
 __global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][65];
     int t = blockIdx.x;
     int l = 0;
     while (l + 1 < job.num_levels && t >= job.tile_begin[l + 1]) l++;
     t -= job.tile_begin[l];
     const int HW = job.HW[l], C = job.C;
-    const int tiles_hw = ceil_div(HW, 32), tiles_c = ceil_div(C, 32);
+    const int tiles_hw = ceil_div(HW, 64), tiles_c = ceil_div(C, 64);
     const int n = t / (tiles_hw * tiles_c);
     const int r = t % (tiles_hw * tiles_c);
-    const int hw0 = (r % tiles_hw) * 32, c0 = (r / tiles_hw) * 32;
+    const int hw0 = (r % tiles_hw) * 64, c0 = (r / tiles_hw) * 64;
     const float* src = job.src[l] + (size_t)n * C * HW;
     float* dst = job.dst[l] + (size_t)n * C * HW;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (TO_NHWC) {  // src [C][HW] -> dst [HW][C]
+    const int tid = threadIdx.x;
+    // source: rows of `SR` index, contiguous along `SC`; destination the other way round
+    const int srcRows = TO_NHWC ? C : HW, srcCols = TO_NHWC ? HW : C;      // src[row * srcCols + col]
+    const int r0 = TO_NHWC ? c0 : hw0, q0 = TO_NHWC ? hw0 : c0;            // tile origin (row, col) in the source
+    const bool vec_in = (srcCols & 3) == 0 && ((size_t)src & 15) == 0;
+    const bool vec_out = (srcRows & 3) == 0 && ((size_t)dst & 15) == 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int c = c0 + ty + 8 * k, hw = hw0 + tx;
-            if (c < C && hw < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)c * HW + hw);
+    for (int k = 0; k < 4; k++) {
+        const int idx = tid + 256 * k;            // 1024 float4 slots: 64 rows x 16 float4
+        const int rr = idx >> 4, cc = (idx & 15) * 4;
+        const int gr = r0 + rr, gc = q0 + cc;
+        if (gr < srcRows) {
+            if (vec_in && gc + 3 < srcCols) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * srcCols + gc));
+                tile[rr][cc] = v.x; tile[rr][cc + 1] = v.y; tile[rr][cc + 2] = v.z; tile[rr][cc + 3] = v.w;
+            } else {
+                for (int e = 0; e < 4; e++)
+                    if (gc + e < srcCols) tile[rr][cc + e] = __ldg(src + (size_t)gr * srcCols + gc + e);
+            }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    // destination: dst[col * srcRows + row]; a float4 covers 4 consecutive source rows of one source column
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int hw = hw0 + ty + 8 * k, c = c0 + tx;
-            if (c < C && hw < HW) dst[(size_t)hw * C + c] = tile[tx][ty + 8 * k];
-        }
-    } else {  // src [HW][C] -> dst [C][HW]
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int hw = hw0 + ty + 8 * k, c = c0 + tx;
-            if (c < C && hw < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)hw * C + c);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int c = c0 + ty + 8 * k, hw = hw0 + tx;
-            if (c < C && hw < HW) dst[(size_t)c * HW + hw] = tile[tx][ty + 8 * k];
+    for (int k = 0; k < 4; k++) {
+        const int idx = tid + 256 * k;
+        const int cc = idx >> 4, rr = (idx & 15) * 4;  // cc = source column (dest row), rr = first of 4 source rows
+        const int gc = q0 + cc, gr = r0 + rr;
+        if (gc < srcCols) {
+            if (vec_out && gr + 3 < srcRows) {
+                const float4 v = make_float4(tile[rr][cc], tile[rr + 1][cc], tile[rr + 2][cc], tile[rr + 3][cc]);
+                *reinterpret_cast<float4*>(dst + (size_t)gc * srcRows + gr) = v;
+            } else {
+                for (int e = 0; e < 4; e++)
+                    if (gr + e < srcRows) dst[(size_t)gc * srcRows + gr + e] = tile[rr + e][cc];
+            }
         }
     }
 }
@@ -107,7 +122,7 @@ static int launch_transpose(bool to_nhwc, const float* const* src, float* const*
     for (int l = 0; l < L; l++) {
         job.src[l] = src[l]; job.dst[l] = dst[l]; job.HW[l] = H[l] * W[l];
         job.tile_begin[l] = total;
-        total += N * ceil_div(job.HW[l], 32) * ceil_div(C, 32);
+        total += N * ceil_div(job.HW[l], 64) * ceil_div(C, 64);
     }
     job.tile_begin[L] = total;
     if (total == 0) return RSDET_OK;
