@@ -90,7 +90,8 @@ int rsdet_assign_wrt_overlaps(const float* overlaps, int num_gts, int n, float p
  *   keep_score_idx  int64 (n): kept ORIGINAL indices in descending score order (order_t[keep], poly_nms;
  *                              py_cpu_nms_poly_fast's python list)
  *   num_keep      int32 (1) device counter
- * Score ties are broken by lower original index first (the reference leaves this unspecified). */
+ * Score ties are broken by lower original index first (the reference leaves this unspecified).
+ * Limit: n <= 2^18 boxes per call (RSDET_ELIMIT above; the workspace query then returns 0). */
 size_t rsdet_nms_workspace_bytes(int kind, int n);
 int rsdet_nms(int kind, const void* dets, const void* scores, const int32_t* labels, int n, double thr,
               const double* thr_per_label, int num_thr, uint8_t* keep_mask, int64_t* keep_sorted_idx,
@@ -103,7 +104,7 @@ int rsdet_nms(int kind, const void* dets, const void* scores, const int32_t* lab
  *   multi_bboxes : (n,5) or (n,5*(num_classes+1)) as bbox_dim says;  multi_scores : (n,num_classes+1)
  *   score_factors: (n) or NULL
  *   out_dets (cap,6) [cx,cy,w,h,theta,score], out_labels int32 (cap), out_count int32 (1);
- *   cap = n*num_classes rows must be available. */
+ *   cap = n*num_classes rows must be available; n*num_classes <= 2^20 (RSDET_ELIMIT above). */
 size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes);
 int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_dim, const float* multi_scores, int n,
                                  int num_classes, float score_thr, float iou_thr, int max_num,

@@ -742,6 +742,7 @@ struct NmsArgs {
     // table is an exclusive scan of the counts (no boundary search over the sorted labels)
     const int* class_counts = nullptr;
     int num_classes = 0;
+    size_t mask_words = 0;  // caller-proved bound on the mask size (0 = worst case n * ceil(n/64))
 };
 
 static size_t box_bytes(int kind) {
@@ -753,7 +754,10 @@ static size_t box_bytes(int kind) {
     }
 }
 
-size_t nms_ws_bytes(int kind, int n) {
+constexpr int kMaxNmsBoxes = 1 << 18;  // dense n x n/64 mask: 8.6 GB at the limit; the remv vector fits shared memory
+
+// mask_words = 0: worst case (every box in one label group)
+size_t nms_ws_bytes(int kind, int n, size_t mask_words = 0) {
     size_t N = (size_t)(n > 0 ? n : 1);
     size_t b = 0;
     b += 2 * ws_bytes<unsigned long long>(N);  // score keys (double buffer)
@@ -762,7 +766,7 @@ size_t nms_ws_bytes(int kind, int n) {
     b += align256(box_bytes(kind) * N);
     b += ws_bytes<int32_t>(N);                                         // label_sorted
     b += ws_bytes<int>(64) + ws_bytes<int>(N + 2) + 2 * ws_bytes<long long>(N + 2) + ws_bytes<double>(N + 1);
-    b += ws_bytes<unsigned long long>(N * ((N + 63) / 64));            // mask (worst case: one segment)
+    b += ws_bytes<unsigned long long>(mask_words ? mask_words : N * ((N + 63) / 64));  // mask (worst case: one group)
     b += 3 * ws_bytes<uint8_t>(N);                                     // keep_sorted, keep_mask tmp, flags
     b += 2 * ws_bytes<int64_t>(N);                                     // vals, scratch index output
     b += ws_bytes<int>(64) + ws_bytes<int>(kFastSegs);                 // scratch count, unordered segment starts
@@ -807,8 +811,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         return cuda_status();
     }
     if (!a.dets || !a.scores) return RSDET_EINVAL;
-    if (n > (1 << 20)) return RSDET_ELIMIT;  // remv vector must fit shared memory (n/64 words)
-    if (workspace_bytes < nms_ws_bytes(a.kind, n)) return RSDET_EWORKSPACE;
+    if (n > (a.mask_words ? (1 << 20) : kMaxNmsBoxes)) return RSDET_ELIMIT;
+    if (workspace_bytes < nms_ws_bytes(a.kind, n, a.mask_words)) return RSDET_EWORKSPACE;
     const bool f64 = a.kind == RSDET_NMS_MERGE || a.kind == RSDET_NMS_HBB;
     const size_t N = (size_t)n;
 
@@ -829,7 +833,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     tb.tile_pref = ws.take<long long>(N + 2);
     tb.mask_off = ws.take<long long>(N + 2);
     tb.seg_thr = ws.take<double>(N + 1);
-    unsigned long long* mask = ws.take<unsigned long long>(N * ((N + 63) / 64));
+    unsigned long long* mask = ws.take<unsigned long long>(a.mask_words ? a.mask_words : N * ((N + 63) / 64));
     uint8_t* keep_sorted = ws.take<uint8_t>(N);
     uint8_t* keep_tmp = ws.take<uint8_t>(N);
     uint8_t* flags = ws.take<uint8_t>(N);
@@ -1037,7 +1041,7 @@ extern "C" int rsdet_iou_poly_pairs(const double* polys1, const double* polys2, 
     return cuda_status();
 }
 
-extern "C" size_t rsdet_nms_workspace_bytes(int kind, int n) { return nms_ws_bytes(kind, n); }
+extern "C" size_t rsdet_nms_workspace_bytes(int kind, int n) { return n > kMaxNmsBoxes ? 0 : nms_ws_bytes(kind, n); }
 
 extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const int32_t* labels, int n, double thr,
                          const double* thr_per_label, int num_thr, uint8_t* keep_mask, int64_t* keep_sorted_idx,
@@ -1046,10 +1050,18 @@ extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const i
     return nms_run(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// every class holds at most n candidates -> the block-sparse mask needs at most C * n * ceil(n/64) words
+static size_t mc_mask_words(int n, int num_classes) {
+    size_t N = (size_t)(n > 0 ? n : 1);
+    return (size_t)(num_classes > 0 ? num_classes : 1) * N * ((N + 63) / 64);
+}
+
 extern "C" size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes) {
     size_t cap = (size_t)(n > 0 ? n : 1) * (size_t)(num_classes > 0 ? num_classes : 1);
+    if (cap > (1u << 20) || n > kMaxNmsBoxes) return 0;  // the call itself answers RSDET_ELIMIT
     return ws_bytes<float>(cap * 5) + ws_bytes<float>(cap) + ws_bytes<int32_t>(cap) + ws_bytes<int>(64) +
-           ws_bytes<int64_t>(cap) + ws_bytes<int32_t>(64) + ws_bytes<int>(kMcHist) + nms_ws_bytes(RSDET_NMS_ROTATED, (int)cap);
+           ws_bytes<int64_t>(cap) + ws_bytes<int32_t>(64) + ws_bytes<int>(kMcHist) +
+           nms_ws_bytes(RSDET_NMS_ROTATED, (int)cap, mc_mask_words(n, num_classes));
 }
 
 extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_dim, const float* multi_scores, int n,
@@ -1065,7 +1077,7 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
     }
     if (!multi_bboxes || !multi_scores || !out_dets || !out_labels) return RSDET_EINVAL;
     long long capll = (long long)n * num_classes;
-    if (capll > (1 << 20)) return RSDET_ELIMIT;
+    if (capll > (1 << 20) || n > kMaxNmsBoxes) return RSDET_ELIMIT;
     int cap = (int)capll;
     if (workspace_bytes < rsdet_multiclass_nms_rotated_workspace_bytes(n, num_classes)) return RSDET_EWORKSPACE;
     Workspace ws(workspace, workspace_bytes);
@@ -1086,6 +1098,7 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
                                                         use_counts ? class_counts : nullptr);
     count_launch();
     NmsArgs a{RSDET_NMS_ROTATED, cbox, cscore, clabel, cap, n_valid, (double)iou_thr, nullptr, 0, nullptr, nullptr, kidx, nkeep};
+    a.mask_words = mc_mask_words(n, num_classes);
     a.label_bits = 1;
     while ((1 << a.label_bits) - 1 < num_classes) a.label_bits++;  // classes 0..C-1, dead rows -> all ones
     if (bbox_dim == 5) {  // class-agnostic boxes: pairwise decisions are shared by all classes

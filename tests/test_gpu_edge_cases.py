@@ -1,0 +1,82 @@
+"""Edge cases through the C ABI: score ties, degenerate boxes, far-from-origin coordinates, size limits."""
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_score_ties_break_by_lower_index(cuda, oracle):
+    from rs_detection_b200.jdet.ops.nms_rotated import ml_nms_rotated, nms_rotated
+    n = 2000
+    d = W.rotated_boxes(n, 3, canvas=500, smin=16, smax=100)
+    s = np.round(W.distinct_scores(n, 3), 2)  # ~100 distinct values -> heavy ties
+    assert len(np.unique(s)) < 200
+    lab = np.random.default_rng(0).integers(0, 4, n)
+    assert np.array_equal(nms_rotated(_t(d), _t(s), 0.2).cpu().numpy(), oracle.nms_rotated(d, s, 0.2))
+    assert np.array_equal(ml_nms_rotated(_t(d), _t(s), _t(lab), 0.2).cpu().numpy(), oracle.ml_nms_rotated(d, s, lab, 0.2))
+
+
+def test_identical_and_degenerate_boxes(cuda, oracle):
+    from rs_detection_b200.jdet.ops import box_iou_rotated
+    from rs_detection_b200.jdet.ops.nms_rotated import nms_rotated
+    b = W.rotated_boxes(300, 9, canvas=200, smin=16, smax=64)
+    b[50:100] = b[0:50]                      # exact duplicates (IoU == 1 up to rounding)
+    b[100:110, 2] = 0.0                      # zero width
+    b[110:120, 2:4] = 1e-9                   # area < 1e-14
+    b[120:130, 3] = -5.0                     # negative height (area < 0 -> IoU 0 in the reference)
+    b[130:140, 4] = 37.0                     # angle far outside (-pi/2, pi/2)
+    got = box_iou_rotated(_t(b), _t(b)).cpu().numpy()
+    want = oracle.box_iou_rotated(b, b, 0, 1)
+    assert np.array_equal(got, want)
+    s = W.distinct_scores(300, 9)
+    for thr in (0.0, 0.3, 0.999):
+        assert np.array_equal(nms_rotated(_t(b), _t(s), thr).cpu().numpy(), oracle.nms_rotated(b, s, thr))
+
+
+def test_far_from_origin_coordinates(cuda, oracle):
+    """FAIR1M scenes reach ~15k px: the pair midpoint shift keeps the float IoU exact there too."""
+    from rs_detection_b200.jdet.ops import box_iou_rotated_v1
+    P = W.rotated_boxes(1500, 4, canvas=600, smin=8, smax=128)
+    G = W.jittered_copies(P, 200, 5)
+    for off in (0.0, 14000.0, -9000.0):
+        p, g = P.copy(), G.copy()
+        p[:, :2] += off; g[:, :2] += off
+        assert np.array_equal(box_iou_rotated_v1(_t(g), _t(p)).cpu().numpy(), oracle.box_iou_rotated(g, p, 1, 1))
+
+
+def test_limits_and_errors(cuda):
+    from rs_detection_b200 import _lib, core
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    # n * classes above 2^20 candidates is refused (RSDET_ELIMIT), not silently truncated
+    n, C = 70000, 16
+    with pytest.raises(RuntimeError, match="limit"):
+        core.multiclass_nms_rotated(torch.zeros((n, 5), device="cuda"), torch.zeros((n, C + 1), device="cuda"), 0.1, 0.1, 100)
+    with pytest.raises(ValueError):
+        core.multiclass_nms_rotated(torch.zeros((10, 7), device="cuda"), torch.zeros((10, 3), device="cuda"), 0.1, 0.1, 100)
+    # one class, one box, nothing suppressed
+    d, l = multiclass_nms_rotated(_t(np.array([[5, 5, 4, 2, 0.1]], np.float32)), _t(np.array([[0.1, 0.9]], np.float32)), 0.05,
+                                  dict(iou_thr=0.1), 10)
+    assert tuple(d.shape) == (1, 6) and l.tolist() == [0]
+    # undersized workspace is reported, not overrun
+    L = _lib.load()
+    b = torch.zeros((100, 5), device="cuda"); s = torch.zeros((100,), device="cuda")
+    ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = L.rsdet_nms(0, b.data_ptr(), s.data_ptr(), None, 100, 0.1, None, 0, None, None, None, None, ws.data_ptr(), 1024, None)
+    assert rc == -2
+
+
+def test_multiclass_class_specific_boxes_many_classes(cuda, oracle):
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    n, C = 400, 37
+    sc = W.class_scores(n, C, 8, logit_scale=2.0)
+    bb = W.rotated_boxes(n, 41, canvas=300, smin=16, smax=120)
+    wd, wl = oracle.multiclass_nms_rotated(bb, sc, 0.02, dict(iou_thr=0.3), 300)
+    gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 0.02, dict(iou_thr=0.3), 300)
+    assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
