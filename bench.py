@@ -322,6 +322,13 @@ def run_ours(args, rank, world, local_rank):
     props = tiles[0][1][:2000, 1:].contiguous()
     ms_iou = timed(lambda: core.assign_wrt_overlaps(core.box_iou_rotated(gt, props, 1, True), 0.5, 0.5, 0.5, False), reps)
     del feats_cl
+    # fused head tail (softmax + delta decode + threshold + obb2poly + compaction), 4000 RoIs
+    gen = torch.Generator(device=dev).manual_seed(1)
+    cls_logits = torch.randn((K_ROIS, NUM_CLASSES + 1), device=dev, generator=gen) * 2.0
+    deltas = torch.randn((K_ROIS, 5), device=dev, generator=gen) * 0.5
+    rois5 = tiles[0][1][:, 1:].contiguous()
+    ms_head = timed(lambda: core.oriented_head_results(rois5, cls_logits, deltas, NUM_CLASSES, True, [0.] * 5,
+                                                       [0.1, 0.1, 0.2, 0.2, 0.1], SCORE_THR, 1.0), reps)
 
     # ---- roofline of the dominant HBM kernel: roi_align_fwd_kernel (one launch per tile)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -434,7 +441,8 @@ def run_ours(args, rank, world, local_rank):
                 "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel,
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
-                "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3)},
+                "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3),
+                "head_tail_4000x10_ms": ms_head, "head_tail_rois_per_s": K_ROIS / (ms_head * 1e-3)},
         }
         print(json.dumps(line))
     if world > 1:

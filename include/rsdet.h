@@ -169,6 +169,17 @@ int rsdet_oriented_head_results(const float* rois5, const float* cls_score, cons
                                 const float* scale_factor4_host, float score_thresh, int apply_softmax, float* out_dets,
                                 int64_t* out_labels, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- evaluation matching
+ * data/devkits/voc_eval.py:236-318 (voc_eval_dota), one class: detections (nd,8) fp64 polygons ALREADY in
+ * descending-confidence order with their image index det_img (nd); ground truths (num_gts,8) grouped by
+ * image (gt_start[num_imgs+1]), gt_difficult uint8 (num_gts).  Per detection: hbb prefilter (the reference's
+ * +1 convention), iou_poly on the survivors, first maximum -> ovmax (nd, -inf if none), jmax (nd, global gt
+ * index or -1); then the TP/FP marking of :303-311 (a gt is claimed by its highest-confidence match):
+ * tp, fp uint8 (nd).  claim: int32 (num_gts) scratch. */
+int rsdet_voc_match(const double* det_polys, const int32_t* det_img, int nd, const double* gt_polys, const int32_t* gt_start,
+                    const uint8_t* gt_difficult, int num_imgs, int num_gts, double ovthresh, double* ovmax, int32_t* jmax,
+                    int32_t* claim, uint8_t* tp, uint8_t* fp, void* stream);
+
 /* counters for bench.py's `gpu_launches`: number of kernels this library has launched so far */
 unsigned long long rsdet_launch_count(void);
 

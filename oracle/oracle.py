@@ -446,3 +446,45 @@ def oriented_head_get_bboxes(rois, cls_score, bbox_pred, scale_factor=None, mean
         return np.zeros((0, 9), np.float32), np.zeros((0,), np.int64)
     dets = np.concatenate([obb2poly(bb[valid]), sc[valid][:, None]], 1)
     return dets.astype(np.float32), np.nonzero(valid)[1].astype(np.int64)
+
+
+# ----------------------------------------------------------------------------- voc_eval
+def voc_match(dets, gts, ovthresh=0.5):
+    """TP/FP marking loop of voc_eval_dota, python/jdet/data/devkits/voc_eval.py:236-311, with `iou_poly`
+    (Shapely stand-in, PARITY UNPINNED).  dets (nd,10) [img_id, 8 coords, confidence]."""
+    dets = np.array(np.asarray(dets).tolist(), dtype=np.float64).reshape(-1, 10)
+    confidence = dets[:, -1]
+    d8 = dets[:, :-1]
+    sorted_ind = np.argsort(-confidence)
+    d8 = d8[sorted_ind]
+    nd = len(d8)
+    tp, fp = np.zeros(nd), np.zeros(nd)
+    taken = {k: np.zeros(len(np.asarray(gts[k]["difficult"])), bool) for k in gts}
+    for d, det in enumerate(d8):
+        bb = det[1:].astype(float)
+        ovmax, jmax = -np.inf, -1
+        R = gts.get(int(det[0]))
+        BBGT = np.asarray(R["box"], float).reshape(-1, 8) if R is not None else np.zeros((0, 8))
+        if BBGT.size > 0:
+            gx1, gy1 = BBGT[:, 0::2].min(1), BBGT[:, 1::2].min(1)
+            gx2, gy2 = BBGT[:, 0::2].max(1), BBGT[:, 1::2].max(1)
+            bx1, by1, bx2, by2 = bb[0::2].min(), bb[1::2].min(), bb[0::2].max(), bb[1::2].max()
+            iw = np.maximum(np.minimum(gx2, bx2) - np.maximum(gx1, bx1) + 1., 0.)
+            ih = np.maximum(np.minimum(gy2, by2) - np.maximum(gy1, by1) + 1., 0.)
+            inters = iw * ih
+            uni = (bx2 - bx1 + 1.) * (by2 - by1 + 1.) + (gx2 - gx1 + 1.) * (gy2 - gy1 + 1.) - inters
+            keep = np.where(inters / uni > 0)[0]
+            if len(keep) > 0:
+                ov = [iou_poly(BBGT[k], bb) for k in keep]
+                ovmax = np.max(ov)
+                jmax = keep[int(np.argmax(ov))]
+        if ovmax > ovthresh:
+            if not np.asarray(R["difficult"]).astype(bool)[jmax]:
+                if not taken[int(det[0])][jmax]:
+                    tp[d] = 1.
+                    taken[int(det[0])][jmax] = True
+                else:
+                    fp[d] = 1.
+        else:
+            fp[d] = 1.
+    return tp, fp

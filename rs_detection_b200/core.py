@@ -281,6 +281,26 @@ def oriented_head_results(rois5: torch.Tensor, cls_score: torch.Tensor, bbox_pre
     return dets, labels, cnt
 
 
+def voc_match(det_polys: torch.Tensor, det_img: torch.Tensor, gt_polys: torch.Tensor, gt_start: torch.Tensor,
+              gt_difficult: torch.Tensor, ovthresh: float):
+    """detections in descending-confidence order -> (tp uint8 (nd), fp uint8 (nd), ovmax f64 (nd), jmax int32 (nd))."""
+    d = det_polys.to(torch.float64).contiguous()
+    di = det_img.to(torch.int32).contiguous()
+    g = gt_polys.to(torch.float64).contiguous().reshape(-1, 8)
+    gs = gt_start.to(torch.int32).contiguous()
+    gd = gt_difficult.to(torch.uint8).contiguous()
+    nd, ng, ni = d.shape[0], g.shape[0], gs.numel() - 1
+    dev = d.device
+    ovmax = torch.empty((nd,), dtype=torch.float64, device=dev)
+    jmax = torch.empty((nd,), dtype=torch.int32, device=dev)
+    claim = torch.empty((max(ng, 1),), dtype=torch.int32, device=dev)
+    tp = torch.zeros((nd,), dtype=torch.uint8, device=dev)
+    fp = torch.zeros((nd,), dtype=torch.uint8, device=dev)
+    check(load().rsdet_voc_match(ptr(d), ptr(di), nd, ptr(g), ptr(gs), ptr(gd), ni, ng, float(ovthresh), ptr(ovmax), ptr(jmax),
+                                 ptr(claim), ptr(tp), ptr(fp), stream_ptr()), "voc_match")
+    return tp, fp, ovmax, jmax
+
+
 def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     x = _f32(x)
     n, c, h, w = x.shape

@@ -1028,6 +1028,70 @@ __global__ void iou_poly_pairs_kernel(const double* __restrict__ a, const double
     out[i] = iou_poly_d(A, B);
 }
 
+// ----------------------------------------------------------------------------- voc_eval matching
+// voc_eval_dota (python/jdet/data/devkits/voc_eval.py:236-318): for every detection (already in descending
+// confidence order) the best-overlapping ground truth of ITS image: hbb prefilter with the reference's `+1`
+// convention (:262-285), then iou_poly (Shapely in the reference) on the survivors, np.argmax = first maximum.
+// One warp per detection, lanes over the image's ground truths.
+__global__ void voc_best_gt_kernel(const double* __restrict__ det, const int32_t* __restrict__ det_img, int nd,
+                                   const double* __restrict__ gt, const int32_t* __restrict__ gt_start, int num_imgs,
+                                   double* __restrict__ ovmax, int32_t* __restrict__ jmax) {
+    const int d = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (d >= nd) return;
+    const int img = det_img[d];
+    double best = -INFINITY;
+    int bj = 0x7fffffff;
+    if (img >= 0 && img < num_imgs) {
+        const MBox D = Traits<RSDET_NMS_MERGE>::prep(det + (size_t)d * 8);
+        for (int j = gt_start[img] + lane; j < gt_start[img + 1]; j += 32) {
+            const MBox G = Traits<RSDET_NMS_MERGE>::prep(gt + (size_t)j * 8);
+            const double iw = fmax(fmin(G.x2, D.x2) - fmax(G.x1, D.x1) + 1., 0.);
+            const double ih = fmax(fmin(G.y2, D.y2) - fmax(G.y1, D.y1) + 1., 0.);
+            const double inters = iw * ih;
+            const double uni = (D.x2 - D.x1 + 1.) * (D.y2 - D.y1 + 1.) + (G.x2 - G.x1 + 1.) * (G.y2 - G.y1 + 1.) - inters;
+            if (inters / uni > 0) {
+                const double ov = iou_poly_d(G, D);  // iou_func(BBGT_keep[index], bb)
+                if (ov > best) { best = ov; bj = j; }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ob > best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    if (lane == 0) { ovmax[d] = best; jmax[d] = bj == 0x7fffffff ? -1 : bj; }
+}
+
+// the sequential TP/FP marking (:303-311) without the sequence: a ground truth is claimed by the FIRST
+// (highest-confidence) detection that matches it
+__global__ void voc_claim_kernel(const double* __restrict__ ovmax, const int32_t* __restrict__ jmax, const uint8_t* __restrict__ difficult,
+                                 int nd, double thr, int32_t* __restrict__ claim) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nd) return;
+    const int j = jmax[d];
+    if (j >= 0 && ovmax[d] > thr && !difficult[j]) atomicMin(&claim[j], d);
+}
+
+__global__ void voc_mark_kernel(const double* __restrict__ ovmax, const int32_t* __restrict__ jmax, const uint8_t* __restrict__ difficult,
+                                int nd, double thr, const int32_t* __restrict__ claim, uint8_t* __restrict__ tp, uint8_t* __restrict__ fp) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nd) return;
+    const int j = jmax[d];
+    uint8_t t = 0, f = 0;
+    if (j >= 0 && ovmax[d] > thr) {
+        if (!difficult[j]) { if (claim[j] == d) t = 1; else f = 1; }
+    } else f = 1;
+    tp[d] = t;
+    fp[d] = f;
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 }  // namespace rsdet
 
 using namespace rsdet;
@@ -1038,6 +1102,22 @@ extern "C" int rsdet_iou_poly_pairs(const double* polys1, const double* polys2, 
     if (!polys1 || !polys2 || !ious) return RSDET_EINVAL;
     iou_poly_pairs_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(polys1, polys2, n, ious);
     count_launch();
+    return cuda_status();
+}
+
+extern "C" int rsdet_voc_match(const double* det_polys, const int32_t* det_img, int nd, const double* gt_polys,
+                               const int32_t* gt_start, const uint8_t* gt_difficult, int num_imgs, int num_gts, double ovthresh,
+                               double* ovmax, int32_t* jmax, int32_t* claim, uint8_t* tp, uint8_t* fp, void* stream) {
+    if (nd < 0 || num_imgs < 0 || num_gts < 0) return RSDET_EINVAL;
+    if (nd == 0) return RSDET_OK;
+    if (!det_polys || !det_img || !gt_start || !ovmax || !jmax || !claim || !tp || !fp) return RSDET_EINVAL;
+    if (num_gts > 0 && (!gt_polys || !gt_difficult)) return RSDET_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    voc_best_gt_kernel<<<ceil_div(nd, 8), 256, 0, st>>>(det_polys, det_img, nd, gt_polys, gt_start, num_imgs, ovmax, jmax);
+    if (num_gts > 0) fill_i32_kernel<<<ceil_div(num_gts, 256), 256, 0, st>>>(claim, num_gts, 0x7fffffff);
+    voc_claim_kernel<<<ceil_div(nd, 256), 256, 0, st>>>(ovmax, jmax, gt_difficult, nd, ovthresh, claim);
+    voc_mark_kernel<<<ceil_div(nd, 256), 256, 0, st>>>(ovmax, jmax, gt_difficult, nd, ovthresh, claim, tp, fp);
+    count_launch(4);
     return cuda_status();
 }
 

@@ -93,4 +93,17 @@ for nobj in ([2000, 20000] if not a.quick else [2000]):
         row["cpu_kept"] = kk
     out["merge"].append(row)
     print(row, file=sys.stderr)
+# voc_eval matching, 200 images x 100 gts, 60k detections of one class
+rng = np.random.default_rng(0)
+nimg, ngt = 200, 100
+g = W.obb_to_poly64(W.rotated_boxes(nimg * ngt, 9, canvas=1024, smin=12, smax=90, dtype=np.float64))
+gt_start = torch.arange(0, nimg * ngt + 1, ngt, dtype=torch.int32, device=dev)
+nd = 60000
+src = rng.integers(0, nimg * ngt, nd)
+dp = g[src] + rng.normal(0, 2.0, (nd, 8))
+dimg = torch.from_numpy((src // ngt).astype(np.int32)).to(dev)
+diff = torch.zeros((nimg * ngt,), dtype=torch.uint8, device=dev)
+dpt, gtt = t(dp), t(g)
+ms = timed(lambda: core.voc_match(dpt, dimg, gtt, gt_start, diff, 0.5))
+out["voc_match"] = {"detections": nd, "images": nimg, "gts_per_image": ngt, "ms": ms, "detections_per_s": nd / ms * 1e3}
 print(json.dumps(out))
