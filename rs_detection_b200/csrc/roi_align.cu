@@ -543,7 +543,10 @@ __device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, i
 __global__ void __launch_bounds__(kRoiThreads, 2)
 roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const float* __restrict__ rois,
                          const int* __restrict__ order, int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // (aligned by hand: an __align__(1024) on the extern array would pad EVERY kernel of this translation unit
+    //  by 1 KB of static shared memory, which costs the register path its fourth CTA per SM)
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbins = L.PH * L.PW;
@@ -891,7 +894,7 @@ static size_t tma_smem_bytes(const rsdet_roi_align_cfg* c) {
     size_t big = (size_t)8 * kTmaStages * 4096;
     if (256 * nbins * 4 > big) big = 256 * nbins * 4;
     if (12 * nbins * cap > big) big = 12 * nbins * cap;
-    return big + 8 * nbins * cap + ((nbins * 4 + 15) & ~(size_t)15) + 8 * 8 * kTmaStages + 64;
+    return big + 8 * nbins * cap + ((nbins * 4 + 15) & ~(size_t)15) + 8 * 8 * kTmaStages + 64 + 1024;
 }
 
 static bool tma_path_ok(const rsdet_roi_align_cfg* c) {
