@@ -49,7 +49,7 @@ SCORE_THR = 0.001
 IOU_THR = 0.1
 MAX_NUM = 2000
 EXTEND = (1.4, 1.2)
-NSTREAMS = 4
+NSTREAMS = int(os.environ.get("RSDET_BENCH_STREAMS", "8"))
 METRIC = "tiles/s (Oriented R-CNN rotated-box hot path: RoIAlignRotated fwd + obb2poly + per-class nms_rotated)"
 WORKLOAD = ("configs[1]: orcnn_van3 inference hot path, 8 synthetic 1024x1024 tiles/GPU, 4000 rotated proposals/tile, "
             "4 FPN levels C=256 fp32 NCHW, RoIAlignRotated_v1 7x7x2x2 -> obb2poly -> multiclass_nms_rotated "
