@@ -67,13 +67,15 @@ int rsdet_assign_wrt_overlaps(const float* overlaps, int num_gts, int n, float p
                               int32_t* assigned_labels, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- NMS (rotated / poly / merge)
- * One engine, four pair predicates.  `kind`: */
+ * One engine, one pair predicate per `kind`: */
 #define RSDET_NMS_ROTATED 0 /* dets (n,5) fp32 obb; suppress IoU >  thr: ops/nms_rotated.py:353-411,450-493 */
 #define RSDET_NMS_ROTATED_GE 1 /* same, suppress IoU >= thr (the CPU body, ops/nms_rotated.py:414-449)        */
 #define RSDET_NMS_POLY 2    /* dets (n,8) fp32 quads, devPolyIoU > thr: ops/nms_poly.py:113-185,187-232       */
 #define RSDET_NMS_MERGE 3   /* dets (n,8) fp64 quads in scene coords; hbb prefilter then polygon IoU > thr:
                                data/devkits/result_merge.py:66-127 + ops/nms_poly.py:247-252              */
 #define RSDET_NMS_HBB 4     /* dets (n,4) fp64 [x1,y1,x2,y2]; suppress IoU >= thr (merge.py:14-27)         */
+#define RSDET_NMS_HBB_P1 5  /* dets (n,4) fp32 [x1,y1,x2,y2], "+1" widths; suppress IoU > thr: jt.nms as called
+                               by models/roi_heads/oriented_rpn_head.py:208 (Jittor 1.3.4.7 misc.py)      */
 
 /* Greedy NMS in descending-score order, independently inside each label group (labels == NULL: one
  * group).  Equivalent to the reference's label-gated IoU (ops/nms_rotated.py:281-286) and to one
@@ -179,6 +181,35 @@ int rsdet_oriented_head_results(const float* rois5, const float* cls_score, cons
 int rsdet_voc_match(const double* det_polys, const int32_t* det_img, int nd, const double* gt_polys, const int32_t* gt_start,
                     const uint8_t* gt_difficult, int num_imgs, int num_gts, double ovthresh, double* ovmax, int32_t* jmax,
                     int32_t* claim, uint8_t* tp, uint8_t* fp, void* stream);
+
+/* ---------------------------------------------------------------- oriented RPN proposals
+ * models/roi_heads/oriented_rpn_head.py:136-216 (_get_bboxes_single), one image: per level sigmoid (or 2-way
+ * softmax) of the (A*c, H, W) class map read in (h, w, a) order, top `nms_pre` by score when the level has
+ * more (:183-190), MidpointOffsetCoder.decode (models/boxes/coder.py:383-433 with rectpoly2obb / regular_obb
+ * ops/bbox_transforms.py:577-599, 501-519), min_bbox_size filter (:200-206), obb2hbb + per-level coordinate
+ * offset (:208-211), jt.nms at nms_thresh, first nms_post rows.
+ *   cls_scores[l]  (A or 2A, H_l, W_l) fp32;  bbox_preds[l] (A*6, H_l, W_l) fp32;  anchors[l] (H_l*W_l*A, 4)
+ *   fp32 [x1,y1,x2,y2] in (h, w, a) order;  all device pointers, the pointer arrays live on the host.
+ *   dets (nms_post, 6) fp32 [cx,cy,w,h,theta,score] in descending score order, num_dets int32 (1).
+ * Optional candidate dump for parity tests (NULL to skip), ncand = sum_l min(n_l, nms_pre) rows in level
+ * order: cand_obb (ncand,5), cand_hbb (ncand,4) WITH the level offsets, cand_score (ncand) (-inf where the
+ * size filter dropped the row), cand_level int32 (ncand). */
+typedef struct rsdet_rpn_cfg {
+    int num_levels;               /* <= 8 */
+    int height[8], width[8];
+    int num_anchors;              /* A per location */
+    int use_sigmoid;              /* 1: A class channels; 0: 2A channels, foreground = softmax(...)[:,1] */
+    int nms_pre, nms_post;
+    double nms_thresh;
+    float min_bbox_size;          /* < 0 disables the filter */
+    float means[6], stds[6];
+    float wh_ratio_clip;          /* 16/1000 */
+} rsdet_rpn_cfg;
+int rsdet_rpn_num_candidates(const rsdet_rpn_cfg* cfg);
+size_t rsdet_rpn_proposals_workspace_bytes(const rsdet_rpn_cfg* cfg);
+int rsdet_rpn_proposals(const rsdet_rpn_cfg* cfg, const float* const* cls_scores, const float* const* bbox_preds,
+                        const float* const* anchors, float* dets, int32_t* num_dets, float* cand_obb, float* cand_hbb,
+                        float* cand_score, int32_t* cand_level, void* workspace, size_t workspace_bytes, void* stream);
 
 /* counters for bench.py's `gpu_launches`: number of kernels this library has launched so far */
 unsigned long long rsdet_launch_count(void);

@@ -488,3 +488,149 @@ def voc_match(dets, gts, ovthresh=0.5):
         else:
             fp[d] = 1.
     return tp, fp
+
+
+# ----------------------------------------------------------------------------- RPN proposals
+def anchor_grid(featmap_size, stride, base_size=None, scales=(8,), ratios=(0.5, 1.0, 2.0)):
+    """python/jdet/models/boxes/anchor_generator.py AnchorGenerator (mmdet v2 semantics, scale_major,
+    center_offset 0): gen_single_level_base_anchors + single_level_grid_anchors -> (H*W*A, 4) float32
+    [x1,y1,x2,y2] in (h, w, a) order."""
+    base = np.float32(stride if base_size is None else base_size)
+    r = np.asarray(ratios, np.float32)
+    s = np.asarray(scales, np.float32)
+    hr = np.sqrt(r)
+    wr = (1 / hr).astype(np.float32)
+    ws = (base * wr[:, None] * s[None, :]).reshape(-1)
+    hs = (base * hr[:, None] * s[None, :]).reshape(-1)
+    basea = np.stack([-0.5 * ws, -0.5 * hs, 0.5 * ws, 0.5 * hs], -1).astype(np.float32)
+    H, W = featmap_size
+    sx = (np.arange(W) * stride).astype(np.float32)
+    sy = (np.arange(H) * stride).astype(np.float32)
+    xx = np.tile(sx, H)
+    yy = np.repeat(sy, W)
+    shifts = np.stack([xx, yy, xx, yy], -1)
+    return (basea[None, :, :] + shifts[:, None, :]).reshape(-1, 4).astype(np.float32)
+
+
+def rectpoly2obb(polys):
+    """python/jdet/ops/bbox_transforms.py:577-599 (float32)."""
+    p = np.asarray(polys, np.float32)
+    theta = np.arctan2(-(p[..., 3] - p[..., 1]), p[..., 2] - p[..., 0]).astype(np.float32)
+    Cos, Sin = np.cos(theta), np.sin(theta)
+    x = (((p[..., 0] + p[..., 2]) + p[..., 4]) + p[..., 6]) / np.float32(4)
+    y = (((p[..., 1] + p[..., 3]) + p[..., 5]) + p[..., 7]) / np.float32(4)
+    ux = p[..., 0::2] - x[..., None]
+    uy = p[..., 1::2] - y[..., None]
+    rx = ux * Cos[..., None] + uy * (-Sin)[..., None]
+    ry = ux * Sin[..., None] + uy * Cos[..., None]
+    w = rx.max(-1) - rx.min(-1)
+    h = ry.max(-1) - ry.min(-1)
+    return regular_obb(np.stack([x, y, w, h, theta], -1).astype(np.float32))
+
+
+def midpoint_offset_decode(bboxes, pred, means=(0., 0., 0., 0., 0., 0.), stds=(1., 1., 1., 1., 0.5, 0.5), wh_ratio_clip=16 / 1000):
+    """python/jdet/models/boxes/coder.py:383-433 MidpointOffsetCoder.decode, (n,4) anchors + (n,6) deltas -> (n,5)."""
+    b = np.asarray(bboxes, np.float32)
+    d = np.asarray(pred, np.float32) * np.asarray(stds, np.float32)[None] + np.asarray(means, np.float32)[None]
+    dx, dy, dw, dh, da, db = [d[:, k] for k in range(6)]
+    mr = np.float32(np.abs(np.log(wh_ratio_clip)))
+    dw = np.clip(dw, -mr, mr)
+    dh = np.clip(dh, -mr, mr)
+    px = (b[:, 0] + b[:, 2]) * np.float32(0.5)
+    py = (b[:, 1] + b[:, 3]) * np.float32(0.5)
+    pw = b[:, 2] - b[:, 0]
+    ph = b[:, 3] - b[:, 1]
+    gw = pw * np.exp(dw)
+    gh = ph * np.exp(dh)
+    gx = px + pw * dx
+    gy = py + ph * dy
+    x1 = gx - gw * np.float32(0.5)
+    y1 = gy - gh * np.float32(0.5)
+    x2 = gx + gw * np.float32(0.5)
+    y2 = gy + gh * np.float32(0.5)
+    da = np.clip(da, np.float32(-0.5), np.float32(0.5))
+    db = np.clip(db, np.float32(-0.5), np.float32(0.5))
+    ga, _ga = gx + da * gw, gx - da * gw
+    gb, _gb = gy + db * gh, gy - db * gh
+    polys = np.stack([ga, y1, x2, gb, _ga, y2, x1, _gb], -1)
+    center = np.stack([gx, gy] * 4, -1)
+    cp = polys - center
+    with np.errstate(divide="ignore", invalid="ignore"):
+        diag = np.sqrt(cp[:, 0::2] * cp[:, 0::2] + cp[:, 1::2] * cp[:, 1::2])
+        f = diag.max(-1, keepdims=True) / diag
+        cp = cp * np.repeat(f, 2, axis=-1)
+    return rectpoly2obb((cp + center).astype(np.float32))
+
+
+def jt_nms(dets, thresh):
+    """jt.nms (Jittor 1.3.4.7, python/jittor/misc.py `nms`; THIRD PARTY, not under /root/reference -- restated
+    from its published source): dets (n,5) float32 [x1,y1,x2,y2,score]; argsort descending, greedy `candidate`
+    selection with fail condition inter/(a_j + a_i - inter) > thresh, '+1' widths, float32 arithmetic and a double
+    threshold literal.  Returns original indices in descending-score order.  Ties: lower index first (unpinned)."""
+    d = np.asarray(dets, np.float32)
+    order = np.argsort(-d[:, 4].astype(np.float64), kind="stable")
+    b = d[order]
+    one = np.float32(1)
+    area = (b[:, 2] - b[:, 0] + one) * (b[:, 3] - b[:, 1] + one)
+    alive = np.ones(len(b), bool)
+    keep = []
+    for i in range(len(b)):
+        if not alive[i]:
+            continue
+        keep.append(i)
+        iw = np.maximum(np.float32(0), np.minimum(b[i, 2], b[i + 1:, 2]) - np.maximum(b[i, 0], b[i + 1:, 0]) + one)
+        ih = np.maximum(np.float32(0), np.minimum(b[i, 3], b[i + 1:, 3]) - np.maximum(b[i, 1], b[i + 1:, 1]) + one)
+        inter = ih * iw
+        with np.errstate(divide="ignore", invalid="ignore"):
+            iou = inter / (area[i + 1:] + area[i] - inter)
+        alive[i + 1:] &= ~(iou.astype(np.float64) > thresh)
+    return order[np.asarray(keep, np.int64)]
+
+
+def rpn_candidates(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid=True, nms_pre=2000, min_bbox_size=0,
+                   means=(0., 0., 0., 0., 0., 0.), stds=(1., 1., 1., 1., 0.5, 0.5)):
+    """python/jdet/models/roi_heads/oriented_rpn_head.py:155-206: per-level scores, top nms_pre, decode, size filter.
+    -> (proposals (m,5), scores (m,), level ids (m,), candidate row of each survivor (m,))"""
+    props, scores, ids = [], [], []
+    for idx, (cs, bp, anchors) in enumerate(zip(cls_scores, bbox_preds, mlvl_anchors)):
+        cs = np.asarray(cs, np.float32).transpose(1, 2, 0)
+        if use_sigmoid:
+            x = cs.reshape(-1)
+            s = (np.float32(1) / (np.float32(1) + np.exp(-x))).astype(np.float32)
+        else:
+            x = cs.reshape(-1, 2)
+            e = np.exp(x - x.max(1, keepdims=True))
+            s = (e[:, 1] / (e[:, 0] + e[:, 1])).astype(np.float32)
+        bp = np.asarray(bp, np.float32).transpose(1, 2, 0).reshape(-1, 6)
+        anchors = np.asarray(anchors, np.float32)
+        if nms_pre > 0 and s.shape[0] > nms_pre:
+            rank = np.argsort(-s.astype(np.float64), kind="stable")[:nms_pre]
+            s, bp, anchors = s[rank], bp[rank], anchors[rank]
+        scores.append(s)
+        props.append(midpoint_offset_decode(anchors, bp, means, stds))
+        ids.append(np.full(s.shape[0], idx, np.int64))
+    props, scores, ids = np.concatenate(props), np.concatenate(scores), np.concatenate(ids)
+    rows = np.arange(len(scores))
+    if min_bbox_size >= 0:
+        m = (props[:, 2] > min_bbox_size) & (props[:, 3] > min_bbox_size)
+        props, scores, ids, rows = props[m], scores[m], ids[m], rows[m]
+    return props, scores, ids, rows
+
+
+def rpn_level_offset_nms(proposals, scores, ids, nms_thresh=0.8, nms_post=2000):
+    """oriented_rpn_head.py:208-216: obb2hbb, per-level coordinate offset, jt.nms, first nms_post rows.
+    -> (dets (k,6), kept rows of `proposals` in output order, offset hbbs (m,4))"""
+    h = obb2hbb(proposals).astype(np.float32)
+    if len(h) == 0:
+        return np.zeros((0, 6), np.float32), np.zeros((0,), np.int64), h
+    max_coordinate = h.max() - h.min()
+    h = h + (ids.astype(np.float32) * (max_coordinate + np.float32(1)))[:, None]
+    keep = jt_nms(np.concatenate([h, scores[:, None]], 1), nms_thresh)[:nms_post]
+    return np.concatenate([proposals, scores[:, None]], 1)[keep], keep, h
+
+
+def rpn_get_bboxes_single(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid=True, nms_pre=2000, nms_post=2000, nms_thresh=0.8,
+                          min_bbox_size=0, means=(0., 0., 0., 0., 0., 0.), stds=(1., 1., 1., 1., 0.5, 0.5)):
+    """oriented_rpn_head.py:136-216 end to end."""
+    p, s, i, _ = rpn_candidates(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid, nms_pre, min_bbox_size, means, stds)
+    return rpn_level_offset_nms(p, s, i, nms_thresh, nms_post)[0]

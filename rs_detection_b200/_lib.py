@@ -15,7 +15,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librsdet.so")
 
-NMS_ROTATED, NMS_ROTATED_GE, NMS_POLY, NMS_MERGE, NMS_HBB = 0, 1, 2, 3, 4
+NMS_ROTATED, NMS_ROTATED_GE, NMS_POLY, NMS_MERGE, NMS_HBB, NMS_HBB_P1 = 0, 1, 2, 3, 4, 5
 MAX_LEVELS = 8
 
 _vp = C.c_void_p
@@ -28,6 +28,13 @@ class RoiAlignCfg(C.Structure):
                 ("pooled_h", C.c_int), ("pooled_w", C.c_int), ("sampling_ratio", C.c_int), ("version", C.c_int),
                 ("extend_w", C.c_float), ("extend_h", C.c_float), ("finest_scale", C.c_float),
                 ("channels_last", C.c_int)]
+
+
+class RpnCfg(C.Structure):
+    _fields_ = [("num_levels", C.c_int), ("height", C.c_int * MAX_LEVELS), ("width", C.c_int * MAX_LEVELS),
+                ("num_anchors", C.c_int), ("use_sigmoid", C.c_int), ("nms_pre", C.c_int), ("nms_post", C.c_int),
+                ("nms_thresh", C.c_double), ("min_bbox_size", C.c_float), ("means", C.c_float * 6), ("stds", C.c_float * 6),
+                ("wh_ratio_clip", C.c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/rsdet.h declares
@@ -61,6 +68,10 @@ SIGNATURES = {
                                               C.c_float, C.POINTER(C.c_float), C.c_float, C.c_int, _vp, _vp, _vp, _vp, C.c_size_t,
                                               _vp]),
     "rsdet_voc_match": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rsdet_rpn_num_candidates": (C.c_int, [C.POINTER(RpnCfg)]),
+    "rsdet_rpn_proposals_workspace_bytes": (C.c_size_t, [C.POINTER(RpnCfg)]),
+    "rsdet_rpn_proposals": (C.c_int, [C.POINTER(RpnCfg), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, C.c_size_t, _vp]),
     "rsdet_nchw_to_nhwc": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rsdet_nhwc_to_nchw": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
 }

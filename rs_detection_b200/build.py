@@ -27,6 +27,7 @@ UNITS = {
     "nms.cu": ["-fmad=false"],
     "transforms.cu": ["-fmad=false"],
     "head.cu": ["-fmad=false"],
+    "rpn.cu": ["-fmad=false"],
     "roi_align.cu": ["-DRSDET_BULK_ROWS=" + os.environ.get("RSDET_BULK_ROWS", "0")],
 }
 

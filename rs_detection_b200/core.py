@@ -315,3 +315,47 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     check(load().rsdet_nhwc_to_nchw(ptr(x), n, c, h, w, ptr(out), stream_ptr()), "nhwc_to_nchw")
     return out
+
+
+# ------------------------------------------------------------------------------- RPN proposals
+def rpn_proposals(cls_scores, bbox_preds, anchors, num_anchors: int, use_sigmoid: bool = True, nms_pre: int = 2000,
+                  nms_post: int = 2000, nms_thresh: float = 0.8, min_bbox_size: float = 0.0,
+                  means=(0., 0., 0., 0., 0., 0.), stds=(1., 1., 1., 1., 0.5, 0.5), wh_ratio_clip: float = 16 / 1000,
+                  want_candidates: bool = False):
+    """One image.  cls_scores[l] (A*c, H, W), bbox_preds[l] (A*6, H, W), anchors[l] (H*W*A, 4) CUDA fp32 tensors.
+    -> dets (nms_post, 6) [cx,cy,w,h,theta,score] (rows past the count are zero), count (1,) int32; with
+    `want_candidates` also (cand_obb, cand_hbb, cand_score, cand_level).  No host synchronisation."""
+    from ._lib import RpnCfg
+    cs = [_f32(t) for t in cls_scores]
+    bp = [_f32(t) for t in bbox_preds]
+    an = [_f32(t) for t in anchors]
+    nl = len(cs)
+    assert nl == len(bp) == len(an) and 1 <= nl <= 8
+    cfg = RpnCfg()
+    cfg.num_levels, cfg.num_anchors, cfg.use_sigmoid = nl, int(num_anchors), int(bool(use_sigmoid))
+    cfg.nms_pre, cfg.nms_post, cfg.nms_thresh = int(nms_pre), int(nms_post), float(nms_thresh)
+    cfg.min_bbox_size, cfg.wh_ratio_clip = float(min_bbox_size), float(wh_ratio_clip)
+    for k in range(6):
+        cfg.means[k], cfg.stds[k] = float(means[k]), float(stds[k])
+    for l in range(nl):
+        h, w = cs[l].shape[-2:]
+        assert tuple(bp[l].shape[-2:]) == (h, w) and bp[l].numel() == num_anchors * 6 * h * w
+        assert cs[l].numel() == num_anchors * (1 if use_sigmoid else 2) * h * w and an[l].numel() == h * w * num_anchors * 4
+        cfg.height[l], cfg.width[l] = int(h), int(w)
+    L = load()
+    nc = L.rsdet_rpn_num_candidates(C.byref(cfg))
+    if nc < 0:
+        raise ValueError("rpn_proposals: bad configuration")
+    dev = cs[0].device
+    dets = torch.empty((int(nms_post), 6), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    cand = (None, None, None, None)
+    if want_candidates:
+        cand = (torch.empty((nc, 5), dtype=torch.float32, device=dev), torch.empty((nc, 4), dtype=torch.float32, device=dev),
+                torch.empty((nc,), dtype=torch.float32, device=dev), torch.empty((nc,), dtype=torch.int32, device=dev))
+    vp = C.c_void_p * nl
+    ws = workspace(L.rsdet_rpn_proposals_workspace_bytes(C.byref(cfg)), "rpn")
+    check(L.rsdet_rpn_proposals(C.byref(cfg), vp(*[ptr(t) for t in cs]), vp(*[ptr(t) for t in bp]), vp(*[ptr(t) for t in an]),
+                                ptr(dets), ptr(cnt), *[ptr(t) if t is not None else None for t in cand], ptr(ws), ws.numel(),
+                                stream_ptr()), "rpn_proposals")
+    return (dets, cnt) + (cand if want_candidates else ())

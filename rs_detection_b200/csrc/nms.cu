@@ -30,6 +30,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "common.cuh"
+#include "nms_engine.cuh"
 #include "poly_iou.cuh"
 #include "rotated_iou.cuh"
 
@@ -101,6 +102,25 @@ template <> struct Traits<RSDET_NMS_HBB> {
         double ov = (brx - tlx) * (bry - tly);
         double iou = ov / ((a.x2 - a.x1) * (a.y2 - a.y1) + (b.x2 - b.x1) * (b.y2 - b.y1) - ov);
         return !(iou < thr);
+    }
+};
+
+// jt.nms (Jittor 1.3.4.7 misc.py `nms`, called from oriented_rpn_head.py:208): fp32 boxes, the "+1" pixel
+// convention, fail condition `inter / (a_j + a_i - inter) > thr` with thr a double literal in Jittor's JIT source.
+struct HBoxF { float x1, y1, x2, y2; };
+template <> struct Traits<RSDET_NMS_HBB_P1> {
+    using Box = HBoxF; using Raw = float; using Thr = double;
+    static constexpr int kRow = 4; static constexpr bool kScratch = false;
+    __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
+    __device__ static bool candidate(const Box& a, const Box& b, Thr) {
+        return fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1) + 1.f > 0.f && fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1) + 1.f > 0.f;
+    }
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
+        float iw = fmaxf(0.f, fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1) + 1.f);
+        float ih = fmaxf(0.f, fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1) + 1.f);
+        float inter = ih * iw;
+        float sa = (a.x2 - a.x1 + 1.f) * (a.y2 - a.y1 + 1.f), sb = (b.x2 - b.x1 + 1.f) * (b.y2 - b.y1 + 1.f);
+        return (double)(inter / (sa + sb - inter)) > thr;
     }
 };
 
@@ -719,37 +739,13 @@ __global__ void score_order_flags_kernel(const uint8_t* __restrict__ keep_mask, 
 }
 
 // ----------------------------------------------------------------------------- engine
-struct NmsArgs {
-    int kind;
-    const void* dets;
-    const void* scores;
-    const int32_t* labels;
-    int n_max;
-    const int* n_dev;
-    double thr;
-    const double* thr_per_label;
-    int num_thr;
-    uint8_t* keep_mask;
-    int64_t* keep_sorted_idx;
-    int64_t* keep_score_idx;
-    int32_t* num_keep;
-    int label_bits = 32;
-    // shared-box mode (multiclass with class-agnostic boxes): candidate e refers to box e / cand_per_box
-    const float* shared_boxes = nullptr;
-    int n_shared = 0;
-    int cand_per_box = 1;
-    // labels are class ids 0..num_classes-1 whose live counts are already known on the device: the segment
-    // table is an exclusive scan of the counts (no boundary search over the sorted labels)
-    const int* class_counts = nullptr;
-    int num_classes = 0;
-    size_t mask_words = 0;  // caller-proved bound on the mask size (0 = worst case n * ceil(n/64))
-};
 
 static size_t box_bytes(int kind) {
     switch (kind) {
         case RSDET_NMS_ROTATED: case RSDET_NMS_ROTATED_GE: return sizeof(RBox);
         case RSDET_NMS_POLY: return sizeof(PolyBox);
         case RSDET_NMS_MERGE: return sizeof(MBox);
+        case RSDET_NMS_HBB_P1: return sizeof(HBoxF);
         default: return sizeof(HBox);
     }
 }
@@ -757,7 +753,7 @@ static size_t box_bytes(int kind) {
 constexpr int kMaxNmsBoxes = 1 << 18;  // dense n x n/64 mask: 8.6 GB at the limit; the remv vector fits shared memory
 
 // mask_words = 0: worst case (every box in one label group)
-size_t nms_ws_bytes(int kind, int n, size_t mask_words = 0) {
+size_t nms_ws_bytes(int kind, int n, size_t mask_words) {
     size_t N = (size_t)(n > 0 ? n : 1);
     size_t b = 0;
     b += 2 * ws_bytes<unsigned long long>(N);  // score keys (double buffer)
@@ -799,13 +795,14 @@ static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t
         case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_HBB_P1: launch_kind<RSDET_NMS_HBB_P1>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
     }
 }
 
 int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int n = a.n_max;
-    if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB) return RSDET_EINVAL;
+    if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB_P1) return RSDET_EINVAL;
     if (n == 0) {
         if (a.num_keep) cudaMemsetAsync(a.num_keep, 0, sizeof(int32_t), st);
         return cuda_status();

@@ -5,7 +5,16 @@
 greedy loop and the Shapely call per candidate pair are replaced by the float64 merge predicate of the
 device NMS engine.  `merge_detections` is the batched form: ALL (scene, class) groups of a result set
 in one launch, per-class thresholds included.
+
+File level (:206-299): `mergesingle` / `mergebase` / `mergebase_parallel` / `mergebypoly`
+read the per-class `before_nms/<Class>.txt` files (`tile_name score x1 y1 ... y4`, tile name
+`<scene>__<rate>__<x>___<y>`), map tile polygons to scene coordinates on the device
+(`rsdet_poly2origpoly`), run ONE merge-NMS launch over every (file, scene) group and write
+`<scene> <score> <8 coords>` lines with the reference's `str(float)` formatting.
 """
+import os
+import re
+
 import numpy as np
 import torch
 
@@ -65,3 +74,120 @@ def merge_detections(polys, scores, group_ids, thresh=nms_threshold_0, group_thr
                    want_score=True, ws_tag="merge")
     keep = res.score_idx
     return keep.cpu().numpy() if host else keep
+
+
+# ------------------------------------------------------------------------------------ file level
+_XY = re.compile(r'__\d+___\d+')             # :224
+_RATE = re.compile(r'__([\d+\.]+)__\d+___')  # :230
+_INT = re.compile(r'\d+')
+
+
+def custombasename(fullname):
+    """dota_utils.py:25-26"""
+    return os.path.basename(os.path.splitext(fullname)[0])
+
+
+def GetFileFromThisRootDir(dir, ext=None):
+    """dota_utils.py:29-40 (note: `extension in ext` is a substring test when ext is a str)."""
+    out = []
+    for root, _, files in os.walk(dir):
+        for f in files:
+            path = os.path.join(root, f)
+            if ext is None or os.path.splitext(path)[1][1:] in ext:
+                out.append(path)
+    return out
+
+
+def parse_tile_name(subname):
+    """'<scene>__<rate>__<x>___<y>' -> (scene, x, y, rate) with the reference's regexes (:219-232)."""
+    x, y = _INT.findall(_XY.findall(subname)[0])[:2]
+    return subname.split('__')[0], int(x), int(y), float(_RATE.findall(subname)[0])
+
+
+def read_tile_detections(fullname):
+    """One before_nms file -> (scene name per row, scene first-appearance order, tile polys (n,8) f64,
+    per-row [x, y, rate] (n,3) f64, scores (n,) f64).  Text -> numbers only; no geometry on the host."""
+    scenes, order, polys, offs, scores = [], [], [], [], []
+    cache = {}
+    with open(fullname, 'r') as f:
+        for line in f:
+            sp = line.strip().split(' ')
+            if len(sp) < 10:
+                continue
+            t = cache.get(sp[0])
+            if t is None:
+                t = cache[sp[0]] = parse_tile_name(sp[0])
+            if t[0] not in order:
+                order.append(t[0])
+            scenes.append(t[0])
+            offs.append((t[1], t[2], t[3]))
+            scores.append(float(sp[1]))
+            polys.append([float(v) for v in sp[2:10]])
+    return (scenes, order, np.asarray(polys, np.float64).reshape(-1, 8), np.asarray(offs, np.float64).reshape(-1, 3),
+            np.asarray(scores, np.float64))
+
+
+def _merge_files(files, dstpath, thresholds):
+    """Shared body of mergesingle / mergebase / mergebypoly: all files, all scenes, one NMS launch."""
+    require_cuda()
+    recs = [read_tile_detections(f) for f in files]
+    gid_of, rows_gid, thr = {}, [], []
+    for fi, (scenes, order, _, _, _) in enumerate(recs):
+        for sc in order:
+            gid_of[(fi, sc)] = len(thr)
+            thr.append(float(thresholds[fi]))
+        rows_gid.append(np.asarray([gid_of[(fi, sc)] for sc in scenes], np.int32))
+    n = sum(r[2].shape[0] for r in recs)
+    kept_rows = np.zeros((0,), np.int64)
+    scene_polys = np.zeros((0, 8))
+    if n > 0:
+        polys = torch.from_numpy(np.concatenate([r[2] for r in recs])).cuda()
+        offs = torch.from_numpy(np.concatenate([r[3] for r in recs])).cuda()
+        scores = torch.from_numpy(np.concatenate([r[4] for r in recs])).cuda()
+        gids = torch.from_numpy(np.concatenate(rows_gid)).cuda()
+        orig = core.poly2origpoly(polys, offs)
+        res = core.nms(NMS_MERGE, orig, scores, nms_threshold_0, labels=gids,
+                       thr_per_label=torch.tensor(thr, dtype=torch.float64, device=orig.device), want_mask=False,
+                       want_sorted=False, want_score=True, ws_tag="merge")
+        kept_rows = res.score_idx.cpu().numpy()
+        scene_polys = orig.cpu().numpy()
+    all_scores = np.concatenate([r[4] for r in recs]) if n else np.zeros((0,))
+    all_gids = np.concatenate(rows_gid) if n else np.zeros((0,), np.int32)
+    per_gid = [[] for _ in thr]
+    for r in kept_rows.tolist():  # already in descending-score order
+        per_gid[all_gids[r]].append(r)
+    os.makedirs(dstpath, exist_ok=True)
+    for fi, f in enumerate(files):
+        dstname = os.path.join(dstpath, custombasename(f) + '.txt')
+        with open(dstname, 'w') as out:
+            for sc in recs[fi][1]:
+                for r in per_gid[gid_of[(fi, sc)]]:
+                    out.write(sc + ' ' + str(float(all_scores[r])) + ' ' + ' '.join(map(str, scene_polys[r].tolist())) + '\n')
+
+
+def _file_threshold(fullname, nms_threshold_type):
+    return nms_threshold_0 if not nms_threshold_type else nms_threshold_1[custombasename(fullname)]
+
+
+def mergesingle(dstpath, nms, fullname, nms_threshold_type=0):
+    """:206-255.  `nms` is accepted for signature parity; anything but `py_cpu_nms_poly_fast` is rejected
+    (the device engine implements that predicate).  `nms_threshold_type` replaces `get_cfg()`."""
+    if nms is not py_cpu_nms_poly_fast:
+        raise ValueError("mergesingle: only py_cpu_nms_poly_fast is implemented on the device")
+    _merge_files([fullname], dstpath, [_file_threshold(fullname, nms_threshold_type)])
+
+
+def mergebase(srcpath, dstpath, nms, nms_threshold_type=0):
+    """:267-270 and mergebase_parallel :258-264 -- the 16-process pool becomes one launch."""
+    if nms is not py_cpu_nms_poly_fast:
+        raise ValueError("mergebase: only py_cpu_nms_poly_fast is implemented on the device")
+    files = GetFileFromThisRootDir(srcpath)
+    _merge_files(files, dstpath, [_file_threshold(f, nms_threshold_type) for f in files])
+
+
+mergebase_parallel = mergebase
+
+
+def mergebypoly(srcpath, dstpath, nms_threshold_type=0):
+    """:286-299"""
+    mergebase_parallel(srcpath, dstpath, py_cpu_nms_poly_fast, nms_threshold_type)

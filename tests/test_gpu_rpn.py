@@ -1,0 +1,88 @@
+"""GPU parity: oriented RPN proposal stage through rsdet_rpn_proposals."""
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+from helpers import close_report
+
+pytestmark = pytest.mark.gpu
+
+STRIDES = (4, 8, 16, 32, 64)
+
+
+def _case(oracle, shapes, seed, cpa=1):
+    cls, reg = W.rpn_outputs(shapes, 3, seed, cpa)
+    anchors = [oracle.anchor_grid(s, st) for s, st in zip(shapes, STRIDES)]
+    return cls, reg, anchors
+
+
+def _cuda(xs):
+    return [torch.from_numpy(x).cuda() for x in xs]
+
+
+@pytest.mark.parametrize("shapes,nms_pre,nms_post,sigmoid,min_size", [
+    (((64, 64), (32, 32), (16, 16), (8, 8), (4, 4)), 1000, 1000, True, 0),
+    (((64, 64), (32, 32), (16, 16), (8, 8), (4, 4)), 500, 300, False, 6.0),
+    (((40, 56), (20, 28), (10, 14)), 2000, 2000, True, -1),
+    (((256, 256), (128, 128), (64, 64), (32, 32), (16, 16)), 2000, 2000, True, 0),
+])
+def test_rpn_proposals_vs_oracle(cuda, oracle, shapes, nms_pre, nms_post, sigmoid, min_size):
+    from rs_detection_b200 import core
+    cls, reg, anchors = _case(oracle, shapes, 11, 1 if sigmoid else 2)
+    dets, cnt, c_obb, c_hbb, c_score, c_level = core.rpn_proposals(
+        _cuda(cls), _cuda(reg), _cuda(anchors), 3, sigmoid, nms_pre, nms_post, 0.8, min_size, want_candidates=True)
+    k = int(cnt.item())
+    dets, c_obb, c_hbb, c_score, c_level = [t.cpu().numpy() for t in (dets, c_obb, c_hbb, c_score, c_level)]
+    # stage 1: candidates (scores, top-k choice, decode, size filter) against the float32 numpy restatement.
+    # expf / atan2f / sinf / cosf differ from glibc by an ulp or two, hence a tolerance (coordinates ~1e3).
+    p, s, ids, rows = oracle.rpn_candidates(cls, reg, anchors, sigmoid, nms_pre, min_size)
+    live = np.isfinite(c_score)
+    near = 0
+    if min_size >= 0:  # rows within 1e-3 of the size threshold may flip under the tolerance above
+        near = int((np.abs(c_obb[:, 2:4] - min_size) < 1e-3).any(1).sum())
+    if near == 0:
+        assert np.array_equal(np.nonzero(live)[0], rows)
+        assert np.array_equal(c_level[live], ids)
+        bad, err, _ = close_report(c_score[live], s, 1e-6, 1e-7)
+        assert bad == 0, err
+        bad, err, _ = close_report(c_obb[live][:, :4], p[:, :4], 1e-5, 2e-3)
+        assert bad == 0, err
+        dth = np.abs(c_obb[live][:, 4] - p[:, 4])
+        dth = np.minimum(dth, np.pi - dth)  # regular_theta wraps at +-pi/2
+        assert dth.max() < 1e-4
+    # stage 2a: obb2hbb + level offsets (sinf / cosf again: tolerance; offsets reach ~1e4 where an ulp is 1e-3)
+    _, _, hb = oracle.rpn_level_offset_nms(c_obb[live], c_score[live], c_level[live].astype(np.int64), 0.8, nms_post)
+    bad, err, _ = close_report(c_hbb[live], hb, 1e-6, 4e-3)
+    assert bad == 0, err
+    # stage 2b: jt.nms + truncation on the DEVICE's own offset boxes must match the oracle bit for bit
+    keep = oracle.jt_nms(np.concatenate([c_hbb[live], c_score[live][:, None]], 1), 0.8)[:nms_post]
+    want = np.concatenate([c_obb[live], c_score[live][:, None]], 1)[keep]
+    assert k == want.shape[0] and 0 < k <= nms_post
+    assert np.array_equal(dets[:k], want)
+    assert not dets[k:].any()
+    assert np.all(np.diff(dets[:k, 5]) <= 0)
+
+
+def test_rpn_mirror_class_and_batch(cuda, oracle):
+    from rs_detection_b200.jdet.models.roi_heads.oriented_rpn_head import OrientedRPNProposals
+    shapes = ((32, 32), (16, 16), (8, 8), (4, 4), (2, 2))
+    head = OrientedRPNProposals(nms_pre=300, nms_post=200)
+    per_img = [W.rpn_outputs(shapes, 3, seed) for seed in (1, 2)]
+    cls = [np.stack([per_img[b][0][l] for b in range(2)]) for l in range(5)]
+    reg = [np.stack([per_img[b][1][l] for b in range(2)]) for l in range(5)]
+    out = head.get_bboxes(cls, reg, None)
+    assert len(out) == 2 and isinstance(out[0], np.ndarray) and out[0].shape[1] == 6
+    anchors = [oracle.anchor_grid(s, st) for s, st in zip(shapes, STRIDES)]
+    for b in range(2):
+        want = oracle.rpn_get_bboxes_single(per_img[b][0], per_img[b][1], anchors, True, 300, 200, 0.8, 0)
+        assert abs(out[b].shape[0] - want.shape[0]) <= 2  # a near-threshold pair may flip under the decode tolerance
+        m = min(out[b].shape[0], want.shape[0], 20)
+        assert np.allclose(out[b][:m, 5], want[:m, 5], atol=1e-6)
+
+
+def test_rpn_bad_config(cuda):
+    from rs_detection_b200 import core
+    x = torch.zeros((3, 4, 4), device="cuda")
+    with pytest.raises(AssertionError):
+        core.rpn_proposals([x], [torch.zeros((17, 4, 4), device="cuda")], [torch.zeros((48, 4), device="cuda")], 3)

@@ -145,3 +145,59 @@ def merge_scene(num_objects=2000, num_classes=10, scene=10000, seed=0, tile=TILE
 
 FAIR1M_CLASSES = ['Airplane', 'Ship', 'Vehicle', 'Basketball_Court', 'Tennis_Court', 'Football_Field',
                   'Baseball_Field', 'Intersection', 'Roundabout', 'Bridge']
+
+
+def tile_results(num_objects=300, num_classes=10, scene=3000, num_scenes=2, seed=0, tile=TILE, gap=200, rates=(0.5, 1.0),
+                 jitter_px=1.0):
+    """The runner's per-tile result list `[((polys (k,8), scores (k,), labels (k,)), {"img_file": ...}), ...]` as
+    data_merge.prepare_data reads it (data_merge.py:29-48): tile names `<scene>__<rate>__<x>___<y>.png`
+    (ImgSplit naming parsed back by result_merge.py:219-232), polygons in TILE coordinates, float32.
+    Scores are distinct at four decimals (the text format keeps four; argsort tie order is unspecified in the
+    reference), so at most 9999 detections in total."""
+    rng = np.random.default_rng(seed + 7151)
+    out = []
+    slide = tile - gap
+    pool = rng.permutation(9999)[: 9999] + 1
+    used = 0
+    for s in range(num_scenes):
+        name = "P%04d" % (s + 1)
+        cls = rng.integers(0, num_classes, num_objects)
+        obj = rotated_boxes(num_objects, seed + 31 * s + 5, canvas=scene, smin=8.0, smax=96.0, rmax=4.0, dtype=np.float64)
+        for rate in rates:
+            size = scene * rate
+            starts = list(range(0, max(int(size) - tile, 0) + 1, slide))
+            if starts[-1] + tile < size:
+                starts.append(int(size) - tile)
+            ob = obj.copy()
+            ob[:, :4] *= rate
+            for x0 in starts:
+                for y0 in starts:
+                    m = (ob[:, 0] >= x0) & (ob[:, 0] < x0 + tile) & (ob[:, 1] >= y0) & (ob[:, 1] < y0 + tile)
+                    k = int(m.sum())
+                    if k == 0:
+                        continue
+                    o = ob[m].copy()
+                    o[:, 0] += rng.normal(0, jitter_px, k) - x0
+                    o[:, 1] += rng.normal(0, jitter_px, k) - y0
+                    o[:, 4] += rng.normal(0, 0.02, k)
+                    if used + k > pool.size:
+                        raise ValueError("tile_results: more than 9999 detections")
+                    sc = pool[used:used + k] / 10000.0
+                    used += k
+                    rate_s = ("%g" % rate) if rate != int(rate) else "%.1f" % rate
+                    out.append(((obb_to_poly64(o).astype(np.float32), sc.astype(np.float32), cls[m].astype(np.int64)),
+                                {"img_file": "/data/images/%s__%s__%d___%d.png" % (name, rate_s, x0, y0)}))
+    return out
+
+
+def rpn_outputs(shapes=((256, 256), (128, 128), (64, 64), (32, 32), (16, 16)), num_anchors=3, seed=0, cls_per_anchor=1):
+    """Synthetic `rpn_cls` / `rpn_reg` maps for one 1024x1024 tile (oriented_rpn_head.py:118-124): class logits
+    N(-2, 2) (few confident anchors), deltas N(0, 0.4) with the two midpoint offsets N(0, 0.6)."""
+    rng = np.random.default_rng(seed + 90001)
+    cls, reg = [], []
+    for h, w in shapes:
+        cls.append(rng.normal(-2.0, 2.0, (num_anchors * cls_per_anchor, h, w)).astype(np.float32))
+        r = rng.normal(0.0, 0.4, (num_anchors, 6, h, w)).astype(np.float32)
+        r[:, 4:] = rng.normal(0.0, 0.6, (num_anchors, 2, h, w)).astype(np.float32)
+        reg.append(r.reshape(num_anchors * 6, h, w))
+    return cls, reg
