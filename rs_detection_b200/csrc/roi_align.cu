@@ -403,6 +403,18 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
     __syncthreads();
 }
 
+// Conflict-free access to the [c][bin] staging block.  A warp touches channels 4*lane + i of one bin at a
+// time; with all lanes on the same component i the 32 addresses fall on 8 banks (4-way conflict: 7.2 M of the
+// forward kernel's 34 M L1 wavefronts in profiles/r1_d).  Lane octet o = lane/8 therefore handles component
+// (i + o) & 3 at step i: for an odd bin count the four octets land on the four residues mod 4 and the 32
+// banks are distinct.  rot4 rotates a quad left by o so that step i finds its value in slot i.
+__device__ __forceinline__ float4 rot4(float4 v, int o) {
+    if (o & 1) v = make_float4(v.y, v.z, v.w, v.x);
+    if (o & 2) v = make_float4(v.z, v.w, v.x, v.y);
+    return v;
+}
+__device__ __forceinline__ float4 unrot4(float4 v, int o) { return rot4(v, (4 - o) & 3); }
+
 // ---------------------------------------------------------------------------------- forward (fast)
 // One CTA per (RoI, chunk of up to 64 channel quads), thread = (channel quad(s), bin group).  QPT = 2:
 // the second channel quad is an immediate +512 B off the same address.
@@ -441,6 +453,7 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     const int lanes = QPT == 2 ? 32 : Qc;                  // threads per bin group
     const int groups = kRoiThreads / lanes;
     const int cq = tid % lanes, grp = tid / lanes;
+    const int oct = (cq >> 3) & 3;
     const float4* __restrict__ feat =
         reinterpret_cast<const float4*>(L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0) + cq;
     const bool pow2 = (spb & (spb - 1)) == 0;
@@ -482,10 +495,11 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
                 if (pow2) { acc[u].x *= inv_count; acc[u].y *= inv_count; acc[u].z *= inv_count; acc[u].w *= inv_count; }
                 else { acc[u].x /= count; acc[u].y /= count; acc[u].z /= count; acc[u].w /= count; }
                 const int c0 = (cq + u * 32) * 4;
-                s_stage[(c0 + 0) * nbins + b] = acc[u].x;
-                s_stage[(c0 + 1) * nbins + b] = acc[u].y;
-                s_stage[(c0 + 2) * nbins + b] = acc[u].z;
-                s_stage[(c0 + 3) * nbins + b] = acc[u].w;
+                const float4 r = rot4(acc[u], oct);
+                s_stage[(c0 + ((0 + oct) & 3)) * nbins + b] = r.x;
+                s_stage[(c0 + ((1 + oct) & 3)) * nbins + b] = r.y;
+                s_stage[(c0 + ((2 + oct) & 3)) * nbins + b] = r.z;
+                s_stage[(c0 + ((3 + oct) & 3)) * nbins + b] = r.w;
             }
         }
     }
@@ -721,6 +735,7 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     const int lanes = QPT == 2 ? 32 : Qc;
     const int groups = kRoiThreads / lanes;
     const int cq = tid % lanes, grp = tid / lanes;
+    const int oct = (cq >> 3) & 3;
     float4* __restrict__ gfeat = reinterpret_cast<float4*>(L.grad[g.level] + (size_t)g.batch * H * W * C + chunk0) + cq;
     const bool pow2 = (spb & (spb - 1)) == 0;
     const float count = (float)spb, inv_count = 1.f / count;  // no max(.,1) in backward (:246)
@@ -730,10 +745,12 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
 #pragma unroll
             for (int u = 0; u < QPT; u++) {
                 const int c0 = (cq + u * 32) * 4;
-                top[u].x = s_stage[(c0 + 0) * nbins + b];
-                top[u].y = s_stage[(c0 + 1) * nbins + b];
-                top[u].z = s_stage[(c0 + 2) * nbins + b];
-                top[u].w = s_stage[(c0 + 3) * nbins + b];
+                float4 r;
+                r.x = s_stage[(c0 + ((0 + oct) & 3)) * nbins + b];
+                r.y = s_stage[(c0 + ((1 + oct) & 3)) * nbins + b];
+                r.z = s_stage[(c0 + ((2 + oct) & 3)) * nbins + b];
+                r.w = s_stage[(c0 + ((3 + oct) & 3)) * nbins + b];
+                top[u] = unrot4(r, oct);
             }
             const int2* lp = s_list + b * cap;
             const int cnt = s_cnt[b];
@@ -966,6 +983,10 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     if (smem > smem_set) {
         cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (const char* cv = getenv("RSDET_ROI_CARVEOUT")) {
+            cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+            cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+        }
         smem_set = smem;
     }
     // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
