@@ -239,6 +239,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 // shared-memory layout of the fast path
 //   taps   : nsamp * Taps (32 B each)
 //   stage  : [4][nbins][Q+1] floats   (k = channel within quad, Q = quads per CTA chunk)
+// merged tap lists: bin pitch cap + 1 entries of 8 bytes, region rounded to 16 bytes (float4 staging follows)
+__host__ __device__ inline size_t list_bytes(size_t nbins, size_t cap) { return (8 * nbins * (cap + 1) + 15) & ~(size_t)15; }
 __host__ __device__ inline int quads_per_chunk(int C) { return (C / 4) < 64 ? (C / 4) : 64; }
 
 // ---------------------------------------------------------------------------------- per-RoI geometry
@@ -316,7 +318,8 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
 // RoI (A1) AND merged per bin (A2): taps of the bin's samples that land on the same pixel are summed
 // into one (offset, weight) entry and zero-weight taps are dropped; on the benchmark proposals 16 taps
 // collapse to ~9.  Offsets are in 16-byte units of the channels-last map (one mad.wide per address).
-//   s_list [nbins*cap] int2 {offset, weight bits}, s_cnt [nbins], tmp: 3*nbins*cap words of scratch.
+//   s_list [nbins*(cap+1)] int2 {offset, weight bits} (bin pitch cap + 1: conflict-free per-bin lanes),
+//   s_cnt [nbins], tmp: 3*nbins*(cap+1) words of scratch.
 //   unit/base: stored offset = base + pixel * unit (unit = C/4 for float4 addressing, 1 for TMA row indices)
 __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet& L, int H, int W, int2* s_list, int* s_cnt,
                                                 float* tmp, int unit, int base) {
@@ -326,9 +329,11 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
     const int nsamp = nbins * spb, cap = 4 * spb, ntaps = nbins * cap;
     const int C4 = unit;
     int* s_off = reinterpret_cast<int*>(tmp);
-    float* s_w = tmp + ntaps;
-    float* s_wsum = tmp + 2 * ntaps;
-    // A1: one thread per sample
+    float* s_w = tmp + ntaps + nbins;      // room for the cap + 1 pitch
+    float* s_wsum = tmp + 2 * (ntaps + nbins);
+    // A1: one thread per sample.  Scratch pitch per bin = cap + 1 words when the per-bin merge below reads it
+    // with one lane per bin (lane stride 17 words: conflict-free; 16 would be a 16-way bank conflict).
+    const int tp = cap == 16 ? 17 : cap;
     for (int s = tid; s < nsamp; s += kRoiThreads) {
         int b = s / spb, q = s % spb;
         int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
@@ -337,12 +342,42 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         const Taps t = make_taps(H, W, y, x);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            s_off[s * 4 + k] = base + t.o[k] * C4;
-            s_w[s * 4 + k] = t.w[k];
+            s_off[b * tp + q * 4 + k] = base + t.o[k] * C4;
+            s_w[b * tp + q * 4 + k] = t.w[k];
         }
     }
     __syncthreads();
-    if (cap == 16 || cap == 4) {
+    if (cap == 16) {
+        // A2 (2x2 sampling grid, the Oriented R-CNN setting): ONE LANE PER BIN, everything in registers.  The
+        // warp-cooperative variant it replaces (below, still used for cap == 4) spent 32 shuffles per 16 taps:
+        // 4.1 M SHFL per 4000 RoIs = 6.9 M of the kernel's 29.8 M L1 wavefronts (shuffles share the data pipe
+        // of the gather loads, profiles/README.md).  Same arithmetic: a tap is a LEADER if its weight is
+        // non-zero and no earlier live tap of the bin hits the same pixel; a leader adds the weights of its
+        // later duplicates in tap order; leaders are compacted in tap order.
+        for (int b = tid; b < nbins; b += kRoiThreads) {
+            int o[16];
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { o[j] = s_off[b * 17 + j]; w[j] = s_w[b * 17 + j]; }
+            int pos = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float acc = w[j];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i <= j) continue;                            // constant trip count: stays in registers
+                    const bool same = o[i] == o[j] && w[j] != 0.f;   // w[j] == 0: dead or already absorbed
+                    acc += same ? w[i] : 0.f;
+                    w[i] = same ? 0.f : w[i];
+                }
+                if (w[j] != 0.f) s_list[b * 17 + pos++] = make_int2(o[j], __float_as_int(acc));
+            }
+            s_cnt[b] = pos;
+        }
+        __syncthreads();
+        return;
+    }
+    if (cap == 4) {
         // A2 (fast): cap lanes per bin, everything in registers.  Each lane walks the cap lanes of its bin with
         // warp shuffles (uniform trip count): it is a LEADER if no earlier live lane hits the same pixel, and it
         // sums the weights of all live lanes on its pixel in lane order; a ballot of the leaders gives each
@@ -368,7 +403,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
             }
             const unsigned leaders = __ballot_sync(0xffffffffu, leader);
             const unsigned segmask = ((1u << cap) - 1u) << seg;       // cap is 4 or 16 here
-            if (leader) s_list[b * cap + __popc(leaders & segmask & ((1u << lane) - 1u))] = make_int2(o, __float_as_int(wsum));
+            if (leader) s_list[b * (cap + 1) + __popc(leaders & segmask & ((1u << lane) - 1u))] = make_int2(o, __float_as_int(wsum));
             if (in && j == 0) s_cnt[b] = __popc(leaders & segmask);
         }
         __syncthreads();
@@ -397,7 +432,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         const float w = ws[j];
         int pos = 0;
         for (int i = 0; i < j; i++) pos += ws[i] != 0.f;
-        if (w != 0.f) s_list[b * cap + pos] = make_int2(s_off[t], __float_as_int(w));
+        if (w != 0.f) s_list[b * (cap + 1) + pos] = make_int2(s_off[t], __float_as_int(w));
         if (j == cap - 1) s_cnt[b] = pos + (w != 0.f);
     }
     __syncthreads();
@@ -434,8 +469,8 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     const int Qc = min(Q, (C - chunk0) / 4);               // quads in this chunk
     // smem: [merged lists: nbins*cap int2][counts: nbins int, padded][staging [c][bin] | phase-A scratch]
     int2* s_list = reinterpret_cast<int2*>(smem_raw);
-    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
-    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + list_bytes(nbins, cap));
+    float* s_stage = reinterpret_cast<float*>(smem_raw + list_bytes(nbins, cap) + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
     if (!geoms) {
@@ -463,7 +498,7 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
             float4 acc[QPT];
 #pragma unroll
             for (int u = 0; u < QPT; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int2* lp = s_list + b * cap;
+            const int2* lp = s_list + b * (cap + 1);
             const int cnt = s_cnt[b];
             for (int e = 0; e < cnt; e += 4) {
                 int2 en[4];
@@ -570,11 +605,11 @@ roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const
     const int chunk0 = blockIdx.y * 256;
     // smem: [ring 8 warps x kTmaStages x 4 KB | staging [256][nbins] | phase-A scratch][lists][counts][mbarriers]
     const size_t ring_bytes = (size_t)8 * kTmaStages * 4096;
-    const size_t big = max(ring_bytes, max((size_t)256 * nbins * 4, (size_t)12 * nbins * cap));
+    const size_t big = max(ring_bytes, max((size_t)256 * nbins * 4, (size_t)12 * nbins * (cap + 1)));
     float* s_stage = reinterpret_cast<float*>(smem_raw);
     int2* s_list = reinterpret_cast<int2*>(smem_raw + big);
-    int* s_cnt = reinterpret_cast<int*>(smem_raw + big + sizeof(int2) * nbins * cap);
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + big + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + big + list_bytes(nbins, cap));
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + big + list_bytes(nbins, cap) + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
     if (tid == 0) {
@@ -608,14 +643,14 @@ roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const
             if (lane == 0) mbar_expect_tx(bar + istage, 1024u * nrow);
             __syncwarp();
             if (lane < nrow) {
-                const int r = s_list[ib * cap + ie + lane].x;
+                const int r = s_list[ib * (cap + 1) + ie + lane].x;
                 const float* src = L.feat[g.level] + (size_t)r * C + chunk0;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(ring + istage * 4096 + lane * 1024)), "l"(src), "r"(1024u), "r"(smem_u32(bar + istage)) : "memory");
             }
         } else if (lane == 0) {
             const int cnt = s_cnt[ib];
-            const int2* lp = s_list + ib * cap;
+            const int2* lp = s_list + ib * (cap + 1);
             const int r0 = lp[ie].x, r1 = lp[min(ie + 1, cnt - 1)].x, r2 = lp[min(ie + 2, cnt - 1)].x, r3 = lp[min(ie + 3, cnt - 1)].x;
             mbar_expect_tx(bar + istage, 4096u);
             tma_gather4(ring + istage * 4096, map, chunk0, r0, r1, r2, r3, bar + istage);
@@ -636,7 +671,7 @@ roi_align_fwd_tma_kernel(LevelSet L, const __grid_constant__ TmaMaps maps, const
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         if (b < nbins) {
             const int cnt = s_cnt[b];
-            const int2* lp = s_list + b * cap;
+            const int2* lp = s_list + b * (cap + 1);
             for (int e = 0; e < cnt; e += 4) {
                 float wt[4];
 #pragma unroll
@@ -709,8 +744,8 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     const int chunk0 = blockIdx.y * Q * 4;
     const int Qc = min(Q, (C - chunk0) / 4);
     int2* s_list = reinterpret_cast<int2*>(smem_raw);
-    int* s_cnt = reinterpret_cast<int*>(smem_raw + sizeof(int2) * nbins * cap);
-    float* s_stage = reinterpret_cast<float*>(smem_raw + sizeof(int2) * nbins * cap + ((nbins * 4 + 15) & ~15));
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + list_bytes(nbins, cap));
+    float* s_stage = reinterpret_cast<float*>(smem_raw + list_bytes(nbins, cap) + ((nbins * 4 + 15) & ~15));
     __shared__ RoiGeom s_g;
 
     if (!geoms) {
@@ -752,7 +787,7 @@ roi_align_bwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
                 r.w = s_stage[(c0 + ((3 + oct) & 3)) * nbins + b];
                 top[u] = unrot4(r, oct);
             }
-            const int2* lp = s_list + b * cap;
+            const int2* lp = s_list + b * (cap + 1);
             const int cnt = s_cnt[b];
             for (int e = 0; e < cnt; e++) {
                 const int2 en = lp[e];
@@ -864,8 +899,8 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
 static size_t fwd_smem_bytes(const rsdet_roi_align_cfg* c) {
     size_t nbins = (size_t)c->pooled_h * c->pooled_w;
     size_t ntaps = nbins * 4 * c->sampling_ratio * c->sampling_ratio;
-    size_t stage = sizeof(float) * 4 * nbins * quads_per_chunk(c->channels), tmp = 12 * ntaps;
-    return 8 * ntaps + ((nbins * 4 + 15) & ~(size_t)15) + (stage > tmp ? stage : tmp);
+    size_t stage = sizeof(float) * 4 * nbins * quads_per_chunk(c->channels), tmp = 12 * (ntaps + nbins);
+    return list_bytes(nbins, ntaps / nbins) + ((nbins * 4 + 15) & ~(size_t)15) + (stage > tmp ? stage : tmp);
 }
 
 static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
@@ -910,8 +945,8 @@ static size_t tma_smem_bytes(const rsdet_roi_align_cfg* c) {
     size_t nbins = (size_t)c->pooled_h * c->pooled_w, cap = 4 * (size_t)c->sampling_ratio * c->sampling_ratio;
     size_t big = (size_t)8 * kTmaStages * 4096;
     if (256 * nbins * 4 > big) big = 256 * nbins * 4;
-    if (12 * nbins * cap > big) big = 12 * nbins * cap;
-    return big + 8 * nbins * cap + ((nbins * 4 + 15) & ~(size_t)15) + 8 * 8 * kTmaStages + 64 + 1024;
+    if (12 * nbins * (cap + 1) > big) big = 12 * nbins * (cap + 1);
+    return big + list_bytes(nbins, cap) + ((nbins * 4 + 15) & ~(size_t)15) + 8 * 8 * kTmaStages + 64 + 1024;
 }
 
 static bool tma_path_ok(const rsdet_roi_align_cfg* c) {
