@@ -29,6 +29,8 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <cstdio>
+
 #include "common.cuh"
 #include "nms_engine.cuh"
 #include "poly_iou.cuh"
@@ -581,7 +583,8 @@ __global__ void prep_shared_kernel(const float* __restrict__ boxes, int n, RBox*
 
 template <bool GE>
 __global__ void __launch_bounds__(kNmsThreads)
-ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long long* __restrict__ ov, int* __restrict__ counter) {
+ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long long* __restrict__ ov, int pitch,
+                int* __restrict__ counter) {
     __shared__ RBox s_row[64];
     __shared__ RBox s_col[64];
     __shared__ unsigned short s_queue[64 * 64];
@@ -639,8 +642,8 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
                 const float iou_ba = rotated_iou_pair<kNmsThreads>(s_col[c], s_row[r], s_pts + tid);
                 d_ba = GE ? iou_ba >= thr : iou_ba > thr;
             }
-            if (d_ab) atomicOr(&ov[(size_t)a * T + (b >> 6)], 1ull << (b & 63));
-            if (d_ba) atomicOr(&ov[(size_t)b * T + (a >> 6)], 1ull << (a & 63));
+            if (d_ab) atomicOr(&ov[(size_t)a * pitch + (b >> 6)], 1ull << (b & 63));
+            if (d_ba) atomicOr(&ov[(size_t)b * pitch + (a >> 6)], 1ull << (a & 63));
         }
     }
 }
@@ -650,7 +653,7 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
 // diagonal block of the class order is gathered bit by bit (256 threads, warp ballots).
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov,
-                 int n_boxes, uint8_t* __restrict__ keep_sorted) {
+                 int pitch, int n_boxes, uint8_t* __restrict__ keep_sorted) {
     extern __shared__ unsigned long long s_remv[];
     __shared__ int s_box2[2][64];  // double-buffered: the OR phase of block b overlaps the loads of block b+1
     __shared__ unsigned int s_diag32[128];
@@ -683,7 +686,7 @@ reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, 
                 bool bit = false;
                 if (i < nr && j < nr && j > i) {
                     const int a = s_box[i], c = s_box[j];
-                    bit = (ov[(size_t)a * T + (c >> 6)] >> (c & 63)) & 1ull;
+                    bit = (ov[(size_t)a * pitch + (c >> 6)] >> (c & 63)) & 1ull;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, bit);
                 if (lane == 0) s_diag32[idx >> 5] = m;
@@ -711,11 +714,159 @@ reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, 
                         unsigned long long acc = 0ull;
 #pragma unroll
                         for (int i = 0; i < 16; i++)
-                            if ((kb16 >> i) & 1u) acc |= ov[(size_t)s_box[rg * 16 + i] * T + w];
+                            if ((kb16 >> i) & 1u) acc |= ov[(size_t)s_box[rg * 16 + i] * pitch + w];
                         if (acc) atomicOr(&s_remv[w], acc);
                     }
                 }
             }
+        }
+    }
+}
+
+// Staged variant of the scan above for n_boxes <= 8192 (the per-tile case: 4000 boxes -> 63 words per row).  The
+// matrix rows a class will need do not depend on its keep decisions, so block b+1's 64 rows are loaded into
+// registers (16-byte loads, one warp per row; the row pitch in global memory is even) while block b is
+// resolved from shared memory, and stored to the other shared buffer at the end of the block.  Per block:
+//   gather  thread (j, quarter) extracts "i suppresses j" for 16 rows i -> 64 column masks   (16 independent LDS)
+//   resolve one warp, fixed point over the column masks                                      (a few ballots)
+//   OR      remv |= rows of the kept candidates, 4 partial ORs per word then one merge       (no atomics)
+// Measured on B200 (clock64, 4000 candidates per class): 7 900 cycles per block for the L2-resident variant
+// (two dependent L2 round trips in gather and OR) -> see profiles/README.md for this one.
+template <int NCH>  // 64-word chunks per row: 1 (n_boxes <= 4096) or 2 (<= 8192)
+__global__ void __launch_bounds__(kReduceThreads, 1)
+reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov,
+                        int pitch, int n_boxes, uint8_t* __restrict__ keep_sorted) {
+    extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][partials: 4 x Ts][rows: 2 x 64 x Ts][cand: n_boxes ints]
+    __shared__ __align__(8) unsigned short s_col16[256];  // s_col16[4j + q]: rows i in quarter q (i < j) that suppress j
+    __shared__ unsigned long long s_keep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nseg = tb.hdr[0];
+    const int T = (n_boxes + 63) >> 6;
+    const int Ts = T | 1;                          // odd shared-memory pitch: lanes on different rows hit different banks
+    unsigned long long* s_remv = s_dyn;
+    unsigned long long* s_part = s_dyn + Ts;
+    unsigned long long* s_rows = s_dyn + 5 * Ts;
+    int* s_cand = reinterpret_cast<int*>(s_dyn + 5 * Ts + 2 * 64 * (size_t)Ts);
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int st = tb.seg_start[s];
+        const int ns = min(tb.seg_start[s + 1] - st, n_boxes);  // one candidate per (box, class): ns <= n_boxes
+        const int nblk = (ns + 63) >> 6;
+        __syncthreads();
+        for (int j = tid; j < Ts; j += kReduceThreads) s_remv[j] = 0ull;
+        for (int p = tid; p < ns; p += kReduceThreads) s_cand[p] = idx_ls[st + p] / cand_per_box;
+        __syncthreads();
+        // warp w holds rows w, w+8, ..., w+56 of the next block: lane l the words 2l, 2l+1 of every 64-word chunk
+        ulonglong2 nxt[8][NCH];
+        auto fetch = [&](int b) {
+            const int nr = min(64, ns - b * 64);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = warp + 8 * k;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const int w = ch * 64 + 2 * lane;
+                    nxt[k][ch] = make_ulonglong2(0ull, 0ull);
+                    if (i < nr && w < pitch)
+                        nxt[k][ch] = *reinterpret_cast<const ulonglong2*>(ov + (size_t)s_cand[b * 64 + i] * pitch + w);
+                }
+            }
+        };
+        auto stash = [&](int b) {
+            unsigned long long* dst = s_rows + (size_t)(b & 1) * 64 * Ts;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = warp + 8 * k;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const int w = ch * 64 + 2 * lane;
+                    if (w < Ts) dst[i * Ts + w] = nxt[k][ch].x;
+                    if (w + 1 < Ts) dst[i * Ts + w + 1] = nxt[k][ch].y;
+                }
+            }
+        };
+        if (nblk > 0) { fetch(0); stash(0); }
+        __syncthreads();
+        for (int b = 0; b < nblk; b++) {
+            const int nr = min(64, ns - b * 64);
+            const int* box = s_cand + b * 64;
+            const unsigned long long* R = s_rows + (size_t)(b & 1) * 64 * Ts;
+            if (b + 1 < nblk) fetch(b + 1);  // in flight while this block is resolved
+            {
+                const int j = tid & 63, q = tid >> 6;
+                unsigned bits = 0u;
+                if (j < nr) {
+                    const int c = box[j];
+                    const unsigned long long* col = R + (c >> 6);
+                    const int sh = c & 63;
+#pragma unroll
+                    for (int ii = 0; ii < 16; ii++) {
+                        const int i = q * 16 + ii;
+                        bits |= (unsigned)((col[i * Ts] >> sh) & 1ull) << ii;
+                    }
+                    // rows i >= j (and rows past the block) do not count
+                    const int lim = j - q * 16;
+                    bits &= lim >= 16 ? 0xffffu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+                }
+                s_col16[4 * j + q] = (unsigned short)bits;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // greedy resolve as a fixed point: a candidate dies once a KEPT lower candidate suppresses it and
+                // is kept once every lower candidate that suppresses it is dead; the lowest undecided candidate
+                // is always decidable, so the loop ends after at most 64 rounds (a handful in practice).
+                unsigned long long col[2];
+                bool und[2];
+                unsigned long long dead = 0ull, kept = 0ull;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = lane + 32 * h;
+                    col[h] = *reinterpret_cast<const unsigned long long*>(&s_col16[4 * j]);
+                    const int a = j < nr ? box[j] : -1;
+                    const bool rem = a < 0 || ((s_remv[a >> 6] >> (a & 63)) & 1ull);
+                    dead |= (unsigned long long)__ballot_sync(0xffffffffu, rem) << (32 * h);
+                    und[h] = !rem;
+                }
+                while (true) {
+                    bool nd[2], nk[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        nd[h] = und[h] && (col[h] & kept) != 0ull;
+                        nk[h] = und[h] && !nd[h] && (col[h] & ~dead) == 0ull;
+                        und[h] = und[h] && !nd[h] && !nk[h];
+                    }
+                    const unsigned long long d2 = (unsigned long long)__ballot_sync(0xffffffffu, nd[0]) |
+                                                  ((unsigned long long)__ballot_sync(0xffffffffu, nd[1]) << 32);
+                    const unsigned long long k2 = (unsigned long long)__ballot_sync(0xffffffffu, nk[0]) |
+                                                  ((unsigned long long)__ballot_sync(0xffffffffu, nk[1]) << 32);
+                    if ((d2 | k2) == 0ull) break;
+                    dead |= d2;
+                    kept |= k2;
+                }
+                if (lane == 0) s_keep = kept;
+            }
+            __syncthreads();
+            const unsigned long long kb = s_keep;
+            if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            {
+                // partial ORs: row group rg = tid / 64 covers 16 rows, lane column w (+64 for the second chunk)
+                const int jj = tid & 63, rg = tid >> 6;
+                const unsigned kb16 = (unsigned)((kb >> (rg * 16)) & 0xffffull);
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const int w = ch * 64 + jj;
+                    if (w < Ts) {
+                        unsigned long long acc = 0ull;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) acc |= ((kb16 >> i) & 1u) ? R[(rg * 16 + i) * Ts + w] : 0ull;
+                        s_part[rg * Ts + w] = acc;
+                    }
+                }
+            }
+            if (b + 1 < nblk) stash(b + 1);
+            __syncthreads();
+            for (int w = tid; w < Ts; w += kReduceThreads)
+                s_remv[w] |= s_part[w] | s_part[Ts + w] | s_part[2 * Ts + w] | s_part[3 * Ts + w];
+            __syncthreads();  // next block's rows and this block's ORs are in place
         }
     }
 }
@@ -898,23 +1049,33 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     if (shared) {
         // 4'. one directed decision matrix for all classes, 5'. per-class scans through it
         const int nb = a.n_shared, Tov = (nb + 63) / 64;
+        const int pitch = (Tov + 1) & ~1;  // even row pitch: 16-byte aligned rows for the staged scan's vector loads
         RBox* sb = (RBox*)boxes;
         prep_shared_kernel<<<ceil_div(nb, 256), 256, 0, st>>>(a.shared_boxes, nb, sb);
-        cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * Tov, st);
+        cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * pitch, st);
         cudaMemsetAsync(cnt_scratch + 32, 0, sizeof(int), st);
         long long tiles = (long long)Tov * (Tov + 1) / 2;
         int grid = (int)(tiles < (long long)kNumSMs * 5 ? tiles : (long long)kNumSMs * 5);
         if (a.kind == RSDET_NMS_ROTATED_GE)
-            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, cnt_scratch + 32);
+            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, cnt_scratch + 32);
         else
-            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, cnt_scratch + 32);
-        size_t smem = sizeof(unsigned long long) * (size_t)Tov;
+            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, cnt_scratch + 32);
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(reduce_ov_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(reduce_ov_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr2 = true;
         }
-        reduce_ov_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, idx_ls, a.cand_per_box, mask, nb, keep_sorted);
+        const size_t Ts = (size_t)(Tov | 1);
+        const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)nb;
+        if (Tov <= 64 && staged <= 200 * 1024)
+            reduce_ov_staged_kernel<1><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+        else if (Tov <= 128 && staged <= 200 * 1024)
+            reduce_ov_staged_kernel<2><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+        else
+            reduce_ov_kernel<<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (size_t)Tov, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch,
+                                                                                                      nb, keep_sorted);
         count_launch(5);
     } else {
     // 4. suppression mask over the upper-triangular tiles of every segment
@@ -1130,7 +1291,7 @@ extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const i
 // every class holds at most n candidates -> the block-sparse mask needs at most C * n * ceil(n/64) words
 static size_t mc_mask_words(int n, int num_classes) {
     size_t N = (size_t)(n > 0 ? n : 1);
-    return (size_t)(num_classes > 0 ? num_classes : 1) * N * ((N + 63) / 64);
+    return (size_t)(num_classes > 0 ? num_classes : 1) * N * ((N + 63) / 64 + 1);  // + 1: the shared matrix uses an even row pitch
 }
 
 extern "C" size_t rsdet_multiclass_nms_rotated_workspace_bytes(int n, int num_classes) {
