@@ -330,6 +330,16 @@ def run_ours(args, rank, world, local_rank):
     ms_head = timed(lambda: core.oriented_head_results(rois5, cls_logits, deltas, NUM_CLASSES, True, [0.] * 5,
                                                        [0.1, 0.1, 0.2, 0.2, 0.1], SCORE_THR, 1.0), reps)
 
+    # oriented RPN proposal stage for one 1024^2 tile (5 levels, 3 anchors, 262k anchors -> 4000)
+    from rs_detection_b200.jdet.models.boxes.anchor_generator import AnchorGenerator
+    rpn_shapes = [(256, 256), (128, 128), (64, 64), (32, 32), (16, 16)]
+    rpn_cls_np, rpn_reg_np = W.rpn_outputs(rpn_shapes, 3, 5)
+    rpn_cls = [torch.from_numpy(x).to(dev) for x in rpn_cls_np]
+    rpn_reg = [torch.from_numpy(x).to(dev) for x in rpn_reg_np]
+    rpn_anc = AnchorGenerator(strides=[4, 8, 16, 32, 64], ratios=[0.5, 1.0, 2.0], scales=[8]).grid_anchors(rpn_shapes, device=dev)
+    ms_rpn = timed(lambda: core.rpn_proposals(rpn_cls, rpn_reg, rpn_anc, 3, True, K_ROIS, K_ROIS, 0.8, 0), reps)
+    del rpn_cls, rpn_reg
+
     # ---- roofline of the dominant HBM kernel: roi_align_fwd_kernel (one launch per tile)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -442,7 +452,8 @@ def run_ours(args, rank, world, local_rank):
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
                 "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3),
-                "head_tail_4000x10_ms": ms_head, "head_tail_rois_per_s": K_ROIS / (ms_head * 1e-3)},
+                "head_tail_4000x10_ms": ms_head, "head_tail_rois_per_s": K_ROIS / (ms_head * 1e-3),
+                "rpn_proposals_262k_anchors_ms": ms_rpn, "rpn_anchors_per_s": 261888 / (ms_rpn * 1e-3)},
         }
         print(json.dumps(line))
     if world > 1:

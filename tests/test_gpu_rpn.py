@@ -86,3 +86,37 @@ def test_rpn_bad_config(cuda):
     x = torch.zeros((3, 4, 4), device="cuda")
     with pytest.raises(AssertionError):
         core.rpn_proposals([x], [torch.zeros((17, 4, 4), device="cuda")], [torch.zeros((48, 4), device="cuda")], 3)
+
+
+def test_rpn_vs_golden(cuda):
+    """Committed fixture (tests/golden/make_golden_rpn.py): scores / levels / top-k rows exact, boxes within
+    the decode tolerance, and at least 99 % of the fixture's kept rows kept (near-threshold pairs may flip)."""
+    import os
+    from rs_detection_b200 import core
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn_golden.npz"))
+    shapes = ((48, 48), (24, 24), (12, 12), (6, 6), (3, 3))
+    cls, reg = W.rpn_outputs(shapes, 3, 21)
+    from rs_detection_b200.jdet.models.boxes.anchor_generator import AnchorGenerator
+    anchors = AnchorGenerator(strides=list(STRIDES), ratios=[0.5, 1.0, 2.0], scales=[8]).grid_anchors(shapes)
+    assert np.array_equal(anchors[2].cpu().numpy(), g["anchors_l2"])
+    dets, cnt, c_obb, _, c_score, c_level = core.rpn_proposals(_cuda(cls), _cuda(reg), anchors, 3, True, 600, 400, 0.8, 0,
+                                                                want_candidates=True)
+    c_obb, c_score, c_level = c_obb.cpu().numpy(), c_score.cpu().numpy(), c_level.cpu().numpy()
+    live_rows = np.nonzero(np.isfinite(c_score))[0]
+    # rows whose width / height sits within 1e-3 of the size threshold may fall on either side (sinf / cosf ulps)
+    flipped = np.setxor1d(live_rows, g["cand_rows"])
+    assert flipped.size <= 4 and np.all(c_obb[flipped][:, 2:4].min(1) < 1e-3)
+    common, ia, ib = np.intersect1d(live_rows, g["cand_rows"], return_indices=True)
+    assert np.array_equal(c_level[common], g["cand_level"][ib])
+    assert np.allclose(c_score[common], g["cand_score"][ib], atol=1e-6)
+    # candidates with scores one ulp apart may swap places (expf vs glibc exp): match boxes per level as sets
+    lv = g["cand_level"][ib]
+    for l in np.unique(lv):
+        a, b = c_obb[common][lv == l][:, :4], g["cand_obb"][ib][lv == l][:, :4]
+        d = np.abs(a[:, None, :] - b[None, :, :]).max(-1).min(1)
+        assert d.max() < 5e-3, (l, d.max())
+    k = int(cnt.item())
+    got = dets[:k].cpu().numpy()
+    assert abs(k - g["dets"].shape[0]) <= 4
+    common = np.intersect1d(np.round(got[:, 5], 6), np.round(g["dets"][:, 5], 6)).size
+    assert common >= 0.99 * g["dets"].shape[0]

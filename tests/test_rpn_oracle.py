@@ -48,3 +48,18 @@ def test_level_offsets_separate_levels():
     assert keep.tolist() == [0, 2] and dets.shape == (2, 6)
     assert O.rpn_level_offset_nms(p, s, np.array([0, 0, 0]), 0.8, 10)[1].tolist() == [0]
     assert O.rpn_level_offset_nms(p, s, np.array([0, 1, 2]), 0.8, 2)[1].tolist() == [0, 1]
+
+
+def test_rpn_golden_drift_guard():
+    import os
+    import workloads as W
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn_golden.npz"))
+    shapes, strides = ((48, 48), (24, 24), (12, 12), (6, 6), (3, 3)), (4, 8, 16, 32, 64)
+    cls, reg = W.rpn_outputs(shapes, 3, 21)
+    anchors = [O.anchor_grid(s, st) for s, st in zip(shapes, strides)]
+    assert np.array_equal(anchors[2], g["anchors_l2"])
+    p, s, ids, rows = O.rpn_candidates(cls, reg, anchors, True, 600, 0)
+    assert np.array_equal(rows, g["cand_rows"]) and np.array_equal(ids, g["cand_level"])
+    assert np.allclose(p, g["cand_obb"], rtol=1e-5, atol=1e-3) and np.allclose(s, g["cand_score"], atol=1e-6)
+    dets, keep, _ = O.rpn_level_offset_nms(g["cand_obb"], g["cand_score"], g["cand_level"].astype(np.int64), 0.8, 400)
+    assert np.array_equal(keep, g["keep"]) and np.array_equal(dets, g["dets"])
