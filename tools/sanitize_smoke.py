@@ -39,5 +39,17 @@ cfg = core.make_roi_cfg([(1, 8, 32, 32)], [0.25], (3, 5), 0, 0)
 out = core.roi_align_rotated_forward(cfg, [torch.randn((1, 8, 32, 32), device="cuda")], t(W.proposals(40, 5, canvas=128)))
 core.roi_align_rotated_backward(cfg, torch.randn_like(out), t(W.proposals(40, 5, canvas=128)), [(1, 8, 32, 32)])
 core.oriented_head_results(t(b), torch.randn((n, 11), device="cuda"), torch.randn((n, 5), device="cuda") * 0.1, 10, True, [0.] * 5, [0.1, 0.1, 0.2, 0.2, 0.1], 0.05, 1.5)[2].item()
+# staged per-class scan with two 64-word chunks per row (n > 4096 boxes), and the L2-resident fallback (n > 8192)
+for nb in (5000, 9000):
+    bb = W.rotated_boxes(nb, 7, canvas=2048, smin=8, smax=96)
+    core.multiclass_nms_rotated(t(bb), t(W.class_scores(nb, 3, 2)), 0.05, 0.1, 500)[2].item()
+# RPN proposal stage (score, sort, decode, offsets, HBB_P1 NMS, output) and VOC matching
+from rs_detection_b200.jdet.models.boxes.anchor_generator import AnchorGenerator
+shp = ((32, 32), (16, 16), (8, 8))
+cls_, reg_ = W.rpn_outputs(shp, 3, 1)
+anc = AnchorGenerator(strides=[4, 8, 16], ratios=[0.5, 1.0, 2.0], scales=[8]).grid_anchors(shp)
+core.rpn_proposals([t(x) for x in cls_], [t(x) for x in reg_], anc, 3, True, 500, 300, 0.8, 0)[1].item()
+cls2, reg2 = W.rpn_outputs(shp, 3, 2, 2)
+core.rpn_proposals([t(x) for x in cls2], [t(x) for x in reg2], anc, 3, False, 100, 50, 0.7, 4.0, want_candidates=True)[1].item()
 torch.cuda.synchronize()
 print("sanitize smoke done")
