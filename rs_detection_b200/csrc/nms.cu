@@ -448,7 +448,7 @@ __device__ __forceinline__ unsigned long long resolve_block(const unsigned long 
 
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted,
-              unsigned long long* __restrict__ pub_keep, int* __restrict__ pub_flag) {
+              unsigned long long* __restrict__ pub_keep, int* __restrict__ pub_flag, int skip_small) {
     extern __shared__ unsigned long long s_remv[];
     __shared__ unsigned long long s_diag[2][64];
     __shared__ unsigned long long s_keep;
@@ -460,7 +460,7 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
         const int st = tb.seg_start[s];
         const int ns = tb.seg_start[s + 1] - st;
         const int T = (ns + 63) >> 6;
-        if (T >= kCoopMinBlocks) continue;
+        if (T >= kCoopMinBlocks || skip_small) continue;  // skip_small: reduce_ov_staged_kernel<2, true> took them
         if ((small_rank++ % (int)gridDim.x) != (int)blockIdx.x) continue;
         const unsigned long long* m = mask + tb.mask_off[s];
         __syncthreads();
@@ -732,29 +732,39 @@ reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, 
 //   OR      remv |= rows of the kept candidates, 4 partial ORs per word then one merge       (no atomics)
 // Measured on B200 (clock64, 4000 candidates per class): 7 900 cycles per block for the L2-resident variant
 // (two dependent L2 round trips in gather and OR) -> see profiles/README.md for this one.
-template <int NCH>  // 64-word chunks per row: 1 (n_boxes <= 4096) or 2 (<= 8192)
+// IDENT = true is the same scan for the generic engine's block-sparse mask: rows and bit positions are the
+// group's own sorted positions (candidate p -> row p, bit p), the pitch is the group's ceil(n_s / 64), and
+// groups of >= kCoopMinBlocks blocks are left to reduce_kernel's cooperative phase.
+template <int NCH, bool IDENT>  // NCH 64-word chunks per row: 1 (<= 4096 columns) or 2 (<= 8192)
 __global__ void __launch_bounds__(kReduceThreads, 1)
-reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov,
-                        int pitch, int n_boxes, uint8_t* __restrict__ keep_sorted) {
+reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov_base,
+                        int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted) {
     extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][partials: 4 x Ts][rows: 2 x 64 x Ts][cand: n_boxes ints]
     __shared__ __align__(8) unsigned short s_col16[256];  // s_col16[4j + q]: rows i in quarter q (i < j) that suppress j
     __shared__ unsigned long long s_keep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nseg = tb.hdr[0];
-    const int T = (n_boxes + 63) >> 6;
-    const int Ts = T | 1;                          // odd shared-memory pitch: lanes on different rows hit different banks
-    unsigned long long* s_remv = s_dyn;
-    unsigned long long* s_part = s_dyn + Ts;
-    unsigned long long* s_rows = s_dyn + 5 * Ts;
-    int* s_cand = reinterpret_cast<int*>(s_dyn + 5 * Ts + 2 * 64 * (size_t)Ts);
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
         const int st = tb.seg_start[s];
-        const int ns = min(tb.seg_start[s + 1] - st, n_boxes);  // one candidate per (box, class): ns <= n_boxes
+        const int ns_all = tb.seg_start[s + 1] - st;
+        const int n_boxes = IDENT ? ns_all : n_boxes_arg;
+        const int ns = min(ns_all, n_boxes);            // shared matrix: one candidate per (box, class), ns <= n_boxes
         const int nblk = (ns + 63) >> 6;
+        const int T = (n_boxes + 63) >> 6;
+        if (IDENT && (T >= kCoopMinBlocks || T > 64 * NCH)) continue;
+        const int pitch = IDENT ? T : pitch_arg;
+        const unsigned long long* ov = IDENT ? ov_base + tb.mask_off[s] : ov_base;
+        const int Ts = T | 1;                           // odd shared-memory pitch: lanes on different rows hit different banks
+        unsigned long long* s_remv = s_dyn;
+        unsigned long long* s_part = s_dyn + Ts;
+        unsigned long long* s_rows = s_dyn + 5 * Ts;
+        int* s_cand = reinterpret_cast<int*>(s_dyn + 5 * Ts + 2 * 64 * (size_t)Ts);
         __syncthreads();
         for (int j = tid; j < Ts; j += kReduceThreads) s_remv[j] = 0ull;
-        for (int p = tid; p < ns; p += kReduceThreads) s_cand[p] = idx_ls[st + p] / cand_per_box;
+        if (!IDENT)
+            for (int p = tid; p < ns; p += kReduceThreads) s_cand[p] = idx_ls[st + p] / cand_per_box;
         __syncthreads();
+        auto cand = [&](int p) { return IDENT ? p : s_cand[p]; };
         // warp w holds rows w, w+8, ..., w+56 of the next block: lane l the words 2l, 2l+1 of every 64-word chunk
         ulonglong2 nxt[8][NCH];
         auto fetch = [&](int b) {
@@ -766,8 +776,15 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
                 for (int ch = 0; ch < NCH; ch++) {
                     const int w = ch * 64 + 2 * lane;
                     nxt[k][ch] = make_ulonglong2(0ull, 0ull);
-                    if (i < nr && w < pitch)
-                        nxt[k][ch] = *reinterpret_cast<const ulonglong2*>(ov + (size_t)s_cand[b * 64 + i] * pitch + w);
+                    if (i < nr && w < pitch) {
+                        const unsigned long long* src = ov + (size_t)cand(b * 64 + i) * pitch + w;
+                        if (IDENT) {  // odd pitches: rows are only 8-byte aligned
+                            nxt[k][ch].x = src[0];
+                            if (w + 1 < pitch) nxt[k][ch].y = src[1];
+                        } else {
+                            nxt[k][ch] = *reinterpret_cast<const ulonglong2*>(src);
+                        }
+                    }
                 }
             }
         };
@@ -788,14 +805,13 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
         __syncthreads();
         for (int b = 0; b < nblk; b++) {
             const int nr = min(64, ns - b * 64);
-            const int* box = s_cand + b * 64;
             const unsigned long long* R = s_rows + (size_t)(b & 1) * 64 * Ts;
             if (b + 1 < nblk) fetch(b + 1);  // in flight while this block is resolved
             {
                 const int j = tid & 63, q = tid >> 6;
                 unsigned bits = 0u;
                 if (j < nr) {
-                    const int c = box[j];
+                    const int c = cand(b * 64 + j);
                     const unsigned long long* col = R + (c >> 6);
                     const int sh = c & 63;
 #pragma unroll
@@ -821,7 +837,7 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
                 for (int h = 0; h < 2; h++) {
                     const int j = lane + 32 * h;
                     col[h] = *reinterpret_cast<const unsigned long long*>(&s_col16[4 * j]);
-                    const int a = j < nr ? box[j] : -1;
+                    const int a = j < nr ? cand(b * 64 + j) : -1;
                     const bool rem = a < 0 || ((s_remv[a >> 6] >> (a & 63)) & 1ull);
                     dead |= (unsigned long long)__ballot_sync(0xffffffffu, rem) << (32 * h);
                     und[h] = !rem;
@@ -1063,16 +1079,16 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(reduce_ov_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(reduce_ov_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(reduce_ov_staged_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(reduce_ov_staged_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr2 = true;
         }
         const size_t Ts = (size_t)(Tov | 1);
         const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)nb;
         if (Tov <= 64 && staged <= 200 * 1024)
-            reduce_ov_staged_kernel<1><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+            reduce_ov_staged_kernel<1, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
         else if (Tov <= 128 && staged <= 200 * 1024)
-            reduce_ov_staged_kernel<2><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+            reduce_ov_staged_kernel<2, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
         else
             reduce_ov_kernel<<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (size_t)Tov, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch,
                                                                                                       nb, keep_sorted);
@@ -1086,11 +1102,19 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         static bool attr_done = false;
         if (!attr_done) {
             cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(reduce_ov_staged_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_done = true;
         }
-        if ((N + 63) / 64 >= (size_t)kCoopMinBlocks) cudaMemsetAsync(pub_flag, 0, sizeof(int) * (2 * N / 64 + 8), st);
-        reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag);
+        // groups of < kCoopMinBlocks blocks: staged scan (rows through shared memory); larger ones: cooperative phase
+        const size_t Tmax = (size_t)(kCoopMinBlocks - 1) | 1;
+        reduce_ov_staged_kernel<2, true><<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (5 * Tmax + 2 * 64 * Tmax), st>>>(
+            tb, nullptr, 1, mask, 0, 0, keep_sorted);
         count_launch();
+        if ((N + 63) / 64 >= (size_t)kCoopMinBlocks) {
+            cudaMemsetAsync(pub_flag, 0, sizeof(int) * (2 * N / 64 + 8), st);
+            reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag, 1);
+            count_launch();
+        }
     }
     }
     // 6. outputs
