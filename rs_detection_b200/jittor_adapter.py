@@ -161,3 +161,59 @@ def make_roi_align(version):
             return g, None
 
     return _Fn
+
+
+def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None):
+    """jdet.ops.nms_rotated.multiclass_nms_rotated (nms_rotated.py:540-596) as ONE jt.code: candidate selection,
+    per-class NMS through the shared decision matrix, score sort and top-k on the device.  Returns
+    (dets (k,6), labels (k,)) like the reference; k is read back once (the reference syncs in jt.where)."""
+    jt = _jt()
+    n, C = multi_scores.shape[0], multi_scores.shape[1] - 1
+    if n == 0:
+        return jt.zeros((0, 6)), jt.zeros((0,)).int32()
+    cap = max_num if max_num > 0 else n * C
+    ins = [multi_bboxes, multi_scores] + ([score_factors] if score_factors is not None else [])
+    dets, labels, cnt = jt.code([(cap, 6), (cap,), (1,)], [multi_bboxes.dtype, "int64", "int32"], ins, cuda_header=_HEADER,
+                                cuda_src=r'''
+        typedef size_t (*ws_t)(int, int);
+        typedef int (*fn_t)(const float*, int, const float*, int, int, float, float, int, const float*, float*, int64_t*,
+                            int32_t*, void*, size_t, void*);
+        static ws_t ws = (ws_t)rsdet_sym("rsdet_multiclass_nms_rotated_workspace_bytes");
+        static fn_t fn = (fn_t)rsdet_sym("rsdet_multiclass_nms_rotated");
+        int n = in1_shape0, C = in1_shape1 - 1;
+        Scratch s(ws(n, C));
+        rsdet_check(fn(in0_p, in0_shape1, in1_p, n, C, %r, %r, %d, %s, out0_p, (int64_t*)out1_p, (int32_t*)out2_p,
+                       s.p, s.bytes, 0), "multiclass_nms_rotated");''' % (float(score_thr), float(nms_cfg.get('iou_thr', 0.1)),
+                                                                          int(max_num), "in2_p" if score_factors is not None else "nullptr"))
+    k = int(cnt.item())
+    return dets[:k], labels[:k]
+
+
+def rpn_proposals(cls_scores, bbox_preds, mlvl_anchors, num_anchors, use_sigmoid=True, nms_pre=2000, nms_post=2000,
+                  nms_thresh=0.8, min_bbox_size=0, means=(0.,) * 6, stds=(1., 1., 1., 1., 0.5, 0.5)):
+    """OrientedRPNHead._get_bboxes_single (oriented_rpn_head.py:136-216) as one jt.code over 3L inputs."""
+    jt = _jt()
+    L = len(cls_scores)
+    ins = list(cls_scores) + list(bbox_preds) + list(mlvl_anchors)
+    lv = "".join("cfg.height[%d] = in%d_shape1; cfg.width[%d] = in%d_shape2; cls[%d] = in%d_p; reg[%d] = in%d_p; anc[%d] = in%d_p;\n"
+                 % (l, l, l, l, l, l, l, L + l, l, 2 * L + l) for l in range(L))
+    dets, cnt = jt.code([(nms_post, 6), (1,)], [cls_scores[0].dtype, "int32"], ins, cuda_header=_HEADER, cuda_src=r'''
+        struct Cfg { int num_levels; int height[8], width[8]; int num_anchors, use_sigmoid, nms_pre, nms_post; double nms_thresh;
+                     float min_bbox_size, means[6], stds[6], wh_ratio_clip; };
+        Cfg cfg; memset(&cfg, 0, sizeof cfg);
+        const float *cls[8], *reg[8], *anc[8];
+        cfg.num_levels = %d; cfg.num_anchors = %d; cfg.use_sigmoid = %d; cfg.nms_pre = %d; cfg.nms_post = %d;
+        cfg.nms_thresh = %r; cfg.min_bbox_size = %r; cfg.wh_ratio_clip = 0.016f;
+        const float mm[6] = {%s}, ss[6] = {%s};
+        for (int k = 0; k < 6; k++) { cfg.means[k] = mm[k]; cfg.stds[k] = ss[k]; }
+        %s
+        typedef size_t (*ws_t)(const Cfg*);
+        typedef int (*fn_t)(const Cfg*, const float* const*, const float* const*, const float* const*, float*, int32_t*, float*,
+                            float*, float*, int32_t*, void*, size_t, void*);
+        static ws_t ws = (ws_t)rsdet_sym("rsdet_rpn_proposals_workspace_bytes");
+        static fn_t fn = (fn_t)rsdet_sym("rsdet_rpn_proposals");
+        Scratch s(ws(&cfg));
+        rsdet_check(fn(&cfg, cls, reg, anc, out0_p, (int32_t*)out1_p, nullptr, nullptr, nullptr, nullptr, s.p, s.bytes, 0),
+                    "rpn_proposals");''' % (L, num_anchors, int(use_sigmoid), nms_pre, nms_post, float(nms_thresh), float(min_bbox_size),
+                                           ", ".join("%rf" % float(m) for m in means), ", ".join("%rf" % float(v) for v in stds), lv))
+    return dets[:int(cnt.item())]

@@ -120,3 +120,33 @@ def test_rpn_vs_golden(cuda):
     assert abs(k - g["dets"].shape[0]) <= 4
     common = np.intersect1d(np.round(got[:, 5], 6), np.round(g["dets"][:, 5], 6)).size
     assert common >= 0.99 * g["dets"].shape[0]
+
+
+def test_rpn_edge_cases(cuda, oracle):
+    """nms_pre <= 0 keeps every anchor in its original order (oriented_rpn_head.py:183); a size filter that drops
+    everything yields zero proposals and an all-zero output block; a single level needs no offsets."""
+    from rs_detection_b200 import core
+    shapes = ((12, 10), (6, 5))
+    cls, reg = W.rpn_outputs(shapes, 3, 31)
+    anchors = [oracle.anchor_grid(s, st) for s, st in zip(shapes, STRIDES)]
+    dets, cnt, c_obb, c_hbb, c_score, c_level = core.rpn_proposals(_cuda(cls), _cuda(reg), _cuda(anchors), 3, True, 0, 50, 0.7, -1,
+                                                                    want_candidates=True)
+    n_all = sum(h * w * 3 for h, w in shapes)
+    assert c_score.shape[0] == n_all
+    _, s, ids, _ = oracle.rpn_candidates(cls, reg, anchors, True, 0, -1)
+    assert np.allclose(c_score.cpu().numpy(), s, atol=1e-6) and np.array_equal(c_level.cpu().numpy(), ids)
+    keep = oracle.jt_nms(np.concatenate([c_hbb.cpu().numpy(), c_score.cpu().numpy()[:, None]], 1), 0.7)[:50]
+    k = int(cnt.item())
+    assert k == len(keep)
+    assert np.array_equal(dets[:k].cpu().numpy(), np.concatenate([c_obb.cpu().numpy(), c_score.cpu().numpy()[:, None]], 1)[keep])
+    # everything filtered
+    dets, cnt = core.rpn_proposals(_cuda(cls), _cuda(reg), _cuda(anchors), 3, True, 100, 50, 0.7, 1e6)
+    assert int(cnt.item()) == 0 and not dets.cpu().numpy().any()
+    # single level
+    dets, cnt, c_obb, c_hbb, c_score, _ = core.rpn_proposals(_cuda(cls[:1]), _cuda(reg[:1]), _cuda(anchors[:1]), 3, True, 64, 64, 0.5, 0,
+                                                              want_candidates=True)
+    live = np.isfinite(c_score.cpu().numpy())
+    keep = oracle.jt_nms(np.concatenate([c_hbb.cpu().numpy()[live], c_score.cpu().numpy()[live][:, None]], 1), 0.5)[:64]
+    assert int(cnt.item()) == len(keep)
+    assert np.array_equal(dets[:len(keep)].cpu().numpy(),
+                          np.concatenate([c_obb.cpu().numpy()[live], c_score.cpu().numpy()[live][:, None]], 1)[keep])
