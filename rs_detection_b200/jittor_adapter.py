@@ -171,18 +171,18 @@ def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms_cfg, max_n
     n, C = multi_scores.shape[0], multi_scores.shape[1] - 1
     if n == 0:
         return jt.zeros((0, 6)), jt.zeros((0,)).int32()
-    cap = max_num if max_num > 0 else n * C
+    cap = n * C  # the C entry point needs n*C rows of output whatever max_num is
     ins = [multi_bboxes, multi_scores] + ([score_factors] if score_factors is not None else [])
-    dets, labels, cnt = jt.code([(cap, 6), (cap,), (1,)], [multi_bboxes.dtype, "int64", "int32"], ins, cuda_header=_HEADER,
+    dets, labels, cnt = jt.code([(cap, 6), (cap,), (1,)], [multi_bboxes.dtype, "int32", "int32"], ins, cuda_header=_HEADER,
                                 cuda_src=r'''
         typedef size_t (*ws_t)(int, int);
-        typedef int (*fn_t)(const float*, int, const float*, int, int, float, float, int, const float*, float*, int64_t*,
+        typedef int (*fn_t)(const float*, int, const float*, int, int, float, float, int, const float*, float*, int32_t*,
                             int32_t*, void*, size_t, void*);
         static ws_t ws = (ws_t)rsdet_sym("rsdet_multiclass_nms_rotated_workspace_bytes");
         static fn_t fn = (fn_t)rsdet_sym("rsdet_multiclass_nms_rotated");
         int n = in1_shape0, C = in1_shape1 - 1;
         Scratch s(ws(n, C));
-        rsdet_check(fn(in0_p, in0_shape1, in1_p, n, C, %r, %r, %d, %s, out0_p, (int64_t*)out1_p, (int32_t*)out2_p,
+        rsdet_check(fn(in0_p, in0_shape1, in1_p, n, C, %r, %r, %d, %s, out0_p, (int32_t*)out1_p, (int32_t*)out2_p,
                        s.p, s.bytes, 0), "multiclass_nms_rotated");''' % (float(score_thr), float(nms_cfg.get('iou_thr', 0.1)),
                                                                           int(max_num), "in2_p" if score_factors is not None else "nullptr"))
     k = int(cnt.item())
