@@ -362,33 +362,54 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end through the public API with host buffers
     ext = OrientedSingleRoIExtractor(dict(type='ROIAlignRotated_v1', output_size=7, sampling_ratio=2), W.CHANNELS,
                                      list(W.STRIDES), extend_factor=EXTEND)
-    pinned = [([torch.from_numpy(f).pin_memory() for f in fs], torch.from_numpy(r).pin_memory(), torch.from_numpy(b).pin_memory(),
-               torch.from_numpy(s).pin_memory()) for fs, r, b, s in tiles_np]
-    h2d_bytes = sum(sum(f.numel() for f in fs) * 4 + (r.numel() + b.numel() + s.numel()) * 4 for fs, r, b, s in pinned)
+    # one pinned slab per tile (pyramid levels, rois, boxes, scores back to back) and one device slab per slot:
+    # a tile goes up as ONE 89.7 MB copy (seven separate copies cost 8 % of the box's 55 GB/s pinned H2D rate)
+    def carve(flat, shapes_):
+        out, off = [], 0
+        for sh in shapes_:
+            n = int(np.prod(sh))
+            out.append(flat[off:off + n].view(sh))
+            off += n
+        return out
+
+    part_shapes = [tuple(sh) for sh in shapes] + [(K_ROIS, 6), (K_ROIS, 5), (K_ROIS, NUM_CLASSES + 1)]
+    slab_elems = sum(int(np.prod(sh)) for sh in part_shapes)
+    pinned = []
+    for fs, r, b, s_ in tiles_np:
+        flat = torch.empty(slab_elems, dtype=torch.float32).pin_memory()
+        for dst, src in zip(carve(flat, part_shapes), list(fs) + [r, b, s_]):
+            dst.copy_(torch.from_numpy(src))
+        pinned.append(flat)
+    h2d_bytes = sum(f.numel() * 4 for f in pinned)
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [([torch.empty(s, device=dev) for s in shapes], torch.empty((K_ROIS, 6), device=dev),
-              torch.empty((K_ROIS, 5), device=dev), torch.empty((K_ROIS, NUM_CLASSES + 1), device=dev)) for _ in range(2)]
+    slabs = [torch.empty(slab_elems, dtype=torch.float32, device=dev) for _ in range(2)]
+    slots = []
+    for sl in slabs:
+        v = carve(sl, part_shapes)
+        slots.append((v[:len(shapes)], v[len(shapes)], v[len(shapes) + 1], v[len(shapes) + 2]))
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     d2h = [0]
 
+    prefetched = [False]
+
     def e2e_step():
         comp = torch.cuda.current_stream()
-        for e in freed:
-            e.record(comp)
+        if not prefetched[0]:
+            for e in freed:
+                e.record(comp)
         results = []
 
         def upload(i):
             sl = slots[i % 2]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[i % 2])
-                fs, r, b, s = pinned[i]
-                for d, h in zip(sl[0], fs):
-                    d.copy_(h, non_blocking=True)
-                sl[1].copy_(r, non_blocking=True); sl[2].copy_(b, non_blocking=True); sl[3].copy_(s, non_blocking=True)
+                slabs[i % 2].copy_(pinned[i], non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
-        upload(0)
+        if not prefetched[0]:
+            upload(0)
+        prefetched[0] = False
         nbytes = 0
         for i in range(TILES_PER_GPU):
             if i + 1 < TILES_PER_GPU:
@@ -399,6 +420,11 @@ def run_ours(args, rank, world, local_rank):
             polys = obb2poly(sl[2])
             dets, labels = multiclass_nms_rotated(sl[2], sl[3], SCORE_THR, dict(type='nms_rotated', iou_thr=IOU_THR), MAX_NUM)
             freed[i % 2].record(comp)
+            if i + 1 == TILES_PER_GPU and TILES_PER_GPU % 2 == 0:
+                # steady-state serving: the next step's first tile starts its upload while this step's last tile is
+                # computed and read back (the copy engine would otherwise idle at every step boundary)
+                upload(0)
+                prefetched[0] = True
             dh, lh, ph = dets.cpu(), labels.cpu(), polys.cpu()  # detections + polygons back to the host
             nbytes += dh.numel() * 4 + lh.numel() * 4 + ph.numel() * 4
             results.append((dh.shape[0], float(feats_roi[0, 0, 0, 0])))
@@ -408,6 +434,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup - 1)):
         e2e_step()
     barrier()
+    prefetched[0] = False  # the first timed step uploads its own first tile: all K x 8 uploads are inside the region
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
