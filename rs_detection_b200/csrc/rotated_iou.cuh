@@ -94,14 +94,56 @@ __device__ __forceinline__ float rbox_inter_upper_bound(const RBox& a, const RBo
     return ub;
 }
 
+// Area of the rectangle with half extents (hw, hh) cut by the half-plane n.p <= s, n a unit vector given in the
+// rectangle's frame through p1 = hw*|nx|, p2 = hh*|ny|.  The chord length perpendicular to n is a trapezoid in s:
+// support [-(p1+p2), p1+p2], plateau |s| <= |p1-p2| of height L = area / (2 max(p1, p2)).
+__device__ __forceinline__ float rect_halfplane_area(float s, float p1, float p2, float L) {
+    const float S = p1 + p2, P = fabsf(p1 - p2);
+    const float inv_ramp = 1.f / fmaxf(S - P, 1e-30f);
+    s = fminf(fmaxf(s, -S), S);
+    const float t1 = fminf(s, -P) + S;            // left ramp, 0 .. S-P
+    const float t2 = fminf(fmaxf(s, -P), P) + P;  // plateau, 0 .. 2P
+    const float t3 = fmaxf(s, P) - P;             // right ramp, 0 .. S-P
+    return L * (0.5f * t1 * t1 * inv_ramp + t2 + t3 - 0.5f * t3 * t3 * inv_ramp);
+}
+
+// Upper bound of area(A n B) from the two strips that make up B: A n B is inside A n {|u_B.(p - c_B)| <= hw_B}
+// and inside A n {|v_B.(p - c_B)| <= hh_B}; each is a rectangle cut by two parallel lines (closed form above).
+// Much tighter than the axis-aligned bound for pairs at an angle: on the benchmark proposals it leaves 1.03x
+// the truly suppressing pairs for the exact clipper instead of 1.6x.
+__device__ __forceinline__ float rbox_strip_bound_one(const RBox& a, const RBox& b, float dx, float dy, float slack) {
+    const float px = dx * a.ax + dy * a.ay, py = dy * a.ax - dx * a.ay;  // centre of B in the frame of A
+    const float c = a.ax * b.ax + a.ay * b.ay, s = a.ax * b.ay - a.ay * b.ax;  // u_B = (c, s), v_B = (-s, c) in that frame
+    float ub;
+    {
+        const float d = px * c + py * s, p1 = a.hw * fabsf(c), p2 = a.hh * fabsf(s);
+        const float L = a.area / fmaxf(2.f * fmaxf(p1, p2), 1e-30f), h = b.hw + slack;
+        ub = rect_halfplane_area(d + h, p1, p2, L) - rect_halfplane_area(d - h, p1, p2, L);
+    }
+    {
+        const float d = py * c - px * s, p1 = a.hw * fabsf(s), p2 = a.hh * fabsf(c);
+        const float L = a.area / fmaxf(2.f * fmaxf(p1, p2), 1e-30f), h = b.hh + slack;
+        ub = fminf(ub, rect_halfplane_area(d + h, p1, p2, L) - rect_halfplane_area(d - h, p1, p2, L));
+    }
+    return ub;
+}
+
 // true when IoU(a,b) certainly stays below `thr` (with a 1e-4 guard band, two orders of magnitude above
 // the float error of the reference's IoU): the pair cannot suppress, whatever the clipper would return.
+// First stage: the cheap axis-aligned bound, evaluated on every pair of a tile.
 __device__ __forceinline__ bool rbox_iou_below(const RBox& a, const RBox& b, float thr) {
     float ub = rbox_inter_upper_bound(a, b);
     if (ub <= 0.f) return true;
     ub *= 1.001f;
-    float un = a.area + b.area - ub;
-    return ub < (thr - 1e-4f) * un;
+    return ub < (thr - 1e-4f) * (a.area + b.area - ub);
+}
+// Second stage: the strip bound, ~200 instructions, meant for the COMPACTED survivors of the first stage
+// (evaluated inside the all-pairs loop it costs more than it saves: one surviving lane stalls its warp).
+__device__ __forceinline__ bool rbox_iou_below_strips(const RBox& a, const RBox& b, float thr) {
+    const float dx = b.x - a.x, dy = b.y - a.y, slack = 1e-3f * (a.r + b.r);
+    float ub = fminf(rbox_strip_bound_one(a, b, dx, dy, slack), rbox_strip_bound_one(b, a, -dx, -dy, slack));
+    ub = fmaxf(ub, 0.f) * 1.001f;
+    return ub < (thr - 1e-4f) * (a.area + b.area - ub);
 }
 
 __device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - bx * ay; }
