@@ -630,12 +630,10 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = (n + 63) >> 6;
     const int total = T * (T + 1) / 2;
-    while (true) {
+    // one tile per CTA when the grid covers them all (the usual case: the block scheduler balances the uneven
+    // tiles and no CTA waits on a global counter), grid-stride otherwise
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
         __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(counter, 1);
-        __syncthreads();
-        const int u = s_tile;
-        if (u >= total) break;
         int rb = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)u)) * 0.5);
         rb = max(0, min(rb, T - 1));
         while (rb > 0 && rb * T - rb * (rb - 1) / 2 > u) rb--;
@@ -1140,7 +1138,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * pitch, st);
         cudaMemsetAsync(cnt_scratch + 32, 0, sizeof(int), st);
         long long tiles = (long long)Tov * (Tov + 1) / 2;
-        int grid = (int)(tiles < (long long)kNumSMs * 5 ? tiles : (long long)kNumSMs * 5);
+        int grid = (int)(tiles < (1ll << 22) ? tiles : (1ll << 22));
         if (a.kind == RSDET_NMS_ROTATED_GE)
             ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, cnt_scratch + 32);
         else
