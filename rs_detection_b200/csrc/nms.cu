@@ -53,10 +53,12 @@ template <> struct Traits<RSDET_NMS_ROTATED> {
     using Box = RBox; using Raw = float; using Thr = float;
     static constexpr int kRow = 5; static constexpr bool kScratch = true;
     __device__ static Box prep(const Raw* r) { return prep_rbox(r, 0); }
-    // bounding circles, then the oriented-frame upper bound of the IoU (exact decisions, see rotated_iou.cuh)
-    __device__ static bool candidate(const Box& a, const Box& b, Thr thr) {
-        return rbox_may_overlap(a, b) && !rbox_iou_below(a, b, thr);
-    }
+    // filter cascade (exact decisions, see rotated_iou.cuh): bounding circles on every pair, then -- dense, on
+    // the compacted survivors -- the axis-aligned and the strip upper bounds of the IoU
+    static constexpr bool kRefine = true;
+    __device__ static bool cheap(const Box& a, const Box& b) { return rbox_may_overlap(a, b); }
+    __device__ static bool refine1(const Box& a, const Box& b, Thr thr) { return !rbox_iou_below(a, b, thr); }
+    __device__ static bool refine2(const Box& a, const Box& b, Thr thr) { return !rbox_iou_below_strips(a, b, thr); }
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2* q) {
         return rotated_iou_pair<kNmsThreads>(a, b, q) > thr;
     }
@@ -70,7 +72,10 @@ template <> struct Traits<RSDET_NMS_POLY> {
     using Box = PolyBox; using Raw = float; using Thr = float;
     static constexpr int kRow = 8; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; for (int i = 0; i < 8; i++) b.p[i] = r[i]; return b; }
-    __device__ static bool candidate(const Box&, const Box&, Thr) { return true; }  // see poly_iou.cuh
+    static constexpr bool kRefine = false;
+    __device__ static bool cheap(const Box&, const Box&) { return true; }  // see poly_iou.cuh
+    __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return poly_iou_f32(a.p, b.p) > thr; }
 };
 template <> struct Traits<RSDET_NMS_MERGE> {
@@ -87,7 +92,10 @@ template <> struct Traits<RSDET_NMS_MERGE> {
         b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2;
         return b;
     }
-    __device__ static bool candidate(const Box& a, const Box& b, Thr) { return merge_hbb_overlap(a, b); }
+    static constexpr bool kRefine = false;
+    __device__ static bool cheap(const Box& a, const Box& b) { return merge_hbb_overlap(a, b); }
+    __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
     // survivors are `iou <= thr` (result_merge.py:118)
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return !(iou_poly_d(a, b) <= thr); }
 };
@@ -95,9 +103,12 @@ template <> struct Traits<RSDET_NMS_HBB> {
     using Box = HBox; using Raw = double; using Thr = double;
     static constexpr int kRow = 4; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
-    __device__ static bool candidate(const Box& a, const Box& b, Thr) {
+    static constexpr bool kRefine = false;
+    __device__ static bool cheap(const Box& a, const Box& b) {
         return fmin(a.x2, b.x2) > fmax(a.x1, b.x1) && fmin(a.y2, b.y2) > fmax(a.y1, b.y1);
     }
+    __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
     // merge.py:21-25: survivors are `iou < thresh`
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
         double tlx = fmax(a.x1, b.x1), tly = fmax(a.y1, b.y1), brx = fmin(a.x2, b.x2), bry = fmin(a.y2, b.y2);
@@ -114,9 +125,12 @@ template <> struct Traits<RSDET_NMS_HBB_P1> {
     using Box = HBoxF; using Raw = float; using Thr = double;
     static constexpr int kRow = 4; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
-    __device__ static bool candidate(const Box& a, const Box& b, Thr) {
+    static constexpr bool kRefine = false;
+    __device__ static bool cheap(const Box& a, const Box& b) {
         return fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1) + 1.f > 0.f && fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1) + 1.f > 0.f;
     }
+    __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
         float iw = fmaxf(0.f, fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1) + 1.f);
         float ih = fmaxf(0.f, fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1) + 1.f);
@@ -329,6 +343,35 @@ segments_from_counts_kernel(const int* __restrict__ counts, int C, double thr, S
 }
 
 // ----------------------------------------------------------------------------- mask tiles
+// Filter cascade of the mask kernels: every stage runs DENSE over the compacted survivors of the previous one
+// (bounding circles on all 64 x 64 pairs -> axis-aligned bound -> strip bound -> exact clipper).  Evaluated
+// inside the all-pairs loop, the bounds cost ~100 warp instructions per 32 pairs at 5 active lanes, because
+// nearly every warp holds at least one pair whose circles touch (16 % of the pairs on the bench proposals).
+template <typename Pred>
+__device__ __forceinline__ int compact_queue(const unsigned short* __restrict__ in, int n_in, unsigned short* __restrict__ out,
+                                             int* s_counter, Pred keep) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) *s_counter = 0;
+    __syncthreads();
+    for (int qi = tid; qi < ((n_in + 31) & ~31); qi += kNmsThreads) {
+        int p = 0;
+        bool live = qi < n_in;
+        if (live) {
+            p = in[qi];
+            live = keep(p);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(s_counter, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) out[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+        }
+    }
+    __syncthreads();
+    return *s_counter;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kNmsThreads)
 mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable tb, unsigned long long* __restrict__ mask) {
@@ -338,8 +381,14 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
     __shared__ Box s_col[64];
     __shared__ unsigned short s_queue[64 * 64];
     __shared__ unsigned long long s_mask[64];
+    constexpr int kQ2 = Tr::kRefine ? 1024 : 1;
+    __shared__ unsigned short s_queue2[kQ2];
+    __shared__ unsigned short s_queue3[kQ2];
     __shared__ float2 s_pts[Tr::kScratch ? 24 * kNmsThreads : 1];
+    __shared__ int s_wsum[kNmsThreads / 32];
     __shared__ int s_count;
+    __shared__ int s_count2;
+    __shared__ int s_count3;
     __shared__ long long s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -378,37 +427,62 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
         } else if (tid - 64 < nc) {
             s_col[tid - 64] = boxes[st + cb * 64 + tid - 64];
         }
-        if (tid == 0) s_count = 0;
         __syncthreads();
 
-        // phase 1: each thread owns ONE column box (registers) and sweeps 32 rows; a warp reads the same
-        // row box at a time (shared-memory broadcast), so the filter runs without bank conflicts.
+        // stage 1: each thread owns ONE column box (registers) and sweeps 32 rows with the cheap test; a warp
+        // reads the same row box at a time (shared-memory broadcast).  Hits go to a register bit mask and are
+        // compacted once per tile.
         const bool diag = rb == cb;
         {
             const int c = tid & 63, rhalf = tid >> 6;
-            Box colbox;
-            if (c < nc) colbox = s_col[c];
-#pragma unroll 2
-            for (int k = 0; k < 32; k++) {
-                const int r = 2 * k + rhalf;
-                bool cand = r < nr && c < nc && (!diag || c > r);
-                if (cand) cand = Tr::candidate(s_row[r], colbox, thr);
-                unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 6) | c);
+            unsigned hits = 0u;
+            if (c < nc) {
+                const Box colbox = s_col[c];
+#pragma unroll 4
+                for (int k = 0; k < 32; k++) {
+                    const int r = 2 * k + rhalf;
+                    const bool cand = r < nr && (!diag || c > r) && Tr::cheap(s_row[r], colbox);
+                    hits |= (cand ? 1u : 0u) << k;
                 }
+            }
+            const int mine = __popc(hits);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) s_wsum[tid >> 5] = incl;
+            __syncthreads();
+            int pos = incl - mine;
+            for (int w = 0; w < (tid >> 5); w++) pos += s_wsum[w];
+            if (tid == kNmsThreads - 1) s_count = pos + mine;
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_queue[pos++] = (unsigned short)(((2 * k + rhalf) << 6) | c);
             }
         }
         __syncthreads();
         const int cnt = s_count;
-        for (int qi = tid; qi < cnt; qi += kNmsThreads) {
-            int p = s_queue[qi];
-            int r = p >> 6, c = p & 63;
-            if (Tr::suppress(s_row[r], s_col[c], thr, s_pts + (Tr::kScratch ? tid : 0)))
-                atomicOr(&s_mask[r], 1ull << c);
+        if (Tr::kRefine) {
+            for (int q0 = 0; q0 < cnt; q0 += kQ2) {
+                const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2,
+                                             [&](int p) { return Tr::refine1(s_row[p >> 6], s_col[p & 63], thr); });
+                const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3,
+                                             [&](int p) { return Tr::refine2(s_row[p >> 6], s_col[p & 63], thr); });
+                for (int qi = tid; qi < n3; qi += kNmsThreads) {
+                    const int p = s_queue3[qi];
+                    const int r = p >> 6, c = p & 63;
+                    if (Tr::suppress(s_row[r], s_col[c], thr, s_pts + (Tr::kScratch ? tid : 0))) atomicOr(&s_mask[r], 1ull << c);
+                }
+            }
+        } else {
+            for (int qi = tid; qi < cnt; qi += kNmsThreads) {
+                const int p = s_queue[qi];
+                const int r = p >> 6, c = p & 63;
+                if (Tr::suppress(s_row[r], s_col[c], thr, s_pts + (Tr::kScratch ? tid : 0))) atomicOr(&s_mask[r], 1ull << c);
+            }
         }
         __syncthreads();
         if (tid < nr) mask[tb.mask_off[s] + (long long)(rb * 64 + tid) * T + cb] = s_mask[tid];
@@ -579,35 +653,6 @@ reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t*
 __global__ void prep_shared_kernel(const float* __restrict__ boxes, int n, RBox* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = prep_rbox(boxes + (size_t)i * 5, 0);
-}
-
-// Filter cascade of ov_tiles_kernel: every stage runs DENSE over the compacted survivors of the previous one
-// (bounding circles on all 64 x 64 pairs -> axis-aligned bound -> strip bound -> exact clipper).  Evaluated
-// inside the all-pairs loop, the bounds cost ~100 warp instructions per 32 pairs at 5 active lanes, because
-// nearly every warp holds at least one pair whose circles touch (16 % of the pairs on the bench proposals).
-template <typename Pred>
-__device__ __forceinline__ int compact_queue(const unsigned short* __restrict__ in, int n_in, unsigned short* __restrict__ out,
-                                             int* s_counter, Pred keep) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) *s_counter = 0;
-    __syncthreads();
-    for (int qi = tid; qi < ((n_in + 31) & ~31); qi += kNmsThreads) {
-        int p = 0;
-        bool live = qi < n_in;
-        if (live) {
-            p = in[qi];
-            live = keep(p);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(s_counter, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (live) out[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
-        }
-    }
-    __syncthreads();
-    return *s_counter;
 }
 
 template <bool GE>
