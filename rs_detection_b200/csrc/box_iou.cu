@@ -6,10 +6,11 @@
 //
 // Kernel plan (FP32-ALU bound; no tensor cores -- nothing here is a contraction):
 //   prep  : one thread per box -> RBox (double sin/cos once per box, not once per pair)
-//   tiles : 64x64 IoU tile per CTA iteration, 128 threads.  Phase 1 runs the bounding-circle test on
-//           all 4096 pairs (coalesced zero stores for the rejects) and warp-aggregates the survivors
-//           into a shared-memory queue; phase 2 hands ONE queued pair to each thread, so the heavy
-//           clipper runs on dense warps instead of the reference's 1-in-10 active lanes.
+//   tiles : 64x64 IoU tile per CTA iteration, 128 threads.  Stage 1 runs the bounding-circle test on
+//           all 4096 pairs (coalesced zero stores for the rejects; hits in a register bit mask, compacted
+//           once per tile); stage 2 runs the separating-axis test densely on the survivors; stage 3 hands
+//           ONE remaining pair to each thread, so the heavy clipper runs on dense warps instead of the
+//           reference's 1-in-10 active lanes.
 #include "common.cuh"
 #include "rotated_iou.cuh"
 
@@ -33,8 +34,12 @@ box_iou_tiles_kernel(const RBox* __restrict__ rows, int n1, const RBox* __restri
     __shared__ RBox s_row[kTile];
     __shared__ RBox s_col[kTile];
     __shared__ unsigned short s_queue[kTile * kTile];
+    constexpr int kQ2 = 1024;
+    __shared__ unsigned short s_queue2[kQ2];
     __shared__ float2 s_pts[24 * kIouThreads];
+    __shared__ int s_wsum[kIouThreads / 32];
     __shared__ int s_count;
+    __shared__ int s_count2;
 
     const int tiles_x = ceil_div(n2, kTile);
     const int tiles_y = ceil_div(n1, kTile);
@@ -53,41 +58,78 @@ box_iou_tiles_kernel(const RBox* __restrict__ rows, int n1, const RBox* __restri
                 s_col[c] = cols[c0 + c];
             }
         }
-        if (tid == 0) s_count = 0;
         __syncthreads();
 
-        // phase 1: exact-zero filters (bounding circles, then separating axes in both box frames); zero
-        // stores are coalesced (a warp covers 32 consecutive columns of one row); survivors are queued.
+        // stage 1: bounding circles on all 4096 pairs.  Thread = (column, row parity); hits go to a register
+        // bit mask, the rejects get their zeros (a warp covers 32 consecutive columns of one row: coalesced),
+        // and the hits are compacted once per tile (a ballot + atomic per 32 pairs costs more than the test).
         {
             const int c = tid & 63, rhalf = tid >> 6;
-            RBox colbox;
-            if (c < nc) colbox = s_col[c];
-#pragma unroll 2
-            for (int k = 0; k < 32; k++) {
-                const int r = 2 * k + rhalf;
-                bool cand = false;
-                if (r < nr && c < nc) {
-                    cand = rbox_may_overlap(s_row[r], colbox) && rbox_inter_upper_bound(s_row[r], colbox) > 0.f;
-                    if (!cand) out[(size_t)(r0 + r) * n2 + c0 + c] = 0.f;
+            unsigned hits = 0u;
+            if (c < nc) {
+                const float cx = s_col[c].x, cy = s_col[c].y, cr = s_col[c].r;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const int r = 2 * k + rhalf;
+                    if (r < nr) {
+                        const float rs = s_row[r].r + cr, dx = s_row[r].x - cx, dy = s_row[r].y - cy;
+                        const bool cand = (rs >= 0.f) && !(dx * dx + dy * dy > rs * rs);  // == rbox_may_overlap
+                        hits |= (cand ? 1u : 0u) << k;
+                        if (!cand) out[(size_t)(r0 + r) * n2 + c0 + c] = 0.f;
+                    }
                 }
-                unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_count, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (cand) s_queue[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)((r << 6) | c);
-                }
+            }
+            const int mine = __popc(hits);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) s_wsum[tid >> 5] = incl;
+            __syncthreads();
+            int pos = incl - mine;
+            for (int w = 0; w < (tid >> 5); w++) pos += s_wsum[w];
+            if (tid == kIouThreads - 1) s_count = pos + mine;
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_queue[pos++] = (unsigned short)(((2 * k + rhalf) << 6) | c);
             }
         }
         __syncthreads();
 
-        // phase 2: one queued pair per thread
+        // stage 2 (dense over the circle survivors): separating axes in both box frames -> exact zeros;
+        // stage 3: one surviving pair per thread through the exact clipper
         const int cnt = s_count;
-        for (int qi = tid; qi < cnt; qi += kIouThreads) {
-            int p = s_queue[qi];
-            int r = p >> 6, c = p & 63;
-            float iou = rotated_iou_pair<kIouThreads>(s_row[r], s_col[c], s_pts + tid);
-            out[(size_t)(r0 + r) * n2 + c0 + c] = iou;
+        for (int q0 = 0; q0 < cnt; q0 += kQ2) {
+            const int qn = min(kQ2, cnt - q0);
+            if (tid == 0) s_count2 = 0;
+            __syncthreads();
+            for (int qi = tid; qi < ((qn + 31) & ~31); qi += kIouThreads) {
+                int p = 0;
+                bool live = qi < qn;
+                if (live) {
+                    p = s_queue[q0 + qi];
+                    live = rbox_inter_upper_bound(s_row[p >> 6], s_col[p & 63]) > 0.f;
+                    if (!live) out[(size_t)(r0 + (p >> 6)) * n2 + c0 + (p & 63)] = 0.f;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, live);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_count2, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (live) s_queue2[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
+                }
+            }
+            __syncthreads();
+            const int cnt2 = s_count2;
+            for (int qi = tid; qi < cnt2; qi += kIouThreads) {
+                const int p = s_queue2[qi];
+                const int r = p >> 6, c = p & 63;
+                out[(size_t)(r0 + r) * n2 + c0 + c] = rotated_iou_pair<kIouThreads>(s_row[r], s_col[c], s_pts + tid);
+            }
+            __syncthreads();
         }
     }
 }
