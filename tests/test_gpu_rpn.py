@@ -150,3 +150,21 @@ def test_rpn_edge_cases(cuda, oracle):
     assert int(cnt.item()) == len(keep)
     assert np.array_equal(dets[:len(keep)].cpu().numpy(),
                           np.concatenate([c_obb.cpu().numpy()[live], c_score.cpu().numpy()[live][:, None]], 1)[keep])
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.7, 0.8])
+def test_jt_nms_kind_direct(cuda, oracle, thr):
+    """rsdet_nms(kind = RSDET_NMS_HBB_P1) is jt.nms: fp32 boxes, '+1' widths, IoU > thr, result in score order."""
+    from rs_detection_b200 import core
+    from rs_detection_b200._lib import NMS_HBB_P1
+    rng = np.random.default_rng(int(thr * 100))
+    n = 3000
+    c = rng.uniform(0, 600, (n, 2)).astype(np.float32)
+    wh = rng.uniform(4, 120, (n, 2)).astype(np.float32)
+    hb = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    hb[:50] = hb[50:100] + rng.normal(0, 1.0, (50, 4)).astype(np.float32)  # near duplicates
+    sc = W.distinct_scores(n, 17)
+    res = core.nms(NMS_HBB_P1, torch.from_numpy(hb).cuda(), torch.from_numpy(sc).cuda(), thr, want_score=True)
+    got = res.score_idx.cpu().numpy()
+    want = oracle.jt_nms(np.concatenate([hb, sc[:, None]], 1), thr)
+    assert np.array_equal(got, want) and 0 < len(want) < n
