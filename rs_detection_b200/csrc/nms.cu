@@ -658,7 +658,8 @@ __global__ void prep_shared_kernel(const float* __restrict__ boxes, int n, RBox*
 template <bool GE>
 __global__ void __launch_bounds__(kNmsThreads, 5)
 ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long long* __restrict__ ov, int pitch,
-                int* __restrict__ counter) {
+                const uint8_t* __restrict__ only_flagged, const unsigned int* __restrict__ num_flagged) {
+    if (only_flagged && *num_flagged == 0u) return;  // the usual case: every tile's survivors fitted the pair queue
     __shared__ RBox s_row[64];
     __shared__ RBox s_col[64];
     __shared__ unsigned short s_queue[64 * 64];
@@ -678,6 +679,7 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
     // one tile per CTA when the grid covers them all (the usual case: the block scheduler balances the uneven
     // tiles and no CTA waits on a global counter), grid-stride otherwise
     for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        if (only_flagged && !only_flagged[u]) continue;  // CTA-uniform
         __syncthreads();
         int rb = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)u)) * 0.5);
         rb = max(0, min(rb, T - 1));
@@ -757,6 +759,137 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
                 if (d_ba) atomicOr(&ov[(size_t)b * pitch + (a >> 6)], 1ull << (a & 63));
             }
         }
+    }
+}
+
+template <bool GE>
+__global__ void __launch_bounds__(kNmsThreads, 8)
+ov_filter_kernel(const RBox* __restrict__ boxes, int n, float thr, int2* __restrict__ pairs, unsigned int cap,
+                 unsigned int* __restrict__ pair_count, uint8_t* __restrict__ tile_flags) {
+    __shared__ RBox s_row[64];
+    __shared__ RBox s_col[64];
+    __shared__ unsigned short s_queue[64 * 64];
+    constexpr int kQ2 = 1024;
+    __shared__ unsigned short s_queue2[kQ2];
+    __shared__ unsigned short s_queue3[kQ2];
+    __shared__ unsigned int s_base;
+    __shared__ float4 s_rowc[64];
+    __shared__ int s_wsum[kNmsThreads / 32];
+    __shared__ int s_count;
+    __shared__ int s_count2;  // one counter per stage: a stage's result is still being read when the next one resets its own
+    __shared__ int s_count3;
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int T = (n + 63) >> 6;
+    const int total = T * (T + 1) / 2;
+    // one tile per CTA when the grid covers them all (the usual case: the block scheduler balances the uneven
+    // tiles and no CTA waits on a global counter), grid-stride otherwise
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        __syncthreads();
+        int rb = (int)(((2.0 * T + 1.0) - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)u)) * 0.5);
+        rb = max(0, min(rb, T - 1));
+        while (rb > 0 && rb * T - rb * (rb - 1) / 2 > u) rb--;
+        while ((rb + 1) * T - (rb + 1) * rb / 2 <= u) rb++;
+        const int cb = rb + (u - (rb * T - rb * (rb - 1) / 2));
+        const int nr = min(64, n - rb * 64), nc = min(64, n - cb * 64);
+        if (tid < 64) {
+            float4 rc = make_float4(0.f, 0.f, -1e30f, 0.f);
+            if (tid < nr) {
+                const RBox bx = boxes[rb * 64 + tid];
+                s_row[tid] = bx;
+                rc = make_float4(bx.x, bx.y, bx.r, 0.f);
+            }
+            s_rowc[tid] = rc;
+        } else if (tid - 64 < nc) {
+            s_col[tid - 64] = boxes[cb * 64 + tid - 64];
+        }
+        __syncthreads();
+        const bool diag = rb == cb;
+        {   // stage 1: bounding circles, all pairs.  Thread = (column c, row parity): 32 rows against one column,
+            // hits collected in a register bit mask and compacted ONCE per tile (a ballot + atomic per 32 pairs
+            // was 65 % of the kernel's instructions: 16 % of the pairs pass, so every warp iteration paid for it)
+            const int c = tid & 63, rhalf = tid >> 6;
+            unsigned hits = 0u;
+            if (c < nc) {
+                const float cx = s_col[c].x, cy = s_col[c].y, cr = s_col[c].r;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const int r = 2 * k + rhalf;
+                    const float4 rc = s_rowc[r];  // x, y, radius (-1e30 past the last row): one broadcast load
+                    const float rs = rc.z + cr, dx = rc.x - cx, dy = rc.y - cy;
+                    const bool cand = (rs >= 0.f) && !(dx * dx + dy * dy > rs * rs) && (!diag || c > r);  // == rbox_may_overlap
+                    hits |= (cand ? 1u : 0u) << k;
+                }
+            }
+            // exclusive prefix of the per-thread hit counts over the CTA
+            const int mine = __popc(hits);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) s_wsum[tid >> 5] = incl;
+            __syncthreads();
+            int pos = incl - mine;
+            for (int w = 0; w < (tid >> 5); w++) pos += s_wsum[w];
+            if (tid == kNmsThreads - 1) s_count = pos + mine;
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                s_queue[pos++] = (unsigned short)(((2 * k + rhalf) << 6) | c);
+            }
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int q0 = 0; q0 < cnt; q0 += kQ2) {
+            // stage 2: axis-aligned bound; stage 3: strip bound (1.03x the truly suppressing pairs survive)
+            const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2,
+                                         [&](int p) { return !rbox_iou_below(s_row[p >> 6], s_col[p & 63], thr); });
+            const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3,
+                                         [&](int p) { return !rbox_iou_below_strips(s_row[p >> 6], s_col[p & 63], thr); });
+            // survivors go to the global pair queue (ov_clip_kernel evens them out over the whole GPU); a tile
+            // that does not fit is flagged and redone by ov_tiles_kernel
+            if (tid == 0) {
+                const unsigned int base = n3 ? atomicAdd(pair_count, (unsigned int)n3) : 0u;
+                if (n3 && base + (unsigned int)n3 > cap) { tile_flags[u] = 1; atomicAdd(pair_count + 1, 1u); }
+                s_base = base;
+            }
+            __syncthreads();
+            // a reservation that straddles the end still fills its slots below `cap` (ov_clip_kernel reads every slot
+            // below min(count, cap)); the flagged tile is redone as a whole, the duplicates are idempotent ORs
+            const unsigned int base = s_base;
+            for (int qi = tid; qi < n3; qi += kNmsThreads) {
+                if (base + (unsigned int)qi < cap) {
+                    const int p = s_queue3[qi];
+                    pairs[base + qi] = make_int2(rb * 64 + (p >> 6), cb * 64 + (p & 63));
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// exact clipper over the global pair queue: one pair per thread, grid-stride, perfectly balanced
+template <bool GE>
+__global__ void __launch_bounds__(kNmsThreads, 8)
+ov_clip_kernel(const RBox* __restrict__ boxes, const int2* __restrict__ pairs, unsigned int cap, const unsigned int* __restrict__ pair_count,
+               float thr, unsigned long long* __restrict__ ov, int pitch) {
+    __shared__ float2 s_pts[24 * kNmsThreads];
+    const unsigned int count = min(*pair_count, cap);
+    const int tid = threadIdx.x;
+    for (unsigned int i = blockIdx.x * kNmsThreads + tid; i < count; i += gridDim.x * kNmsThreads) {
+        const int2 pr = pairs[i];
+        const RBox A = boxes[pr.x], B = boxes[pr.y];
+        const float iou_ab = rotated_iou_pair<kNmsThreads>(A, B, s_pts + tid);
+        const bool d_ab = GE ? iou_ab >= thr : iou_ab > thr;
+        bool d_ba = d_ab;
+        if (fabsf(iou_ab - thr) <= 1e-5f) {
+            const float iou_ba = rotated_iou_pair<kNmsThreads>(B, A, s_pts + tid);
+            d_ba = GE ? iou_ba >= thr : iou_ba > thr;
+        }
+        if (d_ab) atomicOr(&ov[(size_t)pr.x * pitch + (pr.y >> 6)], 1ull << (pr.y & 63));
+        if (d_ba) atomicOr(&ov[(size_t)pr.y * pitch + (pr.x >> 6)], 1ull << (pr.x & 63));
     }
 }
 
@@ -1181,13 +1314,38 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         RBox* sb = (RBox*)boxes;
         prep_shared_kernel<<<ceil_div(nb, 256), 256, 0, st>>>(a.shared_boxes, nb, sb);
         cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * pitch, st);
-        cudaMemsetAsync(cnt_scratch + 32, 0, sizeof(int), st);
         long long tiles = (long long)Tov * (Tov + 1) / 2;
         int grid = (int)(tiles < (1ll << 22) ? tiles : (1ll << 22));
-        if (a.kind == RSDET_NMS_ROTATED_GE)
-            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, cnt_scratch + 32);
-        else
-            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, cnt_scratch + 32);
+        // the part of the mask buffer the n x pitch matrix does not use holds the tile flags and the pair queue
+        const size_t mask_cap = a.mask_words ? a.mask_words : N * ((N + 63) / 64);
+        const size_t used = (size_t)nb * pitch, flag_words = ((size_t)tiles + 7) / 8 + 1;
+        const bool split = grid == tiles && mask_cap > used + flag_words + 4096;
+        if (split) {
+            uint8_t* tile_flags = (uint8_t*)(mask + used);
+            int2* pairs = (int2*)(mask + used + flag_words);
+            const size_t capz = mask_cap - used - flag_words;
+            const unsigned int cap = (unsigned int)(capz < 0x7fffffffull ? capz : 0x7fffffffull);
+            unsigned int* pair_count = (unsigned int*)(cnt_scratch + 32);
+            cudaMemsetAsync(tile_flags, 0, flag_words * 8, st);
+            cudaMemsetAsync(pair_count, 0, 2 * sizeof(int), st);
+            // one pair per thread when the survivors fit (CTAs past the count exit at once); fallback: few CTAs scan the flags
+            const int cgrid = (int)(tiles < (long long)kNumSMs * 8 ? (long long)kNumSMs * 8 : (tiles < (long long)kNumSMs * 64 ? tiles : (long long)kNumSMs * 64));
+            const int fgrid = (int)(tiles < (long long)kNumSMs * 2 ? tiles : (long long)kNumSMs * 2);
+            if (a.kind == RSDET_NMS_ROTATED_GE) {
+                ov_filter_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, pairs, cap, pair_count, tile_flags);
+                ov_clip_kernel<true><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, (float)a.thr, mask, pitch);
+                ov_tiles_kernel<true><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, tile_flags, pair_count + 1);
+            } else {
+                ov_filter_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, pairs, cap, pair_count, tile_flags);
+                ov_clip_kernel<false><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, (float)a.thr, mask, pitch);
+                ov_tiles_kernel<false><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, tile_flags, pair_count + 1);
+            }
+            count_launch(2);
+        } else if (a.kind == RSDET_NMS_ROTATED_GE) {
+            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, nullptr, nullptr);
+        } else {
+            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, nullptr, nullptr);
+        }
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -80,3 +80,23 @@ def test_multiclass_class_specific_boxes_many_classes(cuda, oracle):
     wd, wl = oracle.multiclass_nms_rotated(bb, sc, 0.02, dict(iou_thr=0.3), 300)
     gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 0.02, dict(iou_thr=0.3), 300)
     assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+
+
+def test_multiclass_dense_cluster_overflows_pair_queue(cuda, oracle):
+    """2500 heavily overlapping boxes, 2 classes: nearly every pair survives the filter cascade, far more than the
+    pair queue carved from the workspace holds, so most tiles take the flagged fallback (ov_tiles_kernel).  The keep
+    set must still be the oracle's."""
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    rng = np.random.default_rng(5)
+    n = 2500
+    b = np.empty((n, 5), np.float32)
+    b[:, :2] = 200 + rng.normal(0, 6.0, (n, 2))
+    b[:, 2] = rng.uniform(60, 90, n)
+    b[:, 3] = rng.uniform(25, 40, n)
+    b[:, 4] = rng.uniform(-0.4, 0.4, n)
+    s = W.class_scores(n, 2, 3, 1.0)
+    got_d, got_l = multiclass_nms_rotated(torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda(), 0.01,
+                                          dict(type='nms_rotated', iou_thr=0.6), 1000)
+    want_d, want_l = oracle.multiclass_nms_rotated(b, s, 0.01, dict(iou_thr=0.6), 1000)
+    assert np.array_equal(got_d.cpu().numpy(), want_d) and np.array_equal(got_l.cpu().numpy(), want_l)
+    assert 0 < want_d.shape[0] < 1000
