@@ -74,6 +74,8 @@ int rsdet_assign_wrt_overlaps(const float* overlaps, int num_gts, int n, float p
 #define RSDET_NMS_MERGE 3   /* dets (n,8) fp64 quads in scene coords; hbb prefilter then polygon IoU > thr:
                                data/devkits/result_merge.py:66-127 + ops/nms_poly.py:247-252              */
 #define RSDET_NMS_HBB 4     /* dets (n,4) fp64 [x1,y1,x2,y2]; suppress IoU >= thr (merge.py:14-27)         */
+#define RSDET_NMS_HBB_P1_F64 6 /* dets (n,4) fp64, "+1" widths, survivors IoU <= thr: py_cpu_nms,
+                               data/devkits/result_merge.py:143-174 (mergebyrec)                          */
 #define RSDET_NMS_HBB_P1 5  /* dets (n,4) fp32 [x1,y1,x2,y2], "+1" widths; suppress IoU > thr: jt.nms as called
                                by models/roi_heads/oriented_rpn_head.py:208 (Jittor 1.3.4.7 misc.py)      */
 
@@ -81,7 +83,7 @@ int rsdet_assign_wrt_overlaps(const float* overlaps, int num_gts, int n, float p
  * group).  Equivalent to the reference's label-gated IoU (ops/nms_rotated.py:281-286) and to one
  * reference call per class / per scene file.
  *   dets    : (n, row_floats(kind)) of fp32 or fp64 as the kind says
- *   scores  : (n) fp32, or fp64 for MERGE/HBB
+ *   scores  : (n) fp32, or fp64 for MERGE/HBB/HBB_P1_F64
  *   labels  : (n) int32 group ids (any values) or NULL
  *   thr     : scalar threshold, used when thr_per_label == NULL
  *   thr_per_label : optional device array indexed by label value (0 <= label < num_thr)

@@ -49,7 +49,8 @@ def write_before_nms(results, save_path, classes):
             f.write(''.join(lines))
 
 
-def mergesingle(dstpath, fullname, nms_threshold_type=0):
+def mergesingle(dstpath, fullname, nms_threshold_type=0, nms="poly"):
+    """nms = "poly": py_cpu_nms_poly_fast (mergebypoly); "rec": py_cpu_nms on 4-coordinate rows (mergebyrec :273-283)."""
     name = os.path.basename(os.path.splitext(fullname)[0])
     by_scene = {}
     with open(fullname) as f:
@@ -67,7 +68,8 @@ def mergesingle(dstpath, fullname, nms_threshold_type=0):
     os.makedirs(dstpath, exist_ok=True)
     with open(os.path.join(dstpath, name + '.txt'), 'w') as out:
         for scene, dets in by_scene.items():
-            for k in O.py_cpu_nms_poly_fast(np.array(dets), thr):
+            fn = O.py_cpu_nms_poly_fast if nms == "poly" else O.py_cpu_nms
+            for k in fn(np.array(dets), thr):
                 d = dets[k]
                 out.write(scene + ' ' + str(d[-1]) + ' ' + ' '.join(str(v) for v in d[:-1]) + '\n')
 

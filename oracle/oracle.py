@@ -634,3 +634,23 @@ def rpn_get_bboxes_single(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid=True
     """oriented_rpn_head.py:136-216 end to end."""
     p, s, i, _ = rpn_candidates(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid, nms_pre, min_bbox_size, means, stds)
     return rpn_level_offset_nms(p, s, i, nms_thresh, nms_post)[0]
+
+
+def py_cpu_nms(dets, thresh):
+    """python/jdet/data/devkits/result_merge.py:143-174: horizontal NMS, float64, '+1' areas, survivors ovr <= thresh.
+    Ties: lower index first (the reference's argsort()[::-1] leaves them unspecified)."""
+    d = np.asarray(dets, np.float64).reshape(-1, 5)
+    x1, y1, x2, y2, sc = d[:, 0], d[:, 1], d[:, 2], d[:, 3], d[:, 4]
+    areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+    order = np.argsort(-sc, kind="stable")
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        r = order[1:]
+        w = np.maximum(0.0, np.minimum(x2[i], x2[r]) - np.maximum(x1[i], x1[r]) + 1)
+        h = np.maximum(0.0, np.minimum(y2[i], y2[r]) - np.maximum(y1[i], y1[r]) + 1)
+        inter = w * h
+        ovr = inter / (areas[i] + areas[r] - inter)
+        order = r[np.where(ovr <= thresh)[0]]
+    return keep

@@ -15,8 +15,8 @@ from . import _lib
 from ._lib import (MAX_LEVELS, NMS_HBB, NMS_MERGE, NMS_POLY, NMS_ROTATED, NMS_ROTATED_GE, RoiAlignCfg, check, load, ptr,
                    stream_ptr, workspace)
 
-_F64_KINDS = (NMS_MERGE, NMS_HBB)
-_ROW = {NMS_ROTATED: 5, NMS_ROTATED_GE: 5, NMS_POLY: 8, NMS_MERGE: 8, NMS_HBB: 4, 5: 4}  # 5 = NMS_HBB_P1 (jt.nms)
+_F64_KINDS = (NMS_MERGE, NMS_HBB, 6)  # 6 = NMS_HBB_P1_F64 (py_cpu_nms)
+_ROW = {NMS_ROTATED: 5, NMS_ROTATED_GE: 5, NMS_POLY: 8, NMS_MERGE: 8, NMS_HBB: 4, 5: 4, 6: 4}  # 5 = NMS_HBB_P1 (jt.nms)
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:

@@ -118,6 +118,25 @@ template <> struct Traits<RSDET_NMS_HBB> {
     }
 };
 
+// py_cpu_nms (data/devkits/result_merge.py:143-174, used by mergebyrec): float64, "+1" widths, survivors ovr <= thresh
+template <> struct Traits<RSDET_NMS_HBB_P1_F64> {
+    using Box = HBox; using Raw = double; using Thr = double;
+    static constexpr int kRow = 4; static constexpr bool kScratch = false;
+    static constexpr bool kRefine = false;
+    __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
+    __device__ static bool cheap(const Box& a, const Box& b) {
+        return fmin(a.x2, b.x2) - fmax(a.x1, b.x1) + 1.0 > 0.0 && fmin(a.y2, b.y2) - fmax(a.y1, b.y1) + 1.0 > 0.0;
+    }
+    __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
+        double w = fmax(0.0, fmin(a.x2, b.x2) - fmax(a.x1, b.x1) + 1.0), h = fmax(0.0, fmin(a.y2, b.y2) - fmax(a.y1, b.y1) + 1.0);
+        double inter = w * h;
+        double ovr = inter / ((a.x2 - a.x1 + 1.0) * (a.y2 - a.y1 + 1.0) + (b.x2 - b.x1 + 1.0) * (b.y2 - b.y1 + 1.0) - inter);
+        return !(ovr <= thr);
+    }
+};
+
 // jt.nms (Jittor 1.3.4.7 misc.py `nms`, called from oriented_rpn_head.py:208): fp32 boxes, the "+1" pixel
 // convention, fail condition `inter / (a_j + a_i - inter) > thr` with thr a double literal in Jittor's JIT source.
 struct HBoxF { float x1, y1, x2, y2; };
@@ -1208,13 +1227,14 @@ static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t
         case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         case RSDET_NMS_HBB_P1: launch_kind<RSDET_NMS_HBB_P1>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_HBB_P1_F64: launch_kind<RSDET_NMS_HBB_P1_F64>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
         default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
     }
 }
 
 int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int n = a.n_max;
-    if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB_P1) return RSDET_EINVAL;
+    if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB_P1_F64) return RSDET_EINVAL;
     if (n == 0) {
         if (a.num_keep) cudaMemsetAsync(a.num_keep, 0, sizeof(int32_t), st);
         return cuda_status();
@@ -1222,7 +1242,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     if (!a.dets || !a.scores) return RSDET_EINVAL;
     if (n > (a.mask_words ? (1 << 20) : kMaxNmsBoxes)) return RSDET_ELIMIT;
     if (workspace_bytes < nms_ws_bytes(a.kind, n, a.mask_words)) return RSDET_EWORKSPACE;
-    const bool f64 = a.kind == RSDET_NMS_MERGE || a.kind == RSDET_NMS_HBB;
+    const bool f64 = a.kind == RSDET_NMS_MERGE || a.kind == RSDET_NMS_HBB || a.kind == RSDET_NMS_HBB_P1_F64;
     const size_t N = (size_t)n;
 
     Workspace ws(workspace, workspace_bytes);

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .... import core
-from ...._lib import NMS_MERGE, require_cuda
+from ...._lib import NMS_HBB_P1_F64, NMS_MERGE, require_cuda
 
 # the thresh for nms when merge image (result_merge.py:24-27)
 nms_threshold_0 = 0.1
@@ -35,6 +35,25 @@ def py_cpu_nms_poly_fast(dets, thresh):
         return []
     t = torch.from_numpy(d).cuda()
     res = core.nms(NMS_MERGE, t[:, :8], t[:, 8], float(thresh), want_mask=False, want_sorted=False, want_score=True,
+                   ws_tag="merge")
+    return res.score_idx.cpu().tolist()
+
+
+def py_cpu_nms_poly(dets, thresh):
+    """:30-63 -- the same predicate as the `_fast` variant without the hbb prefilter (pairs whose hbbs do not
+    overlap have IoU 0, which no non-negative threshold suppresses): one engine, same result."""
+    return py_cpu_nms_poly_fast(dets, thresh)
+
+
+def py_cpu_nms(dets, thresh):
+    """:143-174 -- horizontal boxes (n,5) float64 [x1,y1,x2,y2,score], '+1' areas, survivors `ovr <= thresh`;
+    returns the kept indices in descending-score order (python list)."""
+    require_cuda()
+    d = np.ascontiguousarray(dets, dtype=np.float64).reshape(-1, 5)
+    if d.shape[0] == 0:
+        return []
+    t = torch.from_numpy(d).cuda()
+    res = core.nms(NMS_HBB_P1_F64, t[:, :4], t[:, 4], float(thresh), want_mask=False, want_sorted=False, want_score=True,
                    ws_tag="merge")
     return res.score_idx.cpu().tolist()
 
@@ -104,7 +123,7 @@ def parse_tile_name(subname):
     return subname.split('__')[0], int(x), int(y), float(_RATE.findall(subname)[0])
 
 
-def read_tile_detections(fullname):
+def read_tile_detections(fullname, ncoord=8):
     """One before_nms file -> (scene name per row, scene first-appearance order, tile polys (n,8) f64,
     per-row [x, y, rate] (n,3) f64, scores (n,) f64).  Text -> numbers only; no geometry on the host."""
     scenes, order, polys, offs, scores = [], [], [], [], []
@@ -112,7 +131,7 @@ def read_tile_detections(fullname):
     with open(fullname, 'r') as f:
         for line in f:
             sp = line.strip().split(' ')
-            if len(sp) < 10:
+            if len(sp) < 2 + ncoord:
                 continue
             t = cache.get(sp[0])
             if t is None:
@@ -122,15 +141,15 @@ def read_tile_detections(fullname):
             scenes.append(t[0])
             offs.append((t[1], t[2], t[3]))
             scores.append(float(sp[1]))
-            polys.append([float(v) for v in sp[2:10]])
-    return (scenes, order, np.asarray(polys, np.float64).reshape(-1, 8), np.asarray(offs, np.float64).reshape(-1, 3),
+            polys.append([float(v) for v in sp[2:2 + ncoord]])
+    return (scenes, order, np.asarray(polys, np.float64).reshape(-1, ncoord), np.asarray(offs, np.float64).reshape(-1, 3),
             np.asarray(scores, np.float64))
 
 
-def _merge_files(files, dstpath, thresholds):
-    """Shared body of mergesingle / mergebase / mergebypoly: all files, all scenes, one NMS launch."""
+def _merge_files(files, dstpath, thresholds, kind=NMS_MERGE):
+    """Shared body of mergesingle / mergebase / mergebypoly / mergebyrec: all files, all scenes, one NMS launch."""
     require_cuda()
-    recs = [read_tile_detections(f) for f in files]
+    recs = [read_tile_detections(f, 4 if kind == NMS_HBB_P1_F64 else 8) for f in files]
     gid_of, rows_gid, thr = {}, [], []
     for fi, (scenes, order, _, _, _) in enumerate(recs):
         for sc in order:
@@ -145,8 +164,11 @@ def _merge_files(files, dstpath, thresholds):
         offs = torch.from_numpy(np.concatenate([r[3] for r in recs])).cuda()
         scores = torch.from_numpy(np.concatenate([r[4] for r in recs])).cuda()
         gids = torch.from_numpy(np.concatenate(rows_gid)).cuda()
-        orig = core.poly2origpoly(polys, offs)
-        res = core.nms(NMS_MERGE, orig, scores, nms_threshold_0, labels=gids,
+        if polys.shape[1] == 8:
+            orig = core.poly2origpoly(polys, offs)
+        else:  # (n,4) boxes: the same (p + offset) / rate map on two points
+            orig = core.poly2origpoly(torch.cat([polys, polys], 1), offs)[:, :4].contiguous()
+        res = core.nms(kind, orig, scores, nms_threshold_0, labels=gids,
                        thr_per_label=torch.tensor(thr, dtype=torch.float64, device=orig.device), want_mask=False,
                        want_sorted=False, want_score=True, ws_tag="merge")
         kept_rows = res.score_idx.cpu().numpy()
@@ -169,23 +191,32 @@ def _file_threshold(fullname, nms_threshold_type):
     return nms_threshold_0 if not nms_threshold_type else nms_threshold_1[custombasename(fullname)]
 
 
+def _kind_of(nms):
+    if nms is py_cpu_nms_poly_fast or nms is py_cpu_nms_poly:
+        return NMS_MERGE
+    if nms is py_cpu_nms:
+        return NMS_HBB_P1_F64
+    raise ValueError("merge: `nms` must be py_cpu_nms_poly_fast, py_cpu_nms_poly or py_cpu_nms (device predicates)")
+
+
 def mergesingle(dstpath, nms, fullname, nms_threshold_type=0):
-    """:206-255.  `nms` is accepted for signature parity; anything but `py_cpu_nms_poly_fast` is rejected
-    (the device engine implements that predicate).  `nms_threshold_type` replaces `get_cfg()`."""
-    if nms is not py_cpu_nms_poly_fast:
-        raise ValueError("mergesingle: only py_cpu_nms_poly_fast is implemented on the device")
-    _merge_files([fullname], dstpath, [_file_threshold(fullname, nms_threshold_type)])
+    """:206-255.  `nms` selects the device predicate (one of this module's three functions; anything else is
+    rejected).  `nms_threshold_type` replaces `get_cfg()`."""
+    _merge_files([fullname], dstpath, [_file_threshold(fullname, nms_threshold_type)], _kind_of(nms))
 
 
 def mergebase(srcpath, dstpath, nms, nms_threshold_type=0):
     """:267-270 and mergebase_parallel :258-264 -- the 16-process pool becomes one launch."""
-    if nms is not py_cpu_nms_poly_fast:
-        raise ValueError("mergebase: only py_cpu_nms_poly_fast is implemented on the device")
     files = GetFileFromThisRootDir(srcpath)
-    _merge_files(files, dstpath, [_file_threshold(f, nms_threshold_type) for f in files])
+    _merge_files(files, dstpath, [_file_threshold(f, nms_threshold_type) for f in files], _kind_of(nms))
 
 
 mergebase_parallel = mergebase
+
+
+def mergebyrec(srcpath, dstpath, nms_threshold_type=0):
+    """:273-283 -- horizontal-box result files (`tile score x1 y1 x2 y2`)."""
+    mergebase(srcpath, dstpath, py_cpu_nms, nms_threshold_type)
 
 
 def mergebypoly(srcpath, dstpath, nms_threshold_type=0):

@@ -87,3 +87,34 @@ def test_csv_ensemble_vs_oracle(cuda, tmp_path, thresh):
         M.save_to_csv(got, tmp_path / "m.csv")
         back = M.read_csv_to_numpy(tmp_path / "m.csv")
         assert back.shape == got.shape and np.allclose(back, got, atol=5e-5)
+
+
+def test_py_cpu_nms_and_mergebyrec(cuda, oracle, tmp_path):
+    """Horizontal task: py_cpu_nms (float64, '+1' areas, keeps ovr <= thresh) and the file-level mergebyrec."""
+    from rs_detection_b200.jdet.data.devkits import result_merge as RM
+    rng = np.random.default_rng(3)
+    n = 1500
+    c = rng.uniform(0, 800, (n, 2))
+    wh = rng.uniform(10, 150, (n, 2))
+    d = np.concatenate([c - wh / 2, c + wh / 2, W.distinct_scores(n, 5).astype(np.float64)[:, None]], 1)
+    d[:40, :4] = d[40:80, :4] + rng.normal(0, 1.0, (40, 4))
+    for thr in (0.1, 0.5):
+        assert RM.py_cpu_nms(d, thr) == oracle.py_cpu_nms(d, thr)
+    assert RM.py_cpu_nms(np.zeros((0, 5)), 0.3) == []
+    sc = W.merge_scene(num_objects=200, scene=1500, seed=4)
+    dets = np.concatenate([sc["polys"], sc["scores"][:, None]], 1)
+    assert RM.py_cpu_nms_poly(dets, 0.1) == oracle.py_cpu_nms_poly_fast(dets, 0.1)
+    # file level: `tile score x1 y1 x2 y2`
+    lines = []
+    for k in range(600):
+        x, y = rng.integers(0, 3) * 824, rng.integers(0, 3) * 824
+        x1, y1 = rng.uniform(0, 900, 2)
+        w, h = rng.uniform(10, 120, 2)
+        lines.append("P0003__1.0__%d___%d %.4f %.4f %.4f %.4f %.4f\n" % (x, y, (k + 1) / 1000.0, x1, y1, x1 + w, y1 + h))
+    (tmp_path / "src").mkdir()
+    (tmp_path / "src" / "Vehicle.txt").write_text("".join(lines))
+    RM.mergebyrec(str(tmp_path / "src"), str(tmp_path / "got"), nms_threshold_type=1)
+    F.mergesingle(str(tmp_path / "want"), str(tmp_path / "src" / "Vehicle.txt"), 1, nms="rec")
+    _same_dir(tmp_path / "want", tmp_path / "got")
+    with pytest.raises(ValueError):
+        RM.mergebase(str(tmp_path / "src"), str(tmp_path / "x"), max)
