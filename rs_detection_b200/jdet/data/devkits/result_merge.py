@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .... import core
-from ...._lib import NMS_HBB_P1_F64, NMS_MERGE, require_cuda
+from ...._lib import NMS_HBB_P1_F64, NMS_MERGE, NMS_ROTATED_GE, require_cuda
 
 # the thresh for nms when merge image (result_merge.py:24-27)
 nms_threshold_0 = 0.1
@@ -56,6 +56,20 @@ def py_cpu_nms(dets, thresh):
     res = core.nms(NMS_HBB_P1_F64, t[:, :4], t[:, 4], float(thresh), want_mask=False, want_sorted=False, want_score=True,
                    ws_tag="merge")
     return res.score_idx.cpu().tolist()
+
+
+def py_cpu_nms_obb(dets, thresh):
+    """:128-141 -- polygons -> oriented boxes (`poly2obb`: cv2.minAreaRect on the host, as in the reference) ->
+    `nms_rotated_cpu` (suppress IoU >= thresh) -> kept indices in ASCENDING index order (`jt.where(keep)[0]`)."""
+    from ...ops.bbox_transforms import poly2obb
+    require_cuda()
+    d = np.ascontiguousarray(dets, dtype=np.float64).reshape(-1, 9)
+    if d.shape[0] == 0:
+        return np.array([])
+    obb = torch.from_numpy(poly2obb(d[:, :8]).astype(np.float32)).cuda()
+    sc = torch.from_numpy(d[:, 8].astype(np.float32)).cuda()
+    res = core.nms(NMS_ROTATED_GE, obb, sc, float(thresh), want_mask=False, want_sorted=True, ws_tag="merge")
+    return res.sorted_idx.cpu().numpy()
 
 
 def poly2origpoly(poly, x, y, rate):
@@ -189,6 +203,23 @@ def _merge_files(files, dstpath, thresholds, kind=NMS_MERGE):
 
 def _file_threshold(fullname, nms_threshold_type):
     return nms_threshold_0 if not nms_threshold_type else nms_threshold_1[custombasename(fullname)]
+
+
+def mergebyobb(srcpath, dstpath, nms_threshold_type=0):
+    """:301-315 -- oriented-box variant: per scene `py_cpu_nms_obb` (one engine call per scene, like nmsbynamedict)."""
+    os.makedirs(dstpath, exist_ok=True)
+    for f in GetFileFromThisRootDir(srcpath):
+        scenes, order, polys, offs, scores = read_tile_detections(f)
+        thr = _file_threshold(f, nms_threshold_type)
+        orig = np.zeros((0, 8))
+        if polys.shape[0]:
+            orig = core.poly2origpoly(torch.from_numpy(polys).cuda(), torch.from_numpy(offs).cuda()).cpu().numpy()
+        with open(os.path.join(dstpath, custombasename(f) + '.txt'), 'w') as out:
+            for sc_name in order:
+                rows = np.asarray([i for i, s_ in enumerate(scenes) if s_ == sc_name], np.int64)
+                keep = py_cpu_nms_obb(np.concatenate([orig[rows], scores[rows, None]], 1), thr)
+                for r in rows[np.asarray(keep, np.int64)]:
+                    out.write(sc_name + ' ' + str(float(scores[r])) + ' ' + ' '.join(map(str, orig[r].tolist())) + '\n')
 
 
 def _kind_of(nms):

@@ -43,21 +43,9 @@ def read_csv_to_numpy(submit_csvfile_path):
 
 
 def poly2obb(polys):
-    """:73-100 (OpenCV minAreaRect, le90-style normalisation)."""
-    import cv2
-    order = polys.shape[:-1]
-    pts = polys.reshape(-1, polys.shape[-1] // 2, 2).astype(np.float32)
-    out = []
-    for poly in pts:
-        (x, y), (w, h), angle = cv2.minAreaRect(poly)
-        if w >= h:
-            angle = -angle
-        else:
-            w, h = h, w
-            angle = -90 - angle
-        out.append([x, y, w, h, angle / 180 * np.pi])
-    out = np.array(out) if out else np.zeros((0, 5))
-    return np.array(out.reshape(*order, 5))
+    """:73-100 (OpenCV minAreaRect, le90-style normalisation) -- the same code as jdet.ops.bbox_transforms.poly2obb."""
+    from .ops.bbox_transforms import poly2obb as _p2o
+    return _p2o(polys)
 
 
 def obb2hbb(obboxes):

@@ -17,3 +17,24 @@ def obb2hbb(obboxes):
 def poly2hbb(polys):
     p, fl = dev(polys)
     return back(core.poly2hbb(p), fl)
+
+
+def poly2obb(polys):
+    """:549-575 -- the reference's own host loop over `cv2.minAreaRect` (OpenCV, float32 points), le90-style
+    normalisation.  Third-party arithmetic on the host in the reference too; returns a numpy (…, 5) array."""
+    import cv2
+    import numpy as np
+    p = polys.detach().cpu().numpy() if hasattr(polys, "detach") else np.asarray(polys)
+    order = p.shape[:-1]
+    pts = p.reshape(-1, p.shape[-1] // 2, 2).astype(np.float32)
+    out = []
+    for poly in pts:
+        (x, y), (w, h), angle = cv2.minAreaRect(poly)
+        if w >= h:
+            angle = -angle
+        else:
+            w, h = h, w
+            angle = -90 - angle
+        out.append([x, y, w, h, angle / 180 * np.pi])
+    out = np.array(out) if out else np.zeros((0, 5))
+    return out.reshape(*order, 5)

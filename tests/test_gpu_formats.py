@@ -118,3 +118,23 @@ def test_py_cpu_nms_and_mergebyrec(cuda, oracle, tmp_path):
     _same_dir(tmp_path / "want", tmp_path / "got")
     with pytest.raises(ValueError):
         RM.mergebase(str(tmp_path / "src"), str(tmp_path / "x"), max)
+
+
+def test_py_cpu_nms_obb(cuda, oracle, tmp_path):
+    """py_cpu_nms_obb: cv2.minAreaRect boxes -> nms_rotated_cpu (`>=`), ascending kept indices; mergebyobb files."""
+    from rs_detection_b200.jdet.data.devkits import result_merge as RM
+    from rs_detection_b200.jdet.ops.bbox_transforms import poly2obb
+    sc = W.merge_scene(num_objects=250, scene=1800, seed=6)
+    dets = np.concatenate([sc["polys"], sc["scores"][:, None]], 1)
+    got = RM.py_cpu_nms_obb(dets, 0.3)
+    obb = poly2obb(dets[:, :8]).astype(np.float32)
+    s32 = dets[:, 8].astype(np.float32)
+    order = np.argsort(-s32.astype(np.float64), kind="stable").astype(np.int32)
+    want = np.nonzero(oracle.nms_rotated_keep(obb, order, 0.3, 5, ge=True))[0]
+    assert np.array_equal(got, want) and 0 < len(want) < len(dets)
+    res = W.tile_results(120, 3, 2200, 1, seed=8)
+    F.write_before_nms(res, tmp_path / "before", W.FAIR1M_CLASSES)
+    RM.mergebyobb(str(tmp_path / "before"), str(tmp_path / "after"))
+    n_in = sum(len(open(tmp_path / "before" / f).readlines()) for f in os.listdir(tmp_path / "before"))
+    n_out = sum(len(open(tmp_path / "after" / f).readlines()) for f in os.listdir(tmp_path / "after"))
+    assert sorted(os.listdir(tmp_path / "before")) == sorted(os.listdir(tmp_path / "after")) and 0 < n_out < n_in
