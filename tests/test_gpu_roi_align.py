@@ -80,6 +80,26 @@ def test_fused_extractor_vs_oracle(cuda, oracle, K, batch):
         _check(xs[l].grad.cpu().numpy(), wb[l], 1e-4, f"extractor bwd level {l}")
 
 
+def test_rbox_extractor_v0_vs_oracle(cuda, oracle):
+    """RboxSingleRoIExtractor (python/jdet/models/roi_extractors/rbox_single_level.py): v0 layer, levels on the RoI
+    as given, no extension."""
+    from rs_detection_b200.jdet.models.roi_extractors.rbox_single_level import RboxSingleRoIExtractor
+    tile, C, K = 512, 16, 600
+    feats = W.fpn_pyramid(1, 7, tile=tile, channels=C)
+    rois = W.proposals(K, 9, canvas=tile)
+    ext = RboxSingleRoIExtractor(dict(type='ROIAlignRotated', output_size=7, sampling_ratio=2), C, [4, 8, 16, 32])
+    xs = [_t(f).requires_grad_(True) for f in feats]
+    y = ext(xs, _t(rois))
+    want, lv = oracle.oriented_extractor_fwd(feats, rois, [4, 8, 16, 32], extend_factor=(1.0, 1.0), version=0)
+    assert np.array_equal(ext.map_roi_levels(_t(rois), 4).cpu().numpy(), lv)
+    _check(y.detach().cpu().numpy(), want, 1e-5, "rbox extractor fwd")
+    g = np.random.default_rng(2).standard_normal(want.shape).astype(np.float32)
+    y.backward(_t(g))
+    wb = oracle.oriented_extractor_bwd(g, [f.shape for f in feats], rois, [4, 8, 16, 32], extend_factor=(1.0, 1.0), version=0)
+    for l in range(4):
+        _check(xs[l].grad.cpu().numpy(), wb[l], 1e-4, f"rbox extractor bwd level {l}")
+
+
 def test_single_feature_list_and_empty(cuda, oracle):
     from rs_detection_b200.jdet.models.roi_extractors.oriented_single_level import OrientedSingleRoIExtractor
     from rs_detection_b200 import core
