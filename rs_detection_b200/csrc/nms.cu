@@ -26,6 +26,7 @@
 //      through managed memory (nms_rotated.py:475-492).
 //   5. compaction (CUB select) to the three index orders the reference's callers expect.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -393,8 +394,10 @@ __device__ __forceinline__ int compact_queue(const unsigned short* __restrict__ 
 
 template <int KIND>
 __global__ void __launch_bounds__(kNmsThreads)
-mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable tb, unsigned long long* __restrict__ mask) {
+mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable tb, unsigned long long* __restrict__ mask,
+                  const int* __restrict__ gate) {
     using Tr = Traits<KIND>;
+    if (gate && *gate == 0) return;  // the sparse path (below) already produced the keep flags
     using Box = typename Tr::Box;
     __shared__ Box s_row[64];
     __shared__ Box s_col[64];
@@ -541,7 +544,8 @@ __device__ __forceinline__ unsigned long long resolve_block(const unsigned long 
 
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_kernel(SegTable tb, const unsigned long long* __restrict__ mask, uint8_t* __restrict__ keep_sorted,
-              unsigned long long* __restrict__ pub_keep, int* __restrict__ pub_flag, int skip_small) {
+              unsigned long long* __restrict__ pub_keep, int* __restrict__ pub_flag, int skip_small, const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     extern __shared__ unsigned long long s_remv[];
     __shared__ unsigned long long s_diag[2][64];
     __shared__ unsigned long long s_keep;
@@ -1002,7 +1006,8 @@ reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, 
 template <int NCH, bool IDENT>  // NCH 64-word chunks per row: 1 (<= 4096 columns) or 2 (<= 8192)
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov_base,
-                        int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted) {
+                        int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted, const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;
     extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][partials: 4 x Ts][rows: 2 x 64 x Ts][cand: n_boxes ints]
     __shared__ __align__(8) unsigned short s_col16[256];  // s_col16[4j + q]: rows i in quarter q (i < j) that suppress j
     __shared__ unsigned long long s_keep;
@@ -1171,6 +1176,176 @@ __global__ void score_order_flags_kernel(const uint8_t* __restrict__ keep_mask, 
 
 // ----------------------------------------------------------------------------- engine
 
+// ----------------------------------------------------------------------------- sparse greedy NMS (merge stage)
+// A 10k x 10k scene holds ~10^5 small detections: the dense engine tests n_s^2 / 2 hbb pairs per (scene, class)
+// group and scans n_s / 64 dependent blocks (7.3 ms for 90k detections, 90 % in those two kernels).  The overlap
+// graph is sparse (~10 neighbours per detection), so for large MERGE calls:
+//   1. sweep and prune: detections sorted by (group, x1); each looks ahead while the next x1 is left of its x2
+//      and keeps the pairs whose hbbs overlap (the reference's prefilter, result_merge.py:97-100) -- counted, prefix
+//      summed and written without atomics;
+//   2. the polygon IoU of every candidate pair, one per thread; "p suppresses q" (p the higher-scored one) becomes an
+//      in-edge of q in a CSR graph (degree count -> prefix sum -> fill);
+//   3. greedy NMS as a FIXED POINT over that graph, the same rule as the staged scan's warp resolve: a detection
+//      dies once a KEPT in-neighbour exists, is kept once all its in-neighbours are dead.  The highest-scored
+//      undecided detection is always decidable, so this is exactly the sequential greedy result; the number of
+//      rounds is the longest kept/dead dependency chain (a handful).  One persistent kernel with a grid barrier.
+// Anything that does not fit the workspace carved from the (unused) dense mask falls back to the dense kernels,
+// which are always enqueued and exit on a device flag.
+constexpr int kSparseMinBoxes = 8192;
+constexpr int kSparseCtas = kNumSMs;
+constexpr int kSparseThreads = 512;
+
+struct SparseWs {
+    unsigned long long *keyA, *keyB;   // (group << 32 | ordered float x1), double buffer
+    int *valA, *valB;                  // sorted position of the detection
+    int* seg_of;                       // group index of a sorted position
+    int* cnt;                          // n+1: candidates found by each x-sorted detection -> exclusive prefix
+    int* indeg;                        // n+1: in-degree -> row pointers
+    int* cursor;                       // n: fill cursors
+    unsigned char* state;              // n: 0 undecided, 1 kept, 2 dead
+    unsigned long long* cand;          // capC: (dst << 32 | src)
+    unsigned char* flag;               // capC: candidate suppresses
+    int* adj;                          // capE: in-neighbours (sources)
+    int* ctl;                          // [0] gate (1 = run the dense path) [1] barrier count [2] barrier generation [3..4] changed
+    long long capC, capE;
+};
+
+__device__ __forceinline__ unsigned int ord_f32(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_f32_inv(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void sp_keys_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { w.ctl[0] = 0; w.ctl[1] = 0; w.ctl[2] = 0; w.ctl[3] = 0; w.ctl[4] = 0; }
+    if (p > n_max) return;
+    if (p == n_max) { w.cnt[p] = 0; w.indeg[p] = 0; return; }
+    w.cnt[p] = 0; w.indeg[p] = 0; w.cursor[p] = 0; w.state[p] = 0;
+    const int n_eff = min(tb.hdr[1], n_max), nseg = tb.hdr[0];
+    w.valA[p] = p;
+    if (p >= n_eff) { w.keyA[p] = ~0ull; w.seg_of[p] = -1; return; }
+    int lo = 0, hi = nseg;  // largest s with seg_start[s] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tb.seg_start[mid] <= p) lo = mid; else hi = mid;
+    }
+    w.seg_of[p] = lo;
+    w.keyA[p] = ((unsigned long long)lo << 32) | ord_f32(__double2float_rd(boxes[p].x1));  // rounded DOWN: never right of x1
+}
+
+// FILL = false: count the candidate pairs of each x-sorted detection; FILL = true: write them at the prefix offsets
+template <bool FILL>
+__global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, const unsigned long long* __restrict__ key,
+                                const int* __restrict__ val, SparseWs w) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_eff = min(tb.hdr[1], n_max);
+    if (q >= n_eff) return;
+    if (FILL && (long long)w.cnt[n_max] > w.capC) { if (q == 0) w.ctl[0] = 1; return; }
+    const unsigned long long kq = key[q];
+    const unsigned int seg = (unsigned int)(kq >> 32);
+    const int i = val[q];
+    const MBox bi = boxes[i];
+    int found = 0;
+    long long out = FILL ? (long long)w.cnt[q] : 0;
+    for (int r = q + 1; r < n_eff; r++) {
+        const unsigned long long kr = key[r];
+        if ((unsigned int)(kr >> 32) != seg) break;
+        if (!((double)ord_f32_inv((unsigned int)kr) < bi.x2)) break;  // every later x1 is at or right of my x2
+        const int j = val[r];
+        if (merge_hbb_overlap(bi, boxes[j])) {
+            if (FILL) {
+                const int src = min(i, j), dst = max(i, j);  // lower sorted position = higher score
+                w.cand[out++] = ((unsigned long long)dst << 32) | (unsigned int)src;
+            }
+            found++;
+        }
+    }
+    if (!FILL) w.cnt[q] = found;
+}
+
+__global__ void sp_iou_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+    const long long total = w.cnt[n_max];
+    if (total > w.capC || w.ctl[0]) return;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = w.cand[e];
+        const int src = (int)(unsigned int)c, dst = (int)(c >> 32);
+        const double thr = tb.seg_thr[w.seg_of[src]];
+        const bool sup = !(iou_poly_d(boxes[src], boxes[dst]) <= thr);  // survivors are `iou <= thr` (result_merge.py:118)
+        w.flag[e] = sup ? 1 : 0;
+        if (sup) atomicAdd(&w.indeg[dst], 1);
+    }
+}
+
+__global__ void sp_fill_kernel(int n_max, SparseWs w) {
+    const long long total = w.cnt[n_max];
+    if (total > w.capC || w.ctl[0]) return;
+    if ((long long)w.indeg[n_max] > w.capE) { if (blockIdx.x == 0 && threadIdx.x == 0) w.ctl[0] = 1; return; }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        if (!w.flag[e]) continue;
+        const unsigned long long c = w.cand[e];
+        const int dst = (int)(c >> 32);
+        w.adj[w.indeg[dst] + atomicAdd(&w.cursor[dst], 1)] = (int)(unsigned int)c;
+    }
+}
+
+__device__ __forceinline__ void sp_grid_barrier(int* ctl, int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile int* gen = ctl + 2;
+        const int g = *gen;
+        __threadfence();
+        if (atomicAdd(ctl + 1, 1) == nblocks - 1) {
+            ctl[1] = 0;
+            __threadfence();
+            atomicAdd(ctl + 2, 1);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// persistent: kSparseCtas co-resident CTAs, one fixed-point round per grid barrier
+__global__ void __launch_bounds__(kSparseThreads, 1)
+sp_resolve_kernel(SegTable tb, int n_max, SparseWs w, uint8_t* __restrict__ keep_sorted) {
+    if (w.ctl[0] || (long long)w.cnt[n_max] > w.capC || (long long)w.indeg[n_max] > w.capE) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) w.ctl[0] = 1;
+        return;  // uniform over the grid: every CTA reads the same three words
+    }
+    const int n_eff = min(tb.hdr[1], n_max);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    volatile unsigned char* state = w.state;
+    for (int round = 0;; round++) {
+        int* changed = w.ctl + 3 + (round & 1);
+        bool any = false;
+        for (int p = tid; p < n_eff; p += stride) {
+            if (state[p]) continue;
+            const int lo = w.indeg[p], hi = w.indeg[p + 1];
+            bool dead = false, all_dead = true;
+            for (int e = lo; e < hi; e++) {
+                const unsigned char sv = state[w.adj[e]];
+                dead |= sv == 1;
+                all_dead &= sv == 2;
+            }
+            if (dead) { state[p] = 2; any = true; }
+            else if (all_dead) { state[p] = 1; any = true; }
+        }
+        if (any) *changed = 1;
+        // states written in this round may or may not be seen by the other threads of the same round: either way a
+        // value that is read is final, so the rule stays sound; the barrier publishes them for the next round
+        sp_grid_barrier(w.ctl, gridDim.x);
+        const int c = *(volatile int*)changed;
+        sp_grid_barrier(w.ctl, gridDim.x);   // everybody has read `changed` before it is cleared for round + 2
+        if (tid == 0) *changed = 0;
+        if (!c) break;
+    }
+    for (int p = tid; p < n_max; p += stride) keep_sorted[p] = (p < n_eff && state[p] == 1) ? 1 : 0;
+}
+
 static size_t box_bytes(int kind) {
     switch (kind) {
         case RSDET_NMS_ROTATED: case RSDET_NMS_ROTATED_GE: return sizeof(RBox);
@@ -1204,7 +1379,7 @@ size_t nms_ws_bytes(int kind, int n, size_t mask_words) {
 
 template <int KIND>
 static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
-                        unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted) {
+                        unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted, const int* gate = nullptr) {
     using Tr = Traits<KIND>;
     if (!mask_phase) {
         prep_sorted_kernel<KIND><<<ceil_div(a.n_max, 256), 256, 0, st>>>((const typename Tr::Raw*)a.dets, a.labels, idx, a.n_max,
@@ -1214,21 +1389,21 @@ static void launch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* 
         long long T = (a.n_max + 63) / 64;
         long long tiles = T * (T + 1) / 2;
         int grid = (int)(tiles < (long long)kNumSMs * 5 ? tiles : (long long)kNumSMs * 5);  // 5 CTAs/SM fit (39 KB smem, 91 regs)
-        mask_tiles_kernel<KIND><<<grid, kNmsThreads, 0, st>>>((const typename Tr::Box*)boxes, tb, mask);
+        mask_tiles_kernel<KIND><<<grid, kNmsThreads, 0, st>>>((const typename Tr::Box*)boxes, tb, mask, gate);
     }
     count_launch();
 }
 
 static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t* label_sorted, SegTable tb,
-                          unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted) {
+                          unsigned long long* mask, cudaStream_t st, bool mask_phase, int* starts_unsorted, const int* gate = nullptr) {
     switch (a.kind) {
-        case RSDET_NMS_ROTATED: launch_kind<RSDET_NMS_ROTATED>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        case RSDET_NMS_HBB_P1: launch_kind<RSDET_NMS_HBB_P1>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        case RSDET_NMS_HBB_P1_F64: launch_kind<RSDET_NMS_HBB_P1_F64>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
-        default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted); break;
+        case RSDET_NMS_ROTATED: launch_kind<RSDET_NMS_ROTATED>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        case RSDET_NMS_ROTATED_GE: launch_kind<RSDET_NMS_ROTATED_GE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        case RSDET_NMS_POLY: launch_kind<RSDET_NMS_POLY>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        case RSDET_NMS_MERGE: launch_kind<RSDET_NMS_MERGE>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        case RSDET_NMS_HBB_P1: launch_kind<RSDET_NMS_HBB_P1>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        case RSDET_NMS_HBB_P1_F64: launch_kind<RSDET_NMS_HBB_P1_F64>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
+        default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
     }
 }
 
@@ -1376,16 +1551,70 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         const size_t Ts = (size_t)(Tov | 1);
         const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)nb;
         if (Tov <= 64 && staged <= 200 * 1024)
-            reduce_ov_staged_kernel<1, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+            reduce_ov_staged_kernel<1, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted, nullptr);
         else if (Tov <= 128 && staged <= 200 * 1024)
-            reduce_ov_staged_kernel<2, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted);
+            reduce_ov_staged_kernel<2, false><<<kNumSMs, kReduceThreads, staged, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch, nb, keep_sorted, nullptr);
         else
             reduce_ov_kernel<<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (size_t)Tov, st>>>(tb, idx_ls, a.cand_per_box, mask, pitch,
                                                                                                       nb, keep_sorted);
         count_launch(5);
     } else {
+    // 4'. large merge calls: sparse path first; the dense kernels below then run only if it raised the gate
+    const int* gate = nullptr;
+    const size_t mask_cap = a.mask_words ? a.mask_words : N * ((N + 63) / 64);
+    if (a.kind == RSDET_NMS_MERGE && n >= kSparseMinBoxes) {
+        Workspace mw(mask, mask_cap * sizeof(unsigned long long));
+        SparseWs w;
+        w.keyA = mw.take<unsigned long long>(N);
+        w.keyB = mw.take<unsigned long long>(N);
+        w.valA = mw.take<int>(N);
+        w.valB = mw.take<int>(N);
+        w.seg_of = mw.take<int>(N);
+        w.cnt = mw.take<int>(N + 1);
+        w.indeg = mw.take<int>(N + 1);
+        w.cursor = mw.take<int>(N);
+        w.state = mw.take<unsigned char>(N);
+        w.ctl = cnt_scratch + 40;
+        const size_t left = mw.used < mw.size ? mw.size - mw.used : 0;
+        long long cap = (long long)(left / 14);              // 8 (cand) + 1 (flag) + 4 (adj) bytes per entry, + alignment slack
+        if (cap > 32ll * n) cap = 32ll * n;
+        if (cap > 0x3fffffffll) cap = 0x3fffffffll;
+        if (cap >= 8ll * n) {
+            w.capC = cap;
+            w.capE = cap;
+            w.cand = mw.take<unsigned long long>((size_t)cap);
+            w.flag = mw.take<unsigned char>((size_t)cap);
+            w.adj = mw.take<int>((size_t)cap);
+        }
+        if (cap >= 8ll * n && mw.ok()) {
+            const MBox* mb = (const MBox*)boxes;
+            int nbits = 1;
+            while ((1ll << nbits) < (long long)n + 1) nbits++;
+            sp_keys_kernel<<<ceil_div(n + 1, 256), 256, 0, st>>>(mb, tb, n, w);
+            cub::DoubleBuffer<unsigned long long> dk(w.keyA, w.keyB);
+            cub::DoubleBuffer<int> dv(w.valA, w.valB);
+            size_t need = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 32 + nbits, st);
+            if (need > cub_bytes) return RSDET_EWORKSPACE;
+            cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 32 + nbits, st);
+            const unsigned long long* key = dk.Current();
+            const int* val = dv.Current();
+            sp_sweep_kernel<false><<<ceil_div(n, 128), 128, 0, st>>>(mb, tb, n, key, val, w);
+            need = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, need, w.cnt, w.cnt, n + 1, st);
+            if (need > cub_bytes) return RSDET_EWORKSPACE;
+            cub::DeviceScan::ExclusiveSum(cub_tmp, need, w.cnt, w.cnt, n + 1, st);
+            sp_sweep_kernel<true><<<ceil_div(n, 128), 128, 0, st>>>(mb, tb, n, key, val, w);
+            sp_iou_kernel<<<kNumSMs * 8, 128, 0, st>>>(mb, tb, n, w);
+            cub::DeviceScan::ExclusiveSum(cub_tmp, need, w.indeg, w.indeg, n + 1, st);
+            sp_fill_kernel<<<kNumSMs * 8, 256, 0, st>>>(n, w);
+            sp_resolve_kernel<<<kSparseCtas, kSparseThreads, 0, st>>>(tb, n, w, keep_sorted);
+            count_launch(16);
+            gate = w.ctl;
+        }
+    }
     // 4. suppression mask over the upper-triangular tiles of every segment
-    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true, starts_unsorted);
+    dispatch_kind(a, idx_ls, boxes, label_sorted, tb, mask, st, true, starts_unsorted, gate);
     // 5. greedy scan
     {
         size_t smem = sizeof(unsigned long long) * ((N + 63) / 64);
@@ -1398,11 +1627,11 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         // groups of < kCoopMinBlocks blocks: staged scan (rows through shared memory); larger ones: cooperative phase
         const size_t Tmax = (size_t)(kCoopMinBlocks - 1) | 1;
         reduce_ov_staged_kernel<2, true><<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (5 * Tmax + 2 * 64 * Tmax), st>>>(
-            tb, nullptr, 1, mask, 0, 0, keep_sorted);
+            tb, nullptr, 1, mask, 0, 0, keep_sorted, gate);
         count_launch();
         if ((N + 63) / 64 >= (size_t)kCoopMinBlocks) {
             cudaMemsetAsync(pub_flag, 0, sizeof(int) * (2 * N / 64 + 8), st);
-            reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag, 1);
+            reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag, 1, gate);
             count_launch();
         }
     }

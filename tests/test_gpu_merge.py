@@ -66,6 +66,24 @@ def test_batched_merge_per_class_thresholds(cuda, oracle):
     assert 0 < len(want) < sc["scores"].size
 
 
+@pytest.mark.parametrize("objects,scene,jitter", [(4000, 6000, 1.0), (2500, 1500, 3.0)])
+def test_sparse_merge_path_vs_oracle(cuda, oracle, objects, scene, jitter):
+    """>= 8192 detections take the sparse path (sweep-and-prune candidates -> CSR of suppressing pairs -> fixed-point
+    greedy); the second case is a crowded scene (long kept/dead dependency chains, many rounds)."""
+    from rs_detection_b200.jdet.data.devkits.result_merge import merge_detections, nms_threshold_1
+    sc = W.merge_scene(num_objects=objects, scene=scene, seed=11, jitter_px=jitter)
+    assert sc["scores"].size >= 8192
+    thr = np.array([nms_threshold_1[c] for c in W.FAIR1M_CLASSES])
+    got = merge_detections(sc["polys"], sc["scores"], sc["labels"], group_thresh=thr)
+    want = []
+    for c in range(10):
+        idx = np.nonzero(sc["labels"] == c)[0]
+        dets = np.concatenate([sc["polys"][idx], sc["scores"][idx, None]], 1)
+        want += [idx[k] for k in oracle.py_cpu_nms_poly_fast(dets, thr[c])]
+    assert sorted(got.tolist()) == sorted(want)
+    assert np.all(np.diff(sc["scores"][got]) < 0) and 0 < len(want) < sc["scores"].size
+
+
 def test_merge_py_hbb_nms(cuda, oracle):
     from rs_detection_b200.jdet.merge import nms
     rng = np.random.default_rng(8)
