@@ -84,6 +84,24 @@ def test_sparse_merge_path_vs_oracle(cuda, oracle, objects, scene, jitter):
     assert np.all(np.diff(sc["scores"][got]) < 0) and 0 < len(want) < sc["scores"].size
 
 
+def test_sparse_merge_overflow_falls_back_to_dense(cuda, oracle):
+    """85 clusters of 100 near-identical quads: ~100 candidate pairs per detection, more than the sparse path's
+    32 per detection, so its gate opens and the dense kernels produce the result."""
+    from rs_detection_b200.jdet.data.devkits.result_merge import py_cpu_nms_poly_fast
+    rng = np.random.default_rng(21)
+    centres = rng.uniform(200, 5000, (85, 2))
+    obb = np.zeros((8500, 5))
+    obb[:, :2] = np.repeat(centres, 100, 0) + rng.normal(0, 1.5, (8500, 2))
+    obb[:, 2] = rng.uniform(40, 60, 8500)
+    obb[:, 3] = rng.uniform(15, 25, 8500)
+    obb[:, 4] = np.repeat(rng.uniform(-1.5, 1.5, 85), 100) + rng.normal(0, 0.05, 8500)
+    polys = np.round(W.obb_to_poly64(obb), 4)
+    scores = rng.permutation(8500) / 8500.0 + 1e-4
+    dets = np.concatenate([polys, scores[:, None]], 1)
+    got = py_cpu_nms_poly_fast(dets, 0.3)
+    assert got == oracle.py_cpu_nms_poly_fast(dets, 0.3) and 85 <= len(got) < 2000
+
+
 def test_merge_py_hbb_nms(cuda, oracle):
     from rs_detection_b200.jdet.merge import nms
     rng = np.random.default_rng(8)
