@@ -1218,9 +1218,36 @@ __device__ __forceinline__ float ord_f32_inv(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// ctl[5], ctl[6]: float bits of the largest hbb height / width (positive floats order like ints)
+__global__ void sp_extent_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_eff = min(tb.hdr[1], n_max);
+    float h = 0.f, wd = 0.f;
+    if (p < n_eff) {
+        h = __double2float_ru(boxes[p].y2 - boxes[p].y1);
+        wd = __double2float_ru(boxes[p].x2 - boxes[p].x1);
+    }
+    for (int o = 16; o; o >>= 1) {
+        h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        wd = fmaxf(wd, __shfl_xor_sync(0xffffffffu, wd, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (h > 0.f) atomicMax(w.ctl + 5, __float_as_int(h));
+        if (wd > 0.f) atomicMax(w.ctl + 6, __float_as_int(wd));
+    }
+}
+
+// y band of a coordinate: bands are as high as the tallest hbb of the call, so a box touches its own band and at most
+// the next one.  Out-of-range bands are clamped (that only merges bands, i.e. adds candidates).
+constexpr int kBandBits = 14;
+__device__ __forceinline__ unsigned int sp_band(double y, double band_h) {
+    const double b = floor(y / band_h) + (double)(1 << (kBandBits - 1));
+    return (unsigned int)fmin(fmax(b, 0.0), (double)((1 << kBandBits) - 1));
+}
+__device__ __forceinline__ double sp_band_h(const SparseWs& w) { return fmax((double)__int_as_float(w.ctl[5]) * 1.000001, 1e-6); }
+
 __global__ void sp_keys_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) { w.ctl[0] = 0; w.ctl[1] = 0; w.ctl[2] = 0; w.ctl[3] = 0; w.ctl[4] = 0; }
     if (p > n_max) return;
     if (p == n_max) { w.cnt[p] = 0; w.indeg[p] = 0; return; }
     w.cnt[p] = 0; w.indeg[p] = 0; w.cursor[p] = 0; w.state[p] = 0;
@@ -1233,10 +1260,14 @@ __global__ void sp_keys_kernel(const MBox* __restrict__ boxes, SegTable tb, int 
         if (tb.seg_start[mid] <= p) lo = mid; else hi = mid;
     }
     w.seg_of[p] = lo;
-    w.keyA[p] = ((unsigned long long)lo << 32) | ord_f32(__double2float_rd(boxes[p].x1));  // rounded DOWN: never right of x1
+    // (group | y band | x1 rounded DOWN: never right of the true x1)
+    w.keyA[p] = ((unsigned long long)lo << (32 + kBandBits)) | ((unsigned long long)sp_band(boxes[p].y1, sp_band_h(w)) << 32) |
+                ord_f32(__double2float_rd(boxes[p].x1));
 }
 
-// FILL = false: count the candidate pairs of each x-sorted detection; FILL = true: write them at the prefix offsets
+// FILL = false: count the candidate pairs of each sorted detection; FILL = true: write them at the prefix offsets.
+// Candidates of detection i: later members of its own (group, band) run whose x1 is left of x2_i, and -- when i
+// reaches into the next band -- the members of that run whose x1 lies in (x1_i - widest hbb, x2_i).
 template <bool FILL>
 __global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, const unsigned long long* __restrict__ key,
                                 const int* __restrict__ val, SparseWs w) {
@@ -1245,23 +1276,39 @@ __global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int
     if (q >= n_eff) return;
     if (FILL && (long long)w.cnt[n_max] > w.capC) { if (q == 0) w.ctl[0] = 1; return; }
     const unsigned long long kq = key[q];
-    const unsigned int seg = (unsigned int)(kq >> 32);
+    const unsigned int run = (unsigned int)(kq >> 32);
     const int i = val[q];
     const MBox bi = boxes[i];
     int found = 0;
     long long out = FILL ? (long long)w.cnt[q] : 0;
-    for (int r = q + 1; r < n_eff; r++) {
-        const unsigned long long kr = key[r];
-        if ((unsigned int)(kr >> 32) != seg) break;
-        if (!((double)ord_f32_inv((unsigned int)kr) < bi.x2)) break;  // every later x1 is at or right of my x2
-        const int j = val[r];
-        if (merge_hbb_overlap(bi, boxes[j])) {
-            if (FILL) {
-                const int src = min(i, j), dst = max(i, j);  // lower sorted position = higher score
-                w.cand[out++] = ((unsigned long long)dst << 32) | (unsigned int)src;
+    auto visit = [&](int r0, unsigned int want_run) {
+        for (int r = r0; r < n_eff; r++) {
+            const unsigned long long kr = key[r];
+            if ((unsigned int)(kr >> 32) != want_run) break;
+            if (!((double)ord_f32_inv((unsigned int)kr) < bi.x2)) break;  // every later x1 is at or right of my x2
+            const int j = val[r];
+            if (merge_hbb_overlap(bi, boxes[j])) {
+                if (FILL) {
+                    const int src = min(i, j), dst = max(i, j);  // lower sorted position = higher score
+                    w.cand[out++] = ((unsigned long long)dst << 32) | (unsigned int)src;
+                }
+                found++;
             }
-            found++;
         }
+    };
+    visit(q + 1, run);
+    const double band_h = sp_band_h(w);
+    const unsigned int band = run & ((1u << kBandBits) - 1u);
+    if (band + 1 < (1u << kBandBits) && sp_band(bi.y2, band_h) > band) {
+        const unsigned int next_run = run + 1;
+        const float maxw = __int_as_float(w.ctl[6]);
+        const unsigned long long lokey = ((unsigned long long)next_run << 32) | ord_f32(__double2float_rd(bi.x1 - (double)maxw * 1.000001));
+        int lo = q + 1, hi = n_eff;  // first r with key[r] >= lokey (the next band sorts after mine)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (key[mid] < lokey) lo = mid + 1; else hi = mid;
+        }
+        visit(lo, next_run);
     }
     if (!FILL) w.cnt[q] = found;
 }
@@ -1590,13 +1637,16 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
             const MBox* mb = (const MBox*)boxes;
             int nbits = 1;
             while ((1ll << nbits) < (long long)n + 1) nbits++;
+            cudaMemsetAsync(w.ctl, 0, 8 * sizeof(int), st);
+            sp_extent_kernel<<<ceil_div(n, 256), 256, 0, st>>>(mb, tb, n, w);
             sp_keys_kernel<<<ceil_div(n + 1, 256), 256, 0, st>>>(mb, tb, n, w);
             cub::DoubleBuffer<unsigned long long> dk(w.keyA, w.keyB);
             cub::DoubleBuffer<int> dv(w.valA, w.valB);
             size_t need = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, 32 + nbits, st);
+            const int kbits = 32 + kBandBits + nbits < 64 ? 32 + kBandBits + nbits : 64;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, kbits, st);
             if (need > cub_bytes) return RSDET_EWORKSPACE;
-            cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, 32 + nbits, st);
+            cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, kbits, st);
             const unsigned long long* key = dk.Current();
             const int* val = dv.Current();
             sp_sweep_kernel<false><<<ceil_div(n, 128), 128, 0, st>>>(mb, tb, n, key, val, w);
