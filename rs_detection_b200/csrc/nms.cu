@@ -1658,7 +1658,13 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
             sp_iou_kernel<<<kNumSMs * 8, 128, 0, st>>>(mb, tb, n, w);
             cub::DeviceScan::ExclusiveSum(cub_tmp, need, w.indeg, w.indeg, n + 1, st);
             sp_fill_kernel<<<kNumSMs * 8, 256, 0, st>>>(n, w);
-            sp_resolve_kernel<<<kSparseCtas, kSparseThreads, 0, st>>>(tb, n, w, keep_sorted);
+            {   // grid barrier inside: cooperative launch = the driver guarantees the 148 CTAs are co-resident even when
+                // several such kernels are in flight on different streams
+                int n_arg = n;
+                void* args[] = {(void*)&tb, (void*)&n_arg, (void*)&w, (void*)&keep_sorted};
+                cudaError_t ce = cudaLaunchCooperativeKernel((const void*)sp_resolve_kernel, dim3(kSparseCtas), dim3(kSparseThreads), args, 0, st);
+                if (ce != cudaSuccess) return (int)ce;
+            }
             count_launch(16);
             gate = w.ctl;
         }
@@ -1681,7 +1687,14 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         count_launch();
         if ((N + 63) / 64 >= (size_t)kCoopMinBlocks) {
             cudaMemsetAsync(pub_flag, 0, sizeof(int) * (2 * N / 64 + 8), st);
-            reduce_kernel<<<kNumSMs, kReduceThreads, smem, st>>>(tb, mask, keep_sorted, pub_keep, pub_flag, 1, gate);
+            {   // CTAs of one group wait for each other's published keep words: cooperative launch (co-residency)
+                int skip_small = 1;
+                const unsigned long long* mask_c = mask;
+                void* args[] = {(void*)&tb, (void*)&mask_c, (void*)&keep_sorted, (void*)&pub_keep, (void*)&pub_flag, (void*)&skip_small,
+                                (void*)&gate};
+                cudaError_t ce = cudaLaunchCooperativeKernel((const void*)reduce_kernel, dim3(kNumSMs), dim3(kReduceThreads), args, smem, st);
+                if (ce != cudaSuccess) return (int)ce;
+            }
             count_launch();
         }
     }
