@@ -30,8 +30,6 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
-#include <cstdio>
-
 #include "common.cuh"
 #include "nms_engine.cuh"
 #include "poly_iou.cuh"
@@ -695,7 +693,6 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
     __shared__ int s_count;
     __shared__ int s_count2;  // one counter per stage: a stage's result is still being read when the next one resets its own
     __shared__ int s_count3;
-    __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = (n + 63) >> 6;
     const int total = T * (T + 1) / 2;
@@ -801,7 +798,6 @@ ov_filter_kernel(const RBox* __restrict__ boxes, int n, float thr, int2* __restr
     __shared__ int s_count;
     __shared__ int s_count2;  // one counter per stage: a stage's result is still being read when the next one resets its own
     __shared__ int s_count3;
-    __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31;
     const int T = (n + 63) >> 6;
     const int total = T * (T + 1) / 2;

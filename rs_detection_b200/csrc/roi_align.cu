@@ -903,14 +903,6 @@ static size_t fwd_smem_bytes(const rsdet_roi_align_cfg* c) {
     return list_bytes(nbins, ntaps / nbins) + ((nbins * 4 + 15) & ~(size_t)15) + (stage > tmp ? stage : tmp);
 }
 
-static size_t fast_smem_bytes(const rsdet_roi_align_cfg* c) {
-    int nbins = c->pooled_h * c->pooled_w;
-    int nsamp = nbins * c->sampling_ratio * c->sampling_ratio;
-    int Q = quads_per_chunk(c->channels);
-    return sizeof(Taps) * (size_t)nsamp + sizeof(float) * 4 * (size_t)nbins * (Q + 1);  // backward layout is the larger
-}
-
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (librsdet links no libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
