@@ -367,24 +367,32 @@ segments_from_counts_kernel(const int* __restrict__ counts, int C, double thr, S
 // nearly every warp holds at least one pair whose circles touch (16 % of the pairs on the bench proposals).
 template <typename Pred>
 __device__ __forceinline__ int compact_queue(const unsigned short* __restrict__ in, int n_in, unsigned short* __restrict__ out,
-                                             int* s_counter, Pred keep) {
+                                             int* s_counter, int* s_wsum, Pred keep) {
+    // n_in <= 8 * kNmsThreads (the callers' chunk size): a thread tests entries tid, tid + 128, ..., keeps its
+    // verdicts in a register and the survivors are placed with ONE prefix sum (no ballot / atomic per 32 entries)
     const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) *s_counter = 0;
+    unsigned hits = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int qi = tid + k * kNmsThreads;
+        if (qi < n_in && keep((int)in[qi])) hits |= 1u << k;
+    }
+    const int mine = __popc(hits);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_wsum[tid >> 5] = incl;
     __syncthreads();
-    for (int qi = tid; qi < ((n_in + 31) & ~31); qi += kNmsThreads) {
-        int p = 0;
-        bool live = qi < n_in;
-        if (live) {
-            p = in[qi];
-            live = keep(p);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(s_counter, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (live) out[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)p;
-        }
+    int pos = incl - mine;
+    for (int w = 0; w < (tid >> 5); w++) pos += s_wsum[w];
+    if (tid == kNmsThreads - 1) *s_counter = pos + mine;
+    while (hits) {
+        const int k = __ffs(hits) - 1;
+        hits &= hits - 1;
+        out[pos++] = in[tid + k * kNmsThreads];
     }
     __syncthreads();
     return *s_counter;
@@ -487,9 +495,9 @@ mask_tiles_kernel(const typename Traits<KIND>::Box* __restrict__ boxes, SegTable
         const int cnt = s_count;
         if (Tr::kRefine) {
             for (int q0 = 0; q0 < cnt; q0 += kQ2) {
-                const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2,
+                const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2, s_wsum,
                                              [&](int p) { return Tr::refine1(s_row[p >> 6], s_col[p & 63], thr); });
-                const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3,
+                const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3, s_wsum,
                                              [&](int p) { return Tr::refine2(s_row[p >> 6], s_col[p & 63], thr); });
                 for (int qi = tid; qi < n3; qi += kNmsThreads) {
                     const int p = s_queue3[qi];
@@ -759,9 +767,9 @@ ov_tiles_kernel(const RBox* __restrict__ boxes, int n, float thr, unsigned long 
         const int cnt = s_count;
         for (int q0 = 0; q0 < cnt; q0 += kQ2) {
             // stage 2: axis-aligned bound; stage 3: strip bound (1.03x the truly suppressing pairs survive)
-            const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2,
+            const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2, s_wsum,
                                          [&](int p) { return !rbox_iou_below(s_row[p >> 6], s_col[p & 63], thr); });
-            const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3,
+            const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3, s_wsum,
                                          [&](int p) { return !rbox_iou_below_strips(s_row[p >> 6], s_col[p & 63], thr); });
             // stage 4: exact clipper
             for (int qi = tid; qi < n3; qi += kNmsThreads) {
@@ -863,9 +871,9 @@ ov_filter_kernel(const RBox* __restrict__ boxes, int n, float thr, int2* __restr
         const int cnt = s_count;
         for (int q0 = 0; q0 < cnt; q0 += kQ2) {
             // stage 2: axis-aligned bound; stage 3: strip bound (1.03x the truly suppressing pairs survive)
-            const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2,
+            const int n2 = compact_queue(s_queue + q0, min(kQ2, cnt - q0), s_queue2, &s_count2, s_wsum,
                                          [&](int p) { return !rbox_iou_below(s_row[p >> 6], s_col[p & 63], thr); });
-            const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3,
+            const int n3 = compact_queue(s_queue2, n2, s_queue3, &s_count3, s_wsum,
                                          [&](int p) { return !rbox_iou_below_strips(s_row[p >> 6], s_col[p & 63], thr); });
             // survivors go to the global pair queue (ov_clip_kernel evens them out over the whole GPU); a tile
             // that does not fit is flagged and redone by ov_tiles_kernel
