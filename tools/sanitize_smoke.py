@@ -51,5 +51,17 @@ anc = AnchorGenerator(strides=[4, 8, 16], ratios=[0.5, 1.0, 2.0], scales=[8]).gr
 core.rpn_proposals([t(x) for x in cls_], [t(x) for x in reg_], anc, 3, True, 500, 300, 0.8, 0)[1].item()
 cls2, reg2 = W.rpn_outputs(shp, 3, 2, 2)
 core.rpn_proposals([t(x) for x in cls2], [t(x) for x in reg2], anc, 3, False, 100, 50, 0.7, 4.0, want_candidates=True)[1].item()
+# sparse merge path (n >= 8192: sweep, CSR, persistent fixed-point resolve) and the pair-queue overflow fallback of the
+# decision matrix (dense cluster, 2 classes)
+big = W.merge_scene(num_objects=2600, scene=4000, seed=3)
+core.nms(NMS_MERGE, t(big["polys"]), t(big["scores"]), 0.1, labels=t(big["labels"].astype(np.int32)), want_score=True).count
+rng = np.random.default_rng(5)
+dc = np.empty((1500, 5), np.float32)
+dc[:, :2] = 200 + rng.normal(0, 6.0, (1500, 2)); dc[:, 2] = rng.uniform(60, 90, 1500); dc[:, 3] = rng.uniform(25, 40, 1500)
+dc[:, 4] = rng.uniform(-0.4, 0.4, 1500)
+core.multiclass_nms_rotated(t(dc), t(W.class_scores(1500, 2, 3, 1.0)), 0.01, 0.6, 500)[2].item()
+from rs_detection_b200._lib import NMS_HBB_P1, NMS_HBB_P1_F64
+core.nms(NMS_HBB_P1, t(hb.astype(np.float32)), t(W.distinct_scores(200, 3)), 0.5, want_score=True).count
+core.nms(NMS_HBB_P1_F64, t(hb), t(W.distinct_scores(200, 3).astype(np.float64)), 0.5, want_score=True).count
 torch.cuda.synchronize()
 print("sanitize smoke done")
