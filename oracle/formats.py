@@ -109,7 +109,7 @@ def _obb2hbb64(obb):
     return np.concatenate([c - bias, c + bias], axis=-1)
 
 
-def ensemble_with_class(data_list, thresh):
+def ensemble_with_class(data_list, thresh, stable_ties=False):
     out = []
     for image_id in np.unique(data_list[0][:, 0]):
         dets = np.concatenate([d[d[:, 0] == image_id, :] for d in data_list])
@@ -117,18 +117,18 @@ def ensemble_with_class(data_list, thresh):
             t = thresh[FAIR1M_1_5_CLASSES[ci]] if isinstance(thresh, dict) else thresh
             sub = dets[dets[:, -1] == ci + 1]
             prop = np.concatenate([_obb2hbb64(_poly2obb_cv(sub[:, 1:9])), sub[:, 9:10]], axis=1)
-            keep = O.hbb_nms(prop, t)
+            keep = O.hbb_nms(prop, t, stable_ties)
             if len(keep) > 0:
                 out.append(sub[np.asarray(keep, dtype=np.int64), :])
     return np.concatenate(out)
 
 
-def ensemble_without_class(data_list, thresh):
+def ensemble_without_class(data_list, thresh, stable_ties=False):
     out = []
     for image_id in np.unique(data_list[0][:, 0]):
         dets = np.concatenate([d[d[:, 0] == image_id, :] for d in data_list])
         prop = np.concatenate([_obb2hbb64(_poly2obb_cv(dets[:, 1:9])), dets[:, 9:10]], axis=1)
-        keep = O.hbb_nms(prop, thresh)
+        keep = O.hbb_nms(prop, thresh, stable_ties)
         if len(keep) > 0:
             out.append(dets[np.asarray(keep, dtype=np.int64), :])
     return np.concatenate(out)

@@ -353,25 +353,34 @@ def iou_poly(p, q):
     return lib().orc_iou_poly(p.ctypes.data_as(_pd), q.ctypes.data_as(_pd))
 
 
-def py_cpu_nms_poly_fast(dets, thresh):
+def score_order(scores, stable_ties=False):
+    """`scores.argsort()[::-1]` as the reference's merge paths write it.  numpy's default argsort is not stable
+    (and since 2.0 vectorised), so the order of EQUAL scores is an artefact of the numpy build; `stable_ties`
+    gives the well-defined variant `argsort(kind='stable')[::-1]` (higher index first), which is the device
+    engine's tie rule for the float64 merge kinds and what numpy itself does for n <= 16."""
+    s = np.asarray(scores)
+    return np.ascontiguousarray((s.argsort(kind="stable") if stable_ties else s.argsort())[::-1], np.int32)
+
+
+def py_cpu_nms_poly_fast(dets, thresh, stable_ties=False):
     """python/jdet/data/devkits/result_merge.py:66-127 -> list of kept indices in score order."""
     d = np.ascontiguousarray(dets, np.float64).reshape(-1, 9)
     n = d.shape[0]
     if n == 0:
         return []
-    order = np.ascontiguousarray(d[:, 8].argsort()[::-1], np.int32)
+    order = score_order(d[:, 8], stable_ties)
     keep = np.zeros((n,), np.int32)
     nk = lib().orc_merge_nms(d.ctypes.data_as(_pd), order.ctypes.data_as(_pi), n, float(thresh), keep.ctypes.data_as(_pi))
     return keep[:nk].tolist()
 
 
-def hbb_nms(boxes, thresh):
+def hbb_nms(boxes, thresh, stable_ties=False):
     """merge.py:14-27 `nms` -> np.array of kept indices in score order."""
     b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 5)
     n = b.shape[0]
     if n == 0:
         return np.array([], np.int64)
-    order = np.ascontiguousarray(b[:, 4].argsort()[::-1], np.int32)
+    order = score_order(b[:, 4], stable_ties)
     keep = np.zeros((n,), np.int32)
     nk = lib().orc_hbb_nms(b.ctypes.data_as(_pd), order.ctypes.data_as(_pi), n, float(thresh), keep.ctypes.data_as(_pi))
     return keep[:nk].astype(np.int64)
@@ -638,11 +647,11 @@ def rpn_get_bboxes_single(cls_scores, bbox_preds, mlvl_anchors, use_sigmoid=True
 
 def py_cpu_nms(dets, thresh):
     """python/jdet/data/devkits/result_merge.py:143-174: horizontal NMS, float64, '+1' areas, survivors ovr <= thresh.
-    Ties: lower index first (the reference's argsort()[::-1] leaves them unspecified)."""
+    Ties: higher index first (`argsort(kind='stable')[::-1]`, see score_order)."""
     d = np.asarray(dets, np.float64).reshape(-1, 5)
     x1, y1, x2, y2, sc = d[:, 0], d[:, 1], d[:, 2], d[:, 3], d[:, 4]
     areas = (x2 - x1 + 1) * (y2 - y1 + 1)
-    order = np.argsort(-sc, kind="stable")
+    order = score_order(sc, True).astype(np.int64)
     keep = []
     while order.size > 0:
         i = order[0]

@@ -30,6 +30,10 @@ UNITS = {
     "rpn.cu": ["-fmad=false"],
     "roi_align.cu": ["-DRSDET_BULK_ROWS=" + os.environ.get("RSDET_BULK_ROWS", "0")],
 }
+# A/B measurement builds only (RSDET_TUNING=1 python -m rs_detection_b200.build --force): lets the environment pick
+# among the kernels of a path.  The shipped library is built without it and reads no environment variable.
+if os.environ.get("RSDET_TUNING") == "1":
+    COMMON = COMMON + ["-DRSDET_TUNING"]
 
 
 def _deps():

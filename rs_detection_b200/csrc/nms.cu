@@ -103,15 +103,18 @@ template <> struct Traits<RSDET_NMS_HBB> {
     static constexpr int kRow = 4; static constexpr bool kScratch = false;
     __device__ static Box prep(const Raw* r) { Box b; b.x1 = r[0]; b.y1 = r[1]; b.x2 = r[2]; b.y2 = r[3]; return b; }
     static constexpr bool kRefine = false;
+    // pairs without a proper overlap have iou = 0 / (A + B) in the reference: kept for thresh > 0 -- EXCEPT when
+    // both areas are zero (0/0 = NaN, and `NaN < thresh` is false: suppressed), so those pairs pass the filter
     __device__ static bool cheap(const Box& a, const Box& b) {
-        return fmin(a.x2, b.x2) > fmax(a.x1, b.x1) && fmin(a.y2, b.y2) > fmax(a.y1, b.y1);
+        return (fmin(a.x2, b.x2) > fmax(a.x1, b.x1) && fmin(a.y2, b.y2) > fmax(a.y1, b.y1)) ||
+               (a.x2 - a.x1) * (a.y2 - a.y1) + (b.x2 - b.x1) * (b.y2 - b.y1) == 0.0;
     }
     __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
     __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
-    // merge.py:21-25: survivors are `iou < thresh`
+    // merge.py:19-25: overlaps = prod(br - tl) * all(br > tl); survivors are `iou < thresh`
     __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) {
         double tlx = fmax(a.x1, b.x1), tly = fmax(a.y1, b.y1), brx = fmin(a.x2, b.x2), bry = fmin(a.y2, b.y2);
-        double ov = (brx - tlx) * (bry - tly);
+        double ov = (brx - tlx) * (bry - tly) * ((brx > tlx && bry > tly) ? 1.0 : 0.0);
         double iou = ov / ((a.x2 - a.x1) * (a.y2 - a.y1) + (b.x2 - b.x1) * (b.y2 - b.y1) - ov);
         return !(iou < thr);
     }
@@ -179,12 +182,17 @@ __device__ __forceinline__ unsigned long long desc_key(double s) {
 }
 
 // rows that are not live (multiclass candidates below score_thr) carry score -inf and sort last
+// `reverse`: rows are handed to the (stable) radix sort in descending index order, so equal scores come out
+// HIGHER index first -- the order of `scores.argsort(kind='stable')[::-1]`, the tie rule of the float64 merge
+// kinds (result_merge.py:84, merge.py:16).  Text-format scores have four decimals, so ties are common there.
 template <typename ScoreT, typename KeyT>
-__global__ void make_keys_kernel(const ScoreT* __restrict__ scores, int n_max, KeyT* __restrict__ keys, int* __restrict__ idx) {
+__global__ void make_keys_kernel(const ScoreT* __restrict__ scores, int n_max, KeyT* __restrict__ keys, int* __restrict__ idx,
+                                 bool reverse) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_max) return;
-    keys[i] = (KeyT)desc_key(scores[i]);
-    idx[i] = i;
+    const int r = reverse ? n_max - 1 - i : i;
+    keys[i] = (KeyT)desc_key(scores[r]);
+    idx[i] = r;
 }
 
 // label_bits == 32: arbitrary int32 labels (sign-flipped key).  label_bits < 32: the caller guarantees
@@ -1502,10 +1510,11 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     void* cub_tmp = ws.take<char>(cub_bytes);
     if (!ws.ok()) return RSDET_EWORKSPACE;
 
-    // 1. sort by score (descending, stable -> lower index first on ties)
+    // 1. sort by score (descending, stable: lower index first on ties for the fp32 kinds -- Jittor's argsort --,
+    //    higher index first for the float64 merge kinds, see make_keys_kernel)
     const int* idx_score;
     if (f64) {
-        make_keys_kernel<double, unsigned long long><<<ceil_div(n, 256), 256, 0, st>>>((const double*)a.scores, n, keyA, idxA);
+        make_keys_kernel<double, unsigned long long><<<ceil_div(n, 256), 256, 0, st>>>((const double*)a.scores, n, keyA, idxA, true);
         cub::DoubleBuffer<unsigned long long> dk(keyA, keyB);
         cub::DoubleBuffer<int> dv(idxA, idxB);
         size_t need = 0;
@@ -1516,7 +1525,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     } else {
         uint32_t* kA = (uint32_t*)keyA;
         uint32_t* kB = (uint32_t*)keyB;
-        make_keys_kernel<float, uint32_t><<<ceil_div(n, 256), 256, 0, st>>>((const float*)a.scores, n, kA, idxA);
+        make_keys_kernel<float, uint32_t><<<ceil_div(n, 256), 256, 0, st>>>((const float*)a.scores, n, kA, idxA, false);
         cub::DoubleBuffer<uint32_t> dk(kA, kB);
         cub::DoubleBuffer<int> dv(idxA, idxB);
         size_t need = 0;

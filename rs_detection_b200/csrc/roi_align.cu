@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -550,6 +551,315 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     }
 }
 
+// ---------------------------------------------------------------------------------- forward (pixel-major)
+// The default forward path for the Oriented R-CNN geometry (7x7 bins, 2x2 samples per bin, C % 256 == 0).
+//
+// What bounds the gather on B200 is not HBM but the path between L2 and the SM: the bin-major kernel above
+// pulls ~441 merged taps x 1 KB per RoI through L2 -> L1 -> registers although they cover only ~223 DISTINCT
+// feature pixels -- neighbouring bins share the one-pixel border of their bilinear footprints.  Here every
+// distinct pixel of a bin ROW is loaded once and applied to all bins of the row that use it:
+//   * one warp per bin row, lane = 2 channel quads (the warp covers 256 channels), 7 x 8 accumulators in
+//     registers;
+//   * per row a PIXEL LIST (distinct pixels in raster order of the RoI's patch) and a CONTRIBUTION STREAM
+//     {code = bin_col * 4 + slot, weight}: pixels are fetched in batches of four (8 x LDG.128 in flight per
+//     thread), then the batch's contributions are applied through a warp-uniform jump (`switch` on the code:
+//     the register index of an accumulator must be static, so the bin is resolved by control flow);
+//   * lists are built per warp without block barriers: bitmap of the touched patch pixels (shared-memory
+//     atomicOr), rank = prefix popcount, per-pixel contribution slots by shared-memory atomicAdd.  Pixels are
+//     visited in raster order and a (pixel, bin) pair occurs once (per-bin merge A2), so the summation order
+//     per output element -- and the result -- is deterministic.
+// L1 wavefronts per RoI: 304 x 8 for the gather instead of 441 x 8; rows r and r+1 run side by side, so the
+// border pixels they share hit in L1.
+constexpr int kPxRows = 7, kPxCols = 7;
+constexpr int kPxThreads = 32 * kPxRows;
+constexpr int kPxMaxPix = 16 * kPxCols;            // taps of one bin row before pixel dedupe
+constexpr int kPxPixPitch = 128;                   // pixel words per row (batch tail padded)
+constexpr int kPxCtrPitch = kPxMaxPix + kPxMaxPix / 4 + 4;  // contributions + one end marker per batch of 4 pixels
+constexpr int kPxBmWords = 128;                    // dedupe bitmap: patches of up to 4096 pixels (larger: no dedupe)
+constexpr int kPxEnd = 4 * kPxCols;                // contribution code that ends a batch
+
+struct PxSmem {
+    unsigned pixw[kPxRows][kPxPixPitch];
+    int2 ctr[kPxRows][kPxCtrPitch];
+    int npix[8];
+    int box[4];                                    // x0, x1, y0, y1 of the RoI's tap pixels
+    union {
+        float stage[256 * kPxRows * kPxCols];      // [c][bin] = the RoI's output block
+        struct {
+            int key[kPxRows * kPxCols * 17];       // A1: (y << 16 | x) per tap, bin pitch 17
+            float w[kPxRows * kPxCols * 17];
+            int2 list[kPxRows * kPxCols * 17];     // A2: merged per-bin lists
+            int cnt[64];
+            unsigned bm[kPxRows][kPxBmWords];
+            int wpre[kPxRows][kPxBmWords];
+            int cntp[kPxRows][kPxPixPitch];
+        } b;
+    } u;
+};
+
+#define RSDET_PX_FMA8(j, k)                                                                                         \
+    {                                                                                                                \
+        a[j][0].x = fmaf(wt, v[k][0].x, a[j][0].x); a[j][0].y = fmaf(wt, v[k][0].y, a[j][0].y);                      \
+        a[j][0].z = fmaf(wt, v[k][0].z, a[j][0].z); a[j][0].w = fmaf(wt, v[k][0].w, a[j][0].w);                      \
+        a[j][1].x = fmaf(wt, v[k][1].x, a[j][1].x); a[j][1].y = fmaf(wt, v[k][1].y, a[j][1].y);                      \
+        a[j][1].z = fmaf(wt, v[k][1].z, a[j][1].z); a[j][1].w = fmaf(wt, v[k][1].w, a[j][1].w);                      \
+    }
+#define RSDET_PX_CASE(j, k) case (j) * 4 + (k): RSDET_PX_FMA8(j, k) break;
+#define RSDET_PX_ROW(j) RSDET_PX_CASE(j, 0) RSDET_PX_CASE(j, 1) RSDET_PX_CASE(j, 2) RSDET_PX_CASE(j, 3)
+
+// blockDim = (32, 7): threadIdx.y is the warp = bin row, which the compiler then knows to be warp-uniform
+// (list addresses in uniform registers, plain branches in the contribution loop).
+__global__ void __block_size__((32, kPxRows, 1)) __maxnreg__(128)
+roi_align_fwd_px_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom* __restrict__ geoms, int K,
+                        float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PxSmem& S = *reinterpret_cast<PxSmem*>(smem_raw);
+    const int roi = order ? order[blockIdx.x] : blockIdx.x;
+    const int lane = threadIdx.x, row = threadIdx.y, tid = row * 32 + lane;
+    constexpr int nbins = kPxRows * kPxCols;
+    const int C = L.C;
+    const int chunk0 = blockIdx.y * 256;
+    const RoiGeom g = geoms[roi];
+    const int H = L.H[g.level], W = L.W[g.level];
+
+    if (tid == 0) { S.box[0] = 0x7fffffff; S.box[1] = -1; S.box[2] = 0x7fffffff; S.box[3] = -1; }
+    __syncthreads();
+    // A1: one thread per sample -> 4 (pixel key, weight) taps; bounding box of the touched pixels
+    {
+        int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
+        if (tid < nbins * 4) {
+            const int b = tid >> 2, q = tid & 3;
+            const int ph = b / kPxCols, pw = b - ph * kPxCols, iy = q >> 1, ix = q & 1;
+            float x, y;
+            sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+            int kx[2] = {0, 0}, ky[2] = {0, 0};
+            float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
+            if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {   // make_taps, kept as (x, y) pairs
+                if (y < 0) y = 0;
+                if (x < 0) x = 0;
+                int yl = (int)y, xl = (int)x, yh, xh;
+                if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+                wy[0] = __fsub_rn(1.f, ly); wy[1] = ly; wx[0] = __fsub_rn(1.f, lx); wx[1] = lx;
+                kx[0] = xl; kx[1] = xh; ky[0] = yl; ky[1] = yh;
+                x0 = xl; x1 = xh; y0 = yl; y1 = yh;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                S.u.b.key[b * 17 + q * 4 + k] = (ky[k >> 1] << 16) | kx[k & 1];
+                S.u.b.w[b * 17 + q * 4 + k] = __fmul_rn(wy[k >> 1], wx[k & 1]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0 && x1 >= 0) { atomicMin(&S.box[0], x0); atomicMax(&S.box[1], x1); atomicMin(&S.box[2], y0); atomicMax(&S.box[3], y1); }
+    }
+    __syncthreads();
+    // A2: per-bin merge, one lane per bin, 16 taps in registers (see build_tap_lists)
+    if (tid < nbins) {
+        const int b = tid;
+        int o[16];
+        float w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) { o[j] = S.u.b.key[b * 17 + j]; w[j] = S.u.b.w[b * 17 + j]; }
+        int pos = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            float acc = w[j];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (i <= j) continue;
+                const bool same = o[i] == o[j] && w[j] != 0.f;
+                acc += same ? w[i] : 0.f;
+                w[i] = same ? 0.f : w[i];
+            }
+            if (w[j] != 0.f) S.u.b.list[b * 17 + pos++] = make_int2(o[j], __float_as_int(acc));
+        }
+        S.u.b.cnt[b] = pos;
+    }
+    __syncthreads();
+    // G: this warp's row -> distinct pixels + contribution stream (warp-local from here on)
+    {
+        const int px0 = S.box[0], py0 = S.box[2];
+        const int pwid = S.box[1] - px0 + 1, phgt = S.box[3] - py0 + 1;
+        const bool dedupe = pwid > 0 && pwid * phgt <= 32 * kPxBmWords;
+        int key[4], code[4], loc[4], rank[4], pos[4];
+        bool val[4];
+        unsigned* bm = S.u.b.bm[row];
+        int* wpre = S.u.b.wpre[row];
+        int* cntp = S.u.b.cntp[row];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = lane + 32 * i, bc = t >> 4, j = t & 15;
+            const int b = row * kPxCols + bc;
+            val[i] = t < kPxMaxPix && j < S.u.b.cnt[min(b, nbins - 1)];
+            const int2 e = val[i] ? S.u.b.list[b * 17 + j] : make_int2(0, 0);
+            key[i] = e.x; code[i] = bc * 4; pos[i] = e.y;   // pos[] carries the weight bits until the slot is known
+            loc[i] = ((e.x >> 16) - py0) * pwid + ((e.x & 0xffff) - px0);
+            bm[lane + 32 * i] = 0u;
+            cntp[lane + 32 * i] = 0;
+        }
+        __syncwarp();
+        int npix;
+        if (dedupe) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (val[i]) atomicOr(&bm[loc[i] >> 5], 1u << (loc[i] & 31));
+            __syncwarp();
+            const uint4 m = *reinterpret_cast<const uint4*>(bm + 4 * lane);
+            const int c0 = __popc(m.x), c1 = __popc(m.y), c2 = __popc(m.z), c3 = __popc(m.w);
+            int x = c0 + c1 + c2 + c3;
+            const int sum = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            npix = __shfl_sync(0xffffffffu, x, 31);
+            const int ex = x - sum;
+            *reinterpret_cast<int4*>(wpre + 4 * lane) = make_int4(ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                rank[i] = val[i] ? wpre[loc[i] >> 5] + __popc(bm[loc[i] >> 5] & ((1u << (loc[i] & 31)) - 1u)) : 0;
+        } else {
+            int base = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const unsigned bal = __ballot_sync(0xffffffffu, val[i]);
+                rank[i] = base + __popc(bal & ((1u << lane) - 1u));
+                base += __popc(bal);
+            }
+            npix = base;
+        }
+        // slot of every contribution inside its pixel, then the start of every pixel in the stream
+        int wbits[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { wbits[i] = pos[i]; pos[i] = val[i] ? atomicAdd(&cntp[rank[i]], 1) : 0; }
+        __syncwarp();
+        const int4 cc = *reinterpret_cast<const int4*>(cntp + 4 * lane);   // pixels 4*lane .. 4*lane+3 = batch `lane`
+        int x = cc.x + cc.y + cc.z + cc.w;
+        const int sum = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        const int ex = x - sum + lane;                                      // + one end marker per earlier batch
+        __syncwarp();                                                       // wpre is dead: reuse it for the pixel starts
+        *reinterpret_cast<int4*>(wpre + 4 * lane) = make_int4(ex, ex + cc.x, ex + cc.x + cc.y, ex + cc.x + cc.y + cc.z);
+        const int nbatch = (npix + 3) >> 2;
+        if (lane < nbatch) S.ctr[row][ex + sum] = make_int2(kPxEnd, 0);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (val[i]) {
+                S.ctr[row][wpre[rank[i]] + pos[i]] = make_int2(code[i] + (rank[i] & 3), wbits[i]);
+                if (pos[i] == 0) S.pixw[row][rank[i]] = (unsigned)((key[i] >> 16) * W + (key[i] & 0xffff));
+            }
+        __syncwarp();
+        if (lane < 4 && npix > 0 && npix + lane < 4 * nbatch) S.pixw[row][npix + lane] = S.pixw[row][npix - 1];
+        if (lane == 0) S.npix[row] = npix;
+    }
+    __syncthreads();   // the build scratch becomes the staging block
+
+    // gather
+    float4 a[kPxCols][2];
+#pragma unroll
+    for (int j = 0; j < kPxCols; j++) a[j][0] = a[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + lane * 4;
+        const unsigned rowbytes = (unsigned)C * 4u;
+        const int npix = S.npix[row];
+        const unsigned* pw = S.pixw[row];
+        const int2* cp = S.ctr[row];
+        for (int p0 = 0; p0 < npix; p0 += 4) {
+            const uint4 px = *reinterpret_cast<const uint4*>(pw + p0);
+            float4 v[4][2];
+            {
+                unsigned long long ad[4];
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[0]) : "r"(px.x), "r"(rowbytes), "l"((unsigned long long)feat));
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[1]) : "r"(px.y), "r"(rowbytes), "l"((unsigned long long)feat));
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[2]) : "r"(px.z), "r"(rowbytes), "l"((unsigned long long)feat));
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[3]) : "r"(px.w), "r"(rowbytes), "l"((unsigned long long)feat));
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    v[k][0] = ldg_nc_v4(reinterpret_cast<const float*>(ad[k]));
+                    v[k][1] = ldg_nc_v4(reinterpret_cast<const float*>(ad[k]) + 128);
+                }
+            }
+            bool more = true;
+            while (more) {
+                const int2 e = *cp++;
+                const float wt = __int_as_float(e.y);
+                switch (e.x) {
+                    RSDET_PX_ROW(0) RSDET_PX_ROW(1) RSDET_PX_ROW(2) RSDET_PX_ROW(3) RSDET_PX_ROW(4) RSDET_PX_ROW(5) RSDET_PX_ROW(6)
+                    default: more = false; break;
+                }
+            }
+        }
+    }
+    // stage [c][bin] (conflict-free component rotation, see rot4) and stream the block out
+    {
+        const int oct = (lane >> 3) & 3;
+#pragma unroll
+        for (int j = 0; j < kPxCols; j++) {
+            const int b = row * kPxCols + j;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                float4 r = a[j][u];
+                r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;      // /count, count = 4 samples (exact)
+                r = rot4(r, oct);
+                const int c0 = (lane + u * 32) * 4;
+                S.u.stage[(c0 + ((0 + oct) & 3)) * nbins + b] = r.x;
+                S.u.stage[(c0 + ((1 + oct) & 3)) * nbins + b] = r.y;
+                S.u.stage[(c0 + ((2 + oct) & 3)) * nbins + b] = r.z;
+                S.u.stage[(c0 + ((3 + oct) & 3)) * nbins + b] = r.w;
+            }
+        }
+    }
+    __syncthreads();
+    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;     // 256 * 49 floats: 16-byte aligned
+    const float4* s4 = reinterpret_cast<const float4*>(S.u.stage);
+#pragma unroll 2
+    for (int e = tid; e < 256 * nbins / 4; e += kPxThreads) stg_cs_v4(dst + (size_t)e * 4, s4[e]);
+}
+
+// cudaFuncSetAttribute is per device: remember what was set for each one (a process may drive several GPUs)
+static void set_dyn_smem(const void* func, size_t bytes) {
+    struct Slot { const void* f; size_t b; };
+    static Slot slots[64][16];
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64) { cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); return; }
+    for (int i = 0; i < 16; i++) {
+        Slot& s = slots[dev][i];
+        if (s.f == func || s.f == nullptr) {
+            if (s.f == func && s.b >= bytes) return;
+            s.f = func; s.b = bytes;
+            cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            return;
+        }
+    }
+    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// 0 = pixel-major (default), 1 = bin-major register path, 2 = TMA gather4.  Only builds made with
+// -DRSDET_TUNING (profiling / A-B measurements) read the environment; the shipped library always returns 0.
+static int roi_path_choice() {
+#ifdef RSDET_TUNING
+    if (const char* e = getenv("RSDET_ROI_PATH")) return atoi(e);
+#endif
+    return 0;
+}
+
+static bool px_path_ok(const rsdet_roi_align_cfg* c) {
+    if (c->pooled_h != kPxRows || c->pooled_w != kPxCols || c->sampling_ratio != 2 || c->channels % 256 != 0) return false;
+    for (int l = 0; l < c->num_levels; l++)   // pixel keys are (y << 16 | x); pixel indices 32-bit
+        if (c->height[l] >= 32768 || c->width[l] >= 65536 || (long long)c->height[l] * c->width[l] >= (1ll << 31)) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------- forward (TMA gather4)
 // Same decomposition (one CTA per RoI, merged tap lists, warp = bin group), but the feature rows are no
 // longer pulled through the LSU into registers: each group of 4 merged taps is ONE Blackwell
@@ -886,7 +1196,10 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
     L.num_levels = c->num_levels; L.batch = c->batch; L.C = c->channels;
     L.PH = c->pooled_h; L.PW = c->pooled_w; L.sampling_ratio = c->sampling_ratio; L.version = c->version;
     L.extend_w = c->extend_w; L.extend_h = c->extend_h; L.finest_scale = c->finest_scale;
-    { const char* e = getenv("RSDET_ROI_DBG_SKIP_MAIN"); L.dbg_skip_main = e ? atoi(e) : 0; }
+    L.dbg_skip_main = 0;
+#ifdef RSDET_TUNING
+    if (const char* e = getenv("RSDET_ROI_DBG_SKIP_MAIN")) L.dbg_skip_main = atoi(e);
+#endif
     for (int l = 0; l < RSDET_MAX_LEVELS; l++) {
         L.feat[l] = nullptr; L.grad[l] = nullptr;
         L.H[l] = l < c->num_levels ? c->height[l] : 1;
@@ -945,8 +1258,7 @@ static bool tma_path_ok(const rsdet_roi_align_cfg* c) {
     // Opt-in (RSDET_ROI_TMA=1): measured 308 us per 4000-RoI tile against 200 us for the register path on
     // B200 (profiles/README.md, "TMA gather4 experiment") -- correct, but two 105 KB CTAs per SM expose the
     // tap-list and write-out phases that four 57 KB CTAs overlap.  Kept for the round-2 persistent-CTA rework.
-    const char* e = getenv("RSDET_ROI_TMA");
-    if (!(e && e[0] == '1')) return false;
+    if (roi_path_choice() != 2) return false;
     if (c->channels % 256 != 0 || c->pooled_h * c->pooled_w > 8 * kTmaMaxSlots) return false;
     for (int l = 0; l < c->num_levels; l++)
         if ((long long)c->batch * c->height[l] * c->width[l] >= (1ll << 31)) return false;
@@ -1006,16 +1318,8 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         if (rc != RSDET_OK) return rc;
     }
     size_t smem = fwd_smem_bytes(cfg);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (const char* cv = getenv("RSDET_ROI_CARVEOUT")) {
-            cudaFuncSetAttribute(roi_align_fwd_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-            cudaFuncSetAttribute(roi_align_fwd_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
-        }
-        smem_set = smem;
-    }
+    set_dyn_smem((const void*)roi_align_fwd_kernel<1>, smem);
+    set_dyn_smem((const void*)roi_align_fwd_kernel<2>, smem);
     // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
     roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, levels_out);
     count_launch();
@@ -1025,6 +1329,13 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
         count_launch();
     }
+    if (px_path_ok(cfg) && roi_path_choice() == 0) {
+        set_dyn_smem((const void*)roi_align_fwd_px_kernel, sizeof(PxSmem));
+        dim3 pgrid(num_rois, cfg->channels / 256), pblock(32, kPxRows, 1);
+        roi_align_fwd_px_kernel<<<pgrid, pblock, sizeof(PxSmem), st>>>(L, order, geoms, num_rois, out);
+        count_launch();
+        return cuda_status();
+    }
     if (tma_path_ok(cfg)) {
         TmaMaps maps;
         bool ok = true;
@@ -1033,11 +1344,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         for (int l = cfg->num_levels; l < RSDET_MAX_LEVELS; l++) maps.m[l] = maps.m[0];
         if (ok) {
             const size_t tsmem = tma_smem_bytes(cfg);
-            static size_t tsmem_set = 0;
-            if (tsmem > tsmem_set) {
-                cudaFuncSetAttribute(roi_align_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-                tsmem_set = tsmem;
-            }
+            set_dyn_smem((const void*)roi_align_fwd_tma_kernel, tsmem);
             dim3 tgrid(num_rois, cfg->channels / 256);
             roi_align_fwd_tma_kernel<<<tgrid, kRoiThreads, tsmem, st>>>(L, maps, rois, order, num_rois, out, levels_out);
             count_launch();
@@ -1094,12 +1401,8 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
             roi_align_generic_kernel<true><<<grid, 256, 0, st>>>(L, M, rois, num_rois, const_cast<float*>(grad_out), nullptr);
         } else {
             size_t smem = fwd_smem_bytes(cfg);
-            static size_t smem_set = 0;
-            if (smem > smem_set) {
-                cudaFuncSetAttribute(roi_align_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaFuncSetAttribute(roi_align_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                smem_set = smem;
-            }
+            set_dyn_smem((const void*)roi_align_bwd_kernel<1>, smem);
+            set_dyn_smem((const void*)roi_align_bwd_kernel<2>, smem);
             roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, nullptr);
             count_launch();
             int* order = nullptr;

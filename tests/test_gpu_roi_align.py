@@ -150,3 +150,43 @@ def test_full_size_linearity(cuda):
     lhs = float((fx.double() * g.double()).sum())
     rhs = float(sum((a.double() * b.double()).sum() for a, b in zip(xs, gx)))
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_pixel_major_large_patch_and_border(cuda, oracle):
+    """The pixel-major forward path (7x7, sampling_ratio 2, C % 256 == 0) on RoIs whose tap patch exceeds the
+    4096-pixel dedupe bitmap (long, diagonal: the per-row lists fall back to one pixel per tap), on tiny RoIs
+    (all 196 samples inside a few pixels: every pixel feeds many bins) and on RoIs hanging over the border."""
+    from rs_detection_b200 import core
+    rng = np.random.default_rng(11)
+    feat = rng.standard_normal((1, 256, 112, 120)).astype(np.float32)
+    rois = W.proposals(64, 21, canvas=480)
+    rois[0, 1:] = [240, 220, 430, 12, 0.78]      # ~108 x 3 px at 45 degrees: patch ~ 78 x 78 > 4096
+    rois[1, 1:] = [200, 200, 600, 40, -0.70]
+    rois[2, 1:] = [100, 100, 2.0, 1.0, 0.3]      # clamped to 1 x 1 feature pixel
+    rois[3, 1:] = [101.3, 57.9, 6.0, 9.0, 1.2]
+    rois[4, 1:] = [-30, 470, 200, 90, 0.5]       # mostly outside
+    rois[5, 1:] = [4000, 4000, 50, 50, 0.0]      # entirely outside: zeros
+    rois[6, 1:] = [478, 2, 64, 64, -1.5]
+    for version in (1, 0):
+        cfg = core.make_roi_cfg([feat.shape], [0.25], 7, 2, version)
+        got = core.roi_align_rotated_forward(cfg, [_t(feat)], _t(rois)).cpu().numpy()
+        want = oracle.roi_align_rotated_fwd(feat, rois, (7, 7), 0.25, 2, version)
+        _check(got, want, 1e-5, f"pixel-major v{version}")
+        assert np.abs(got[5]).max() == 0.0
+
+
+def test_fused_extractor_full_size_subset(cuda, oracle):
+    """BASELINE config 2 / config 1 sizes (1024^2 tile, C=256, K=4000 / K=2000): the real launch, checked against
+    the oracle on a random 200-RoI subset (RoIs are independent, so the oracle runs on the subset only)."""
+    from rs_detection_b200 import core
+    import bench as B
+    fs, rois, _, _ = B.tile_inputs(0)
+    shapes = [f.shape for f in fs]
+    cfg = core.make_roi_cfg(shapes, [1 / s for s in W.STRIDES], 7, 2, 1, B.EXTEND, 56.0)
+    xs = [_t(f) for f in fs]
+    for K in (4000, 2000):
+        r = rois[:K]
+        got = core.roi_align_rotated_forward(cfg, xs, _t(r))
+        sub = np.sort(np.random.default_rng(K).choice(K, 200, replace=False))
+        want, _ = oracle.oriented_extractor_fwd(fs, r[sub], list(W.STRIDES), extend_factor=B.EXTEND)
+        _check(got[torch.from_numpy(sub).cuda()].cpu().numpy(), want, 1e-5, f"full-size extractor K={K} (200-RoI subset)")
