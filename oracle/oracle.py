@@ -110,7 +110,7 @@ def box_iou_rotated_v1(boxes1, boxes2, sort_kind: int = 0, literal_quirk: bool =
 
 # ----------------------------------------------------------------------------- assignment
 def max_iou_assign(overlaps, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.5, match_low_quality=False,
-                   gt_max_assign_all=True, gt_labels=None, assigned_labels_filled=-1):
+                   gt_max_assign_all=True, gt_labels=None, assigned_labels_filled=0):
     """MaxIoUAssigner.assign_wrt_overlaps, python/jdet/models/boxes/assigner.py:111-170.
     overlaps (G, n) -> (assigned_gt_inds int32 (n,), max_overlaps (n,), labels or None).
     argmax ties resolve to the first maximum."""

@@ -30,7 +30,7 @@ class AssignResult:
 
 class MaxIoUAssigner:
     def __init__(self, pos_iou_thr, neg_iou_thr, min_pos_iou=.0, gt_max_assign_all=True, ignore_iof_thr=-1,
-                 ignore_wrt_candidates=True, match_low_quality=True, assigned_labels_filled=-1,
+                 ignore_wrt_candidates=True, match_low_quality=True, assigned_labels_filled=0,
                  iou_calculator=dict(type='BboxOverlaps2D_rotated_v1')):
         self.pos_iou_thr = pos_iou_thr
         self.neg_iou_thr = neg_iou_thr

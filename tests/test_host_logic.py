@@ -39,8 +39,10 @@ def test_multiclass_glue_semantics(oracle):
 def test_assign_semantics(oracle):
     ov = np.array([[0.6, 0.2, 0.0, 0.5], [0.7, 0.4, 0.0, 0.5]], np.float32)
     inds, mx, lab = oracle.max_iou_assign(ov, 0.5, 0.5, 0.5, False, gt_labels=np.array([3, 9]))
-    assert inds.tolist() == [2, 0, 0, 1] and lab.tolist() == [9, -1, -1, 3]  # argmax ties -> first gt
+    assert inds.tolist() == [2, 0, 0, 1] and lab.tolist() == [9, 0, 0, 3]  # argmax ties -> first gt; default fill 0 (assigner.py:52)
     np.testing.assert_allclose(mx, [0.7, 0.4, 0.0, 0.5])
+    _, _, lab = oracle.max_iou_assign(ov, 0.5, 0.5, 0.5, False, gt_labels=np.array([3, 9]), assigned_labels_filled=-1)
+    assert lab.tolist() == [9, -1, -1, 3]  # the Oriented R-CNN configs pass -1 (oriented_head.py:70)
     inds, _, _ = oracle.max_iou_assign(ov, 0.9, 0.3, 0.3, True)
     assert inds.tolist() == [2, -1, 0, -1]  # low-quality matching: each gt claims its best column, later gts win
 
