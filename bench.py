@@ -238,6 +238,74 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+MERGE_SCENES = (("scene_90k", 20000), ("scene_250k", 55000))   # (name, true objects in the 10k x 10k scene)
+
+
+def merge_component(dev, rank, world, dist, max_over_ranks, barrier):
+    """BASELINE config 5 under the driver: the same synthetic 10k x 10k scene on every rank (504 tiles at rates
+    0.5/1.0/1.5 emit ~4.5 near-duplicates per object), merged by `merge_sharded` -- classes over the ranks, per-class
+    thresholds, one all-gather of the survivors.  Device-timed (best of 5 after 2 warm-ups), max over ranks; rank 0
+    also checks the result against the unsharded single-launch engine call.  Returns a dict per scene size."""
+    import torch
+    from rs_detection_b200.jdet.data.devkits.result_merge import merge_detections, nms_threshold_1
+    from rs_detection_b200.merge import merge_sharded, plan_class_shards
+    thr = [nms_threshold_1[c] for c in W.FAIR1M_CLASSES]
+    out = {}
+    for name, nobj in MERGE_SCENES:
+        sc = W.merge_scene(num_objects=nobj, scene=10000, seed=1)
+        counts = np.bincount(sc["labels"], minlength=len(thr)).tolist()   # host knowledge: one before_nms file per class
+        p, s_, l = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (sc["polys"], sc["scores"], sc["labels"])]
+        run = lambda: merge_sharded(p, s_, l, class_thr=thr, class_counts=counts)
+        for _ in range(2):
+            res = run()
+        barrier()
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = run()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        ms = max_over_ranks(best)
+        entry = {"detections": int(p.shape[0]), "n_gpus": world, "ms": ms, "boxes_per_s": p.shape[0] / (ms * 1e-3),
+                 "collectives_per_call": 1 if world > 1 else 0, "owner": plan_class_shards(counts, world)}
+        if rank == 0:
+            kept = res.indices()
+            ref = merge_detections(p, s_, l, group_thresh=thr)   # all classes in one launch on this GPU
+            entry["kept"] = int(kept.numel())
+            entry["matches_unsharded"] = bool(sorted(ref.tolist()) == sorted(kept.tolist()))
+        out[name] = entry
+        del p, s_, l
+        torch.cuda.empty_cache()
+    return out
+
+
+def verify_tile0(tile_np, tile_dev, out_bufs, device_step, cfg, core):
+    """Compare what one more (untimed) device step leaves behind for tile 0 with the CPU oracle: the kept set of
+    `multiclass_nms_rotated` (4000 x 10 candidates, score_thr 0.001) must be identical, RoI features of 64 RoIs
+    must agree to 1e-5 (relative to the tensor's scale, the contract of tests/test_gpu_roi_align.py)."""
+    import torch
+    from oracle import oracle as O
+    feats, rois, boxes, scores = tile_np
+    device_step()
+    torch.cuda.synchronize()
+    got_feat = out_bufs[0]                                   # tile 0 writes slot 0 (tiles 0 and NSTREAMS share it: see below)
+    got_feat = core.roi_align_rotated_forward(cfg, tile_dev[0], tile_dev[1]) if TILES_PER_GPU > NSTREAMS else got_feat
+    sub = np.sort(np.random.default_rng(0).choice(K_ROIS, 64, replace=False))
+    want, _ = O.oriented_extractor_fwd(feats, rois[sub], list(W.STRIDES), extend_factor=EXTEND)
+    g = got_feat[torch.from_numpy(sub).to(got_feat.device)].cpu().numpy()
+    scale = float(np.abs(want).max())
+    roi_err = float(np.abs(g - want).max())
+    dets, labels, cnt = core.multiclass_nms_rotated(tile_dev[2], tile_dev[3], SCORE_THR, IOU_THR, MAX_NUM)
+    k = int(cnt.item())
+    wd, wl = O.multiclass_nms_rotated(boxes, scores, SCORE_THR, dict(iou_thr=IOU_THR), MAX_NUM)
+    nms_ok = bool(k == wd.shape[0] and np.array_equal(dets[:k].cpu().numpy(), wd) and np.array_equal(labels[:k].cpu().numpy(), wl))
+    return {"ok": bool(nms_ok and roi_err <= 1e-5 * 2 * scale), "nms_kept": k, "nms_kept_oracle": int(wd.shape[0]),
+            "nms_identical": nms_ok, "roi_max_abs_err": roi_err, "roi_scale": scale, "roi_rois_checked": int(len(sub)),
+            "checksum_out_tile0": float(got_feat.double().sum())}
+
+
 def run_ours(args, rank, world, local_rank):
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
@@ -476,6 +544,12 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = max_over_ranks(a.elapsed_time(b))
     e2e_val = world * TILES_PER_GPU * args.steps / (ms_e2e * 1e-3)
 
+    # ---- config 5 (full-scene merge NMS) at this N: class-sharded over the ranks, ONE all-gather (rs_detection_b200/merge.py)
+    merge_comp = merge_component(dev, rank, world, dist, max_over_ranks, barrier)
+
+    # ---- self-check of what the timed region produced (rank 0): tile 0 against the CPU oracle
+    verified = verify_tile0(tiles_np[0], tiles[0], out_bufs, device_step, cfg, core) if rank == 0 and not args.no_verify else None
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -504,8 +578,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h[0]),
                     "ms_per_step": ms_e2e / args.steps},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "verified": verified,
             "components": {
+                "merge": merge_comp,
                 "roi_extractor_fwd_ms_per_tile": ms_ext, "roi_extractor_fwd_rois_per_s": K_ROIS / (ms_ext * 1e-3),
                 "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel,
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
@@ -526,6 +601,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of tile 0 after the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.warmup_ref = min(args.warmup, 1)

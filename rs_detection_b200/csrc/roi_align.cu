@@ -233,6 +233,17 @@ __device__ __forceinline__ float4 ldg_cs_v4(const float* p) {
     asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// shared -> global bulk copy (cp.async.bulk, SASS UBLKCP) with an evict-first L2 policy: the output stream must
+// not push the feature pyramid out of L2.  Returns once the source has been read (shared memory may be reused
+// or the CTA may exit); global visibility follows at kernel end.
+__device__ __forceinline__ void bulk_store_evict_first(float* dst, const float* src_smem, unsigned bytes) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -539,84 +550,338 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
             }
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // the staged block IS the output block of this (roi, chunk): straight coalesced copy, streaming stores
+    // the staged block IS the output block of this (roi, chunk): one bulk copy shared -> global (TMA) when it is
+    // 16-byte aligned, else a coalesced copy with streaming stores
     float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;
     const int total = Qc * 4 * nbins;
-    if ((((size_t)roi * C + chunk0) * nbins & 3) == 0 && (total & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(s_stage);
-        for (int e = tid; e < total / 4; e += kRoiThreads) stg_cs_v4(dst + (size_t)e * 4, s4[e]);
+    if ((((size_t)roi * C + chunk0) * nbins & 3) == 0 && (total & 3) == 0 && (((size_t)out) & 15) == 0) {
+        if (tid == 0) bulk_store_evict_first(dst, s_stage, (unsigned)total * 4u);
     } else {
         for (int e = tid; e < total; e += kRoiThreads) __stcs(dst + e, s_stage[e]);
     }
 }
 
-// ---------------------------------------------------------------------------------- forward (pixel-major)
+// ---------------------------------------------------------------------------------- forward (row windows)
 // The default forward path for the Oriented R-CNN geometry (7x7 bins, 2x2 samples per bin, C % 256 == 0).
 //
-// What bounds the gather on B200 is not HBM but the path between L2 and the SM: the bin-major kernel above
-// pulls ~441 merged taps x 1 KB per RoI through L2 -> L1 -> registers although they cover only ~223 DISTINCT
-// feature pixels -- neighbouring bins share the one-pixel border of their bilinear footprints.  Here every
-// distinct pixel of a bin ROW is loaded once and applied to all bins of the row that use it:
-//   * one warp per bin row, lane = 2 channel quads (the warp covers 256 channels), 7 x 8 accumulators in
-//     registers;
-//   * per row a PIXEL LIST (distinct pixels in raster order of the RoI's patch) and a CONTRIBUTION STREAM
-//     {code = bin_col * 4 + slot, weight}: pixels are fetched in batches of four (8 x LDG.128 in flight per
-//     thread), then the batch's contributions are applied through a warp-uniform jump (`switch` on the code:
-//     the register index of an accumulator must be static, so the bin is resolved by control flow);
-//   * lists are built per warp without block barriers: bitmap of the touched patch pixels (shared-memory
-//     atomicOr), rank = prefix popcount, per-pixel contribution slots by shared-memory atomicAdd.  Pixels are
-//     visited in raster order and a (pixel, bin) pair occurs once (per-bin merge A2), so the summation order
-//     per output element -- and the result -- is deterministic.
-// L1 wavefronts per RoI: 304 x 8 for the gather instead of 441 x 8; rows r and r+1 run side by side, so the
-// border pixels they share hit in L1.
+// What bounds the gather on B200 is the path from L2 to the SM, not HBM: the bin-major kernel above pulls ~441
+// merged taps x 1 KB per RoI through it although they cover only ~223 DISTINCT feature pixels -- neighbouring bins
+// share the one-pixel border of their bilinear footprints.  Here a warp owns one bin ROW and walks it in WINDOWS of
+// two adjacent bins (w, w+1): every distinct pixel of the row is loaded once, in the first window that uses it,
+// and applied to both bins of the window with two weights; the accumulator of bin w+1 is carried into window w+1
+// as its first bin.  Accumulators are therefore statically indexed (no per-contribution control flow), a row needs
+// ~44 pixel loads instead of ~63, and a pixel feeding three or more consecutive bins (tiny RoIs) simply appears in
+// a later window again.  Rows r and r+1 run side by side in neighbouring warps, so their shared border hits in L1.
+//
+// List construction is warp-local and deterministic:
+//   A1  one thread per sample: 4 (pixel, weight) taps in the reference's float arithmetic, bounding box of the
+//       RoI's tap pixels;
+//   per row warp: bitmap of the row's pixels inside that box (shared-memory atomicOr) -> rank = prefix popcount =
+//       raster order; weight table wt[pixel][bin] accumulated in four rounds (round q = sample q of every bin, so a
+//       (pixel, bin) cell receives at most one add per round: plain read-modify-write, fixed order); per pixel the
+//       windows are chosen greedily over its bin mask and window lists are laid out with ballots (pixel order).
+// RoIs whose box exceeds the 4096-pixel bitmap (long diagonal ones) skip the dedupe: one entry per tap.
 constexpr int kPxRows = 7, kPxCols = 7;
-constexpr int kPxThreads = 32 * kPxRows;
-constexpr int kPxMaxPix = 16 * kPxCols;            // taps of one bin row before pixel dedupe
-constexpr int kPxPixPitch = 128;                   // pixel words per row (batch tail padded)
-constexpr int kPxCtrPitch = kPxMaxPix + kPxMaxPix / 4 + 4;  // contributions + one end marker per batch of 4 pixels
-constexpr int kPxBmWords = 128;                    // dedupe bitmap: patches of up to 4096 pixels (larger: no dedupe)
-constexpr int kPxEnd = 4 * kPxCols;                // contribution code that ends a batch
+constexpr int kPxBins = kPxRows * kPxCols;
+constexpr int kPxMaxTaps = 16 * kPxCols;             // taps of one bin row
+constexpr int kPxEntPitch = kPxMaxTaps + 3 * kPxCols + 3 + 8;  // entries per row: <= one per tap, windows 4-aligned, batch over-read -> 144
+constexpr int kPxBmWords = 128;                      // dedupe bitmap: boxes of up to 4096 pixels
+constexpr int kPxPixPad = 128;                       // per-pixel arrays (<= 112 pixels per row)
 
+struct alignas(16) PxLists {                         // what the gather reads: one RoI
+    unsigned pix[kPxRows][kPxEntPitch];              // pixel index (y * W + x) per entry
+    float wa[kPxRows][kPxEntPitch];                  // weight for the window's first bin
+    float wb[kPxRows][kPxEntPitch];                  // weight for the window's second bin
+    int wbeg[kPxRows][8], wcnt[kPxRows][8];
+};
+constexpr int kPxTapPitch = 20;                      // taps of a bin: 16 + 4 pad words (the rounds read bin * 20 + q * 4 + k: 28 banks)
+struct alignas(16) PxTaps {                          // A1 output: (y << 16 | x, weight) per tap, tap = bin * 20 + sample * 4 + k
+    int key[kPxBins * kPxTapPitch];
+    float w[kPxBins * kPxTapPitch];
+};
+struct alignas(16) PxRowScratch {                    // per-row build scratch
+    unsigned bm[kPxBmWords];
+    int wpre[kPxBmWords];
+    float wt[kPxMaxTaps * 8];                        // [pixel rank][bin column]
+    unsigned pid[kPxPixPad];                         // its pixel index
+    unsigned char rk[kPxPixPad];                     // pixel rank of every tap of the row
+};
+
+// windows chosen for a pixel feeding the bins in `m`: lowest uncovered bin w opens window (w, w+1)
+__device__ __forceinline__ unsigned px_windows(unsigned m) {
+    unsigned e = 0;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        if (m) { const int w = __ffs(m) - 1; e |= 1u << w; m &= ~(3u << w); }
+    }
+    return e;
+}
+
+__device__ __forceinline__ unsigned ws_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(unsigned long long* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWS_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WS_DONE_%=;\n\tbra WS_WAIT_%=;\n\tWS_DONE_%=:\n\t}"
+        ::"r"(ws_smem_u32(b)), "r"(parity) : "memory");
+}
+
+// A1 for sample s (= bin * 4 + q): the four bilinear taps of make_taps, kept as (x, y) keys; updates the caller's
+// bounding box of touched pixels.  (A clamped sample repeats a pixel, but the repeated tap then has weight exactly 0.)
+__device__ __forceinline__ void px_sample(const RoiGeom& g, int version, int H, int W, int s, PxTaps& T, int& x0, int& x1,
+                                          int& y0, int& y1) {
+    const int b = s >> 2, q = s & 3;
+    const int ph = b / kPxCols, pw = b - ph * kPxCols, iy = q >> 1, ix = q & 1;
+    float x, y;
+    sample_xy(g, version, ph, pw, iy, ix, x, y);
+    int kx[2] = {0, 0}, ky[2] = {0, 0};
+    float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
+    if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {
+        if (y < 0) y = 0;
+        if (x < 0) x = 0;
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+        const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
+        wy[0] = __fsub_rn(1.f, ly); wy[1] = ly; wx[0] = __fsub_rn(1.f, lx); wx[1] = lx;
+        kx[0] = xl; kx[1] = xh; ky[0] = yl; ky[1] = yh;
+        x0 = min(x0, xl); x1 = max(x1, xh); y0 = min(y0, yl); y1 = max(y1, yh);
+    }
+    int4 kk;
+    float4 ww;
+    kk.x = (ky[0] << 16) | kx[0]; kk.y = (ky[0] << 16) | kx[1]; kk.z = (ky[1] << 16) | kx[0]; kk.w = (ky[1] << 16) | kx[1];
+    ww.x = __fmul_rn(wy[0], wx[0]); ww.y = __fmul_rn(wy[0], wx[1]); ww.z = __fmul_rn(wy[1], wx[0]); ww.w = __fmul_rn(wy[1], wx[1]);
+    *reinterpret_cast<int4*>(&T.key[b * kPxTapPitch + q * 4]) = kk;
+    *reinterpret_cast<float4*>(&T.w[b * kPxTapPitch + q * 4]) = ww;
+}
+
+// One warp builds the window lists of bin row `row` (warp-local: only __syncwarp inside).
+__device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, PxLists& Lst, int row, int lane, int W,
+                                             const int* box) {
+    const int px0 = box[0], py0 = box[2];
+    const int pwid = box[1] - px0 + 1, phgt = box[3] - py0 + 1;
+    const bool dedupe = pwid > 0 && pwid * phgt <= 32 * kPxBmWords;
+    int key[4], loc[4], rank[4];
+    float wgt[4];
+    bool val[4];
+    // lane's taps t = lane + 32 i: bin column 2 i + (lane >> 4), sample (lane >> 2) & 3 (the same for all four)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int t = lane + 32 * i;
+        const bool in = t < kPxMaxTaps;
+        const int ti = (row * kPxCols + (t >> 4)) * kPxTapPitch + (t & 15);
+        key[i] = in ? T.key[ti] : 0;
+        wgt[i] = in ? T.w[ti] : 0.f;
+        val[i] = wgt[i] != 0.f;
+        // bit position of the pixel in the box bitmap.  Any fixed bijection gives a deterministic pixel order; this
+        // one sends raster neighbours to different words (word = index mod 128), because the taps of a bin row sit
+        // in a few adjacent pixel rows and a raster bitmap would serialise their atomicOr on the same words
+        const int ras = ((key[i] >> 16) - py0) * pwid + ((key[i] & 0xffff) - px0);
+        loc[i] = ((ras & (kPxBmWords - 1)) << 5) | (ras >> 7);
+        R.bm[lane + 32 * i] = 0u;
+    }
+    __syncwarp();
+    int npix;
+    if (dedupe) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (val[i]) atomicOr(&R.bm[loc[i] >> 5], 1u << (loc[i] & 31));
+        __syncwarp();
+        const uint4 m = *reinterpret_cast<const uint4*>(R.bm + 4 * lane);
+        const int c0 = __popc(m.x), c1 = __popc(m.y), c2 = __popc(m.z), c3 = __popc(m.w);
+        int x = c0 + c1 + c2 + c3;
+        const int sum = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        npix = __shfl_sync(0xffffffffu, x, 31);
+        const int ex = x - sum;
+        *reinterpret_cast<int4*>(R.wpre + 4 * lane) = make_int4(ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            rank[i] = val[i] ? R.wpre[loc[i] >> 5] + __popc(R.bm[loc[i] >> 5] & ((1u << (loc[i] & 31)) - 1u)) : 0;
+    } else {
+        int base = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, val[i]);
+            rank[i] = base + __popc(bal & ((1u << lane) - 1u));
+            base += __popc(bal);
+        }
+        npix = base;
+    }
+    // pixel index per rank; tap -> rank table for the rounds below
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (val[i]) {
+            R.pid[rank[i]] = (unsigned)((key[i] >> 16) * W + (key[i] & 0xffff));
+            R.rk[lane + 32 * i] = (unsigned char)rank[i];
+        }
+    // weight table wt[pixel][bin]: zero the live rows, then four rounds.  Round q adds sample q of every bin
+    // (lane = bin column * 4 + tap): a (pixel, bin) cell receives at most one add per round, so the plain
+    // read-modify-write is race-free and the summation order is fixed.
+    for (int e = lane; e < npix * 2; e += 32) reinterpret_cast<float4*>(R.wt)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    {
+        const int bc = lane >> 2, k = lane & 3;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (lane < 4 * kPxCols) {
+                const float wq = T.w[(row * kPxCols + bc) * kPxTapPitch + q * 4 + k];
+                if (wq != 0.f) R.wt[R.rk[bc * 16 + q * 4 + k] * 8 + bc] += wq;
+            }
+            __syncwarp();
+        }
+    }
+    // window lists: count, lay out (4-aligned starts), fill -- all in pixel (rank) order.  The bins a pixel feeds are
+    // the non-zero cells of its weight row (weights are positive, sums cannot cancel).
+    const int nchunk = (npix + 31) >> 5;
+    unsigned ew[4], pm[4];
+    float wv[4][8];
+    int cnt[kPxCols];
+#pragma unroll
+    for (int w = 0; w < kPxCols; w++) cnt[w] = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        ew[c] = 0u; pm[c] = 0u;
+        if (c < nchunk) {
+            const int r = c * 32 + lane;
+            const bool live = r < npix;
+            const float4 lo = live ? *reinterpret_cast<const float4*>(R.wt + r * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 hi = live ? *reinterpret_cast<const float4*>(R.wt + r * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[c][0] = lo.x; wv[c][1] = lo.y; wv[c][2] = lo.z; wv[c][3] = lo.w;
+            wv[c][4] = hi.x; wv[c][5] = hi.y; wv[c][6] = hi.z; wv[c][7] = 0.f;
+#pragma unroll
+            for (int w = 0; w < kPxCols; w++) pm[c] |= wv[c][w] != 0.f ? 1u << w : 0u;
+            ew[c] = px_windows(pm[c]);
+#pragma unroll
+            for (int w = 0; w < kPxCols; w++) cnt[w] += __popc(__ballot_sync(0xffffffffu, (ew[c] >> w) & 1u));
+        }
+    }
+    int beg[kPxCols];
+    {
+        int acc = 0;
+#pragma unroll
+        for (int w = 0; w < kPxCols; w++) { beg[w] = acc; acc += (cnt[w] + 3) & ~3; }
+    }
+    if (lane < kPxCols) {
+        int bsel = 0, csel = 0;
+#pragma unroll
+        for (int w = 0; w < kPxCols; w++) if (lane == w) { bsel = beg[w]; csel = cnt[w]; }
+        Lst.wbeg[row][lane] = bsel;
+        Lst.wcnt[row][lane] = csel;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (c < nchunk) {
+            const int r = c * 32 + lane;
+            const unsigned P = r < npix ? R.pid[r] : 0u;
+#pragma unroll
+            for (int w = 0; w < kPxCols; w++) {
+                const bool has = (ew[c] >> w) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, has);
+                if (has) {
+                    const int idx = beg[w] + __popc(bal & ((1u << lane) - 1u));
+                    Lst.pix[row][idx] = P;
+                    Lst.wa[row][idx] = wv[c][w];
+                    Lst.wb[row][idx] = ((pm[c] >> (w + 1)) & 1u) ? wv[c][w + 1] : 0.f;
+                }
+                beg[w] += __popc(bal);
+            }
+        }
+    }
+}
+
+// One warp gathers bin row `row`: windows (w, w+1), PB pixels (2 x PB LDG.128) in flight per thread; finished bins go
+// to the [c][bin] staging block (conflict-free component rotation, see rot4).  `feat` already points at this lane's
+// first channel quad of the RoI's image.
+template <int PB>
+__device__ __forceinline__ void px_gather_row(const PxLists& Lst, const float* __restrict__ feat, unsigned rowbytes,
+                                              float* __restrict__ stage, int row, int lane,
+                                              unsigned long long* stage_free = nullptr, unsigned free_parity = 0) {
+    const int oct = (lane >> 3) & 3;
+    float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), A1 = A0;
+    for (int w = 0; w < kPxCols; w++) {
+        float4 B0 = make_float4(0.f, 0.f, 0.f, 0.f), B1 = B0;
+        const int beg = Lst.wbeg[row][w], cnt = Lst.wcnt[row][w];
+        for (int e = 0; e < cnt; e += PB) {
+            unsigned pxs[PB];
+            float was[PB], wbs[PB];
+#pragma unroll
+            for (int h = 0; h < PB / 4; h++) {
+                const uint4 px = *reinterpret_cast<const uint4*>(&Lst.pix[row][beg + e + 4 * h]);
+                const float4 fa = *reinterpret_cast<const float4*>(&Lst.wa[row][beg + e + 4 * h]);
+                const float4 fb = *reinterpret_cast<const float4*>(&Lst.wb[row][beg + e + 4 * h]);
+                pxs[4 * h] = px.x; pxs[4 * h + 1] = px.y; pxs[4 * h + 2] = px.z; pxs[4 * h + 3] = px.w;
+                was[4 * h] = fa.x; was[4 * h + 1] = fa.y; was[4 * h + 2] = fa.z; was[4 * h + 3] = fa.w;
+                wbs[4 * h] = fb.x; wbs[4 * h + 1] = fb.y; wbs[4 * h + 2] = fb.z; wbs[4 * h + 3] = fb.w;
+            }
+            const int rem = cnt - e;
+            float4 v[PB][2];
+#pragma unroll
+            for (int k = 0; k < PB; k++)
+                if (k < rem) {
+                    unsigned long long ad;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad) : "r"(pxs[k]), "r"(rowbytes), "l"((unsigned long long)feat));
+                    v[k][0] = ldg_nc_v4(reinterpret_cast<const float*>(ad));
+                    v[k][1] = ldg_nc_v4(reinterpret_cast<const float*>(ad) + 128);
+                }
+#pragma unroll
+            for (int k = 0; k < PB; k++)
+                if (k < rem) {
+                    const float a = was[k], b = wbs[k];
+                    A0.x = fmaf(a, v[k][0].x, A0.x); A0.y = fmaf(a, v[k][0].y, A0.y); A0.z = fmaf(a, v[k][0].z, A0.z); A0.w = fmaf(a, v[k][0].w, A0.w);
+                    A1.x = fmaf(a, v[k][1].x, A1.x); A1.y = fmaf(a, v[k][1].y, A1.y); A1.z = fmaf(a, v[k][1].z, A1.z); A1.w = fmaf(a, v[k][1].w, A1.w);
+                    B0.x = fmaf(b, v[k][0].x, B0.x); B0.y = fmaf(b, v[k][0].y, B0.y); B0.z = fmaf(b, v[k][0].z, B0.z); B0.w = fmaf(b, v[k][0].w, B0.w);
+                    B1.x = fmaf(b, v[k][1].x, B1.x); B1.y = fmaf(b, v[k][1].y, B1.y); B1.z = fmaf(b, v[k][1].z, B1.z); B1.w = fmaf(b, v[k][1].w, B1.w);
+                }
+        }
+        if (w == 0 && stage_free) ws_mbar_wait(stage_free, free_parity);   // the previous block has left shared memory
+        const int b = row * kPxCols + w;       // bin (row, w) is complete
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            float4 r = u ? A1 : A0;
+            r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;      // /count, count = 4 samples (exact)
+            r = rot4(r, oct);
+            const int c0 = (lane + u * 32) * 4;
+            stage[(c0 + ((0 + oct) & 3)) * kPxBins + b] = r.x;
+            stage[(c0 + ((1 + oct) & 3)) * kPxBins + b] = r.y;
+            stage[(c0 + ((2 + oct) & 3)) * kPxBins + b] = r.z;
+            stage[(c0 + ((3 + oct) & 3)) * kPxBins + b] = r.w;
+        }
+        A0 = B0; A1 = B1;
+    }
+}
+
+// ---- one CTA per RoI (7 warps = 7 bin rows; build, barrier, gather, bulk store).  Kept for small calls and as the
+// A/B reference of the persistent kernel below.
 struct PxSmem {
-    unsigned pixw[kPxRows][kPxPixPitch];
-    int2 ctr[kPxRows][kPxCtrPitch];
-    int npix[8];
-    int box[4];                                    // x0, x1, y0, y1 of the RoI's tap pixels
-    union {
-        float stage[256 * kPxRows * kPxCols];      // [c][bin] = the RoI's output block
-        struct {
-            int key[kPxRows * kPxCols * 17];       // A1: (y << 16 | x) per tap, bin pitch 17
-            float w[kPxRows * kPxCols * 17];
-            int2 list[kPxRows * kPxCols * 17];     // A2: merged per-bin lists
-            int cnt[64];
-            unsigned bm[kPxRows][kPxBmWords];
-            int wpre[kPxRows][kPxBmWords];
-            int cntp[kPxRows][kPxPixPitch];
-        } b;
+    PxLists lists;
+    int box[4];                                      // x0, x1, y0, y1 of the RoI's tap pixels
+    union alignas(16) {
+        float stage[256 * kPxBins];                  // [c][bin] = the RoI's output block
+        struct { PxTaps taps; PxRowScratch row[kPxRows]; } b;
     } u;
 };
 
-#define RSDET_PX_FMA8(j, k)                                                                                         \
-    {                                                                                                                \
-        a[j][0].x = fmaf(wt, v[k][0].x, a[j][0].x); a[j][0].y = fmaf(wt, v[k][0].y, a[j][0].y);                      \
-        a[j][0].z = fmaf(wt, v[k][0].z, a[j][0].z); a[j][0].w = fmaf(wt, v[k][0].w, a[j][0].w);                      \
-        a[j][1].x = fmaf(wt, v[k][1].x, a[j][1].x); a[j][1].y = fmaf(wt, v[k][1].y, a[j][1].y);                      \
-        a[j][1].z = fmaf(wt, v[k][1].z, a[j][1].z); a[j][1].w = fmaf(wt, v[k][1].w, a[j][1].w);                      \
-    }
-#define RSDET_PX_CASE(j, k) case (j) * 4 + (k): RSDET_PX_FMA8(j, k) break;
-#define RSDET_PX_ROW(j) RSDET_PX_CASE(j, 0) RSDET_PX_CASE(j, 1) RSDET_PX_CASE(j, 2) RSDET_PX_CASE(j, 3)
-
-// blockDim = (32, 7): threadIdx.y is the warp = bin row, which the compiler then knows to be warp-uniform
-// (list addresses in uniform registers, plain branches in the contribution loop).
-__global__ void __block_size__((32, kPxRows, 1)) __maxnreg__(128)
+// blockDim = (32, 7): threadIdx.y is the warp = bin row and is known to be warp-uniform (list addresses live in
+// uniform registers, loop bounds are uniform branches).
+template <int PB>
+__global__ void __block_size__((32, kPxRows, 1)) __maxnreg__(PB == 8 ? 128 : 96)
 roi_align_fwd_px_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom* __restrict__ geoms, int K,
                         float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PxSmem& S = *reinterpret_cast<PxSmem*>(smem_raw);
     const int roi = order ? order[blockIdx.x] : blockIdx.x;
     const int lane = threadIdx.x, row = threadIdx.y, tid = row * 32 + lane;
-    constexpr int nbins = kPxRows * kPxCols;
     const int C = L.C;
     const int chunk0 = blockIdx.y * 256;
     const RoiGeom g = geoms[roi];
@@ -624,203 +889,127 @@ roi_align_fwd_px_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
 
     if (tid == 0) { S.box[0] = 0x7fffffff; S.box[1] = -1; S.box[2] = 0x7fffffff; S.box[3] = -1; }
     __syncthreads();
-    // A1: one thread per sample -> 4 (pixel key, weight) taps; bounding box of the touched pixels
     {
         int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
-        if (tid < nbins * 4) {
-            const int b = tid >> 2, q = tid & 3;
-            const int ph = b / kPxCols, pw = b - ph * kPxCols, iy = q >> 1, ix = q & 1;
-            float x, y;
-            sample_xy(g, L.version, ph, pw, iy, ix, x, y);
-            int kx[2] = {0, 0}, ky[2] = {0, 0};
-            float wx[2] = {0.f, 0.f}, wy[2] = {0.f, 0.f};
-            if (!(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W)) {   // make_taps, kept as (x, y) pairs
-                if (y < 0) y = 0;
-                if (x < 0) x = 0;
-                int yl = (int)y, xl = (int)x, yh, xh;
-                if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
-                if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-                const float ly = __fsub_rn(y, (float)yl), lx = __fsub_rn(x, (float)xl);
-                wy[0] = __fsub_rn(1.f, ly); wy[1] = ly; wx[0] = __fsub_rn(1.f, lx); wx[1] = lx;
-                kx[0] = xl; kx[1] = xh; ky[0] = yl; ky[1] = yh;
-                x0 = xl; x1 = xh; y0 = yl; y1 = yh;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                S.u.b.key[b * 17 + q * 4 + k] = (ky[k >> 1] << 16) | kx[k & 1];
-                S.u.b.w[b * 17 + q * 4 + k] = __fmul_rn(wy[k >> 1], wx[k & 1]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        }
+        if (tid < kPxBins * 4) px_sample(g, L.version, H, W, tid, S.u.b.taps, x0, x1, y0, y1);
+        x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);     // REDUX: off the LSU data pipe
+        y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
         if (lane == 0 && x1 >= 0) { atomicMin(&S.box[0], x0); atomicMax(&S.box[1], x1); atomicMin(&S.box[2], y0); atomicMax(&S.box[3], y1); }
     }
     __syncthreads();
-    // A2: per-bin merge, one lane per bin, 16 taps in registers (see build_tap_lists)
-    if (tid < nbins) {
-        const int b = tid;
-        int o[16];
-        float w[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) { o[j] = S.u.b.key[b * 17 + j]; w[j] = S.u.b.w[b * 17 + j]; }
-        int pos = 0;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            float acc = w[j];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (i <= j) continue;
-                const bool same = o[i] == o[j] && w[j] != 0.f;
-                acc += same ? w[i] : 0.f;
-                w[i] = same ? 0.f : w[i];
-            }
-            if (w[j] != 0.f) S.u.b.list[b * 17 + pos++] = make_int2(o[j], __float_as_int(acc));
-        }
-        S.u.b.cnt[b] = pos;
-    }
-    __syncthreads();
-    // G: this warp's row -> distinct pixels + contribution stream (warp-local from here on)
-    {
-        const int px0 = S.box[0], py0 = S.box[2];
-        const int pwid = S.box[1] - px0 + 1, phgt = S.box[3] - py0 + 1;
-        const bool dedupe = pwid > 0 && pwid * phgt <= 32 * kPxBmWords;
-        int key[4], code[4], loc[4], rank[4], pos[4];
-        bool val[4];
-        unsigned* bm = S.u.b.bm[row];
-        int* wpre = S.u.b.wpre[row];
-        int* cntp = S.u.b.cntp[row];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int t = lane + 32 * i, bc = t >> 4, j = t & 15;
-            const int b = row * kPxCols + bc;
-            val[i] = t < kPxMaxPix && j < S.u.b.cnt[min(b, nbins - 1)];
-            const int2 e = val[i] ? S.u.b.list[b * 17 + j] : make_int2(0, 0);
-            key[i] = e.x; code[i] = bc * 4; pos[i] = e.y;   // pos[] carries the weight bits until the slot is known
-            loc[i] = ((e.x >> 16) - py0) * pwid + ((e.x & 0xffff) - px0);
-            bm[lane + 32 * i] = 0u;
-            cntp[lane + 32 * i] = 0;
-        }
-        __syncwarp();
-        int npix;
-        if (dedupe) {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (val[i]) atomicOr(&bm[loc[i] >> 5], 1u << (loc[i] & 31));
-            __syncwarp();
-            const uint4 m = *reinterpret_cast<const uint4*>(bm + 4 * lane);
-            const int c0 = __popc(m.x), c1 = __popc(m.y), c2 = __popc(m.z), c3 = __popc(m.w);
-            int x = c0 + c1 + c2 + c3;
-            const int sum = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            npix = __shfl_sync(0xffffffffu, x, 31);
-            const int ex = x - sum;
-            *reinterpret_cast<int4*>(wpre + 4 * lane) = make_int4(ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                rank[i] = val[i] ? wpre[loc[i] >> 5] + __popc(bm[loc[i] >> 5] & ((1u << (loc[i] & 31)) - 1u)) : 0;
-        } else {
-            int base = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const unsigned bal = __ballot_sync(0xffffffffu, val[i]);
-                rank[i] = base + __popc(bal & ((1u << lane) - 1u));
-                base += __popc(bal);
-            }
-            npix = base;
-        }
-        // slot of every contribution inside its pixel, then the start of every pixel in the stream
-        int wbits[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { wbits[i] = pos[i]; pos[i] = val[i] ? atomicAdd(&cntp[rank[i]], 1) : 0; }
-        __syncwarp();
-        const int4 cc = *reinterpret_cast<const int4*>(cntp + 4 * lane);   // pixels 4*lane .. 4*lane+3 = batch `lane`
-        int x = cc.x + cc.y + cc.z + cc.w;
-        const int sum = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        const int ex = x - sum + lane;                                      // + one end marker per earlier batch
-        __syncwarp();                                                       // wpre is dead: reuse it for the pixel starts
-        *reinterpret_cast<int4*>(wpre + 4 * lane) = make_int4(ex, ex + cc.x, ex + cc.x + cc.y, ex + cc.x + cc.y + cc.z);
-        const int nbatch = (npix + 3) >> 2;
-        if (lane < nbatch) S.ctr[row][ex + sum] = make_int2(kPxEnd, 0);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (val[i]) {
-                S.ctr[row][wpre[rank[i]] + pos[i]] = make_int2(code[i] + (rank[i] & 3), wbits[i]);
-                if (pos[i] == 0) S.pixw[row][rank[i]] = (unsigned)((key[i] >> 16) * W + (key[i] & 0xffff));
-            }
-        __syncwarp();
-        if (lane < 4 && npix > 0 && npix + lane < 4 * nbatch) S.pixw[row][npix + lane] = S.pixw[row][npix - 1];
-        if (lane == 0) S.npix[row] = npix;
-    }
+    px_build_row(S.u.b.taps, S.u.b.row[row], S.lists, row, lane, W, S.box);
     __syncthreads();   // the build scratch becomes the staging block
-
-    // gather
-    float4 a[kPxCols][2];
-#pragma unroll
-    for (int j = 0; j < kPxCols; j++) a[j][0] = a[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + lane * 4;
-        const unsigned rowbytes = (unsigned)C * 4u;
-        const int npix = S.npix[row];
-        const unsigned* pw = S.pixw[row];
-        const int2* cp = S.ctr[row];
-        for (int p0 = 0; p0 < npix; p0 += 4) {
-            const uint4 px = *reinterpret_cast<const uint4*>(pw + p0);
-            float4 v[4][2];
-            {
-                unsigned long long ad[4];
-                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[0]) : "r"(px.x), "r"(rowbytes), "l"((unsigned long long)feat));
-                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[1]) : "r"(px.y), "r"(rowbytes), "l"((unsigned long long)feat));
-                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[2]) : "r"(px.z), "r"(rowbytes), "l"((unsigned long long)feat));
-                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(ad[3]) : "r"(px.w), "r"(rowbytes), "l"((unsigned long long)feat));
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    v[k][0] = ldg_nc_v4(reinterpret_cast<const float*>(ad[k]));
-                    v[k][1] = ldg_nc_v4(reinterpret_cast<const float*>(ad[k]) + 128);
-                }
-            }
-            bool more = true;
-            while (more) {
-                const int2 e = *cp++;
-                const float wt = __int_as_float(e.y);
-                switch (e.x) {
-                    RSDET_PX_ROW(0) RSDET_PX_ROW(1) RSDET_PX_ROW(2) RSDET_PX_ROW(3) RSDET_PX_ROW(4) RSDET_PX_ROW(5) RSDET_PX_ROW(6)
-                    default: more = false; break;
-                }
-            }
-        }
+    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + lane * 4;
+    px_gather_row<PB>(S.lists, feat, (unsigned)C * 4u, S.u.stage, row, lane);
+    // the staged block IS the RoI's output block: one bulk copy shared -> global through the async proxy (TMA),
+    // which keeps the 50 KB read-out and the stores off the LSU data pipe the gather is bound by
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        float* dst = out + ((size_t)roi * C + chunk0) * kPxBins;            // 256 * 49 floats: 16-byte aligned
+        bulk_store_evict_first(dst, S.u.stage, 256u * kPxBins * 4u);
     }
-    // stage [c][bin] (conflict-free component rotation, see rot4) and stream the block out
-    {
-        const int oct = (lane >> 3) & 3;
-#pragma unroll
-        for (int j = 0; j < kPxCols; j++) {
-            const int b = row * kPxCols + j;
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                float4 r = a[j][u];
-                r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;      // /count, count = 4 samples (exact)
-                r = rot4(r, oct);
-                const int c0 = (lane + u * 32) * 4;
-                S.u.stage[(c0 + ((0 + oct) & 3)) * nbins + b] = r.x;
-                S.u.stage[(c0 + ((1 + oct) & 3)) * nbins + b] = r.y;
-                S.u.stage[(c0 + ((2 + oct) & 3)) * nbins + b] = r.z;
-                S.u.stage[(c0 + ((3 + oct) & 3)) * nbins + b] = r.w;
-            }
-        }
+}
+
+// ---- persistent, warp-specialised form (the default).  Each CTA loops over RoIs i = blockIdx.x, + gridDim.x, ...
+// of the locality order with three roles that only meet at mbarriers:
+//   builders  (warps 0-3):  sampling grid + window lists of RoI i+1 into the other list buffer, while
+//   gatherers (warps 4-10): one warp per bin row stream RoI i's pixels (nothing but loads + FMAs + staging stores),
+//   storer    (warp 11):    hands the finished 50 KB block to the TMA (bulk copy shared -> global) and frees it.
+// Register budget is rebalanced with setmaxnreg (builders 64, gather group 88 per thread).  In the one-CTA-per-RoI
+// kernel above the list construction (~40 % of a CTA's life) overlaps other CTAs' gathers only by chance; here
+// the memory pipe of an SM always has its gather warps issuing.
+constexpr int kWsBuilders = 4, kWsGatherWarps = 8;   // gather group = 7 row warps + the storer
+constexpr int kWsWarps = kWsBuilders + kWsGatherWarps;
+constexpr int kWsRegsLaunch = 80, kWsRegsBuild = 64, kWsRegsGather = 88;  // 128*64 + 256*88 = 384*80
+
+struct WsSmem {
+    PxLists lists[2];
+    const float* feat[2];                            // image base of the RoI in buffer b (level, batch, chunk applied)
+    int box[4];
+    int pad_[2];
+    unsigned long long full[2], empty[2], stage_full, stage_free;   // mbarriers
+    PxTaps taps;
+    PxRowScratch row[kWsBuilders];
+    alignas(16) float stage[256 * kPxBins];
+};
+
+template <int PB>
+__global__ void __block_size__((32, kWsWarps, 1)) __maxnreg__(kWsRegsLaunch)
+roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom* __restrict__ geoms, int K,
+                        float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsSmem& S = *reinterpret_cast<WsSmem*>(smem_raw);
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int C = L.C;
+    const int chunk0 = blockIdx.y * 256;
+    if (warp == 0 && lane == 0) {
+        ws_mbar_init(&S.full[0], kWsBuilders); ws_mbar_init(&S.full[1], kWsBuilders);
+        ws_mbar_init(&S.empty[0], kPxRows); ws_mbar_init(&S.empty[1], kPxRows);
+        ws_mbar_init(&S.stage_full, kPxRows); ws_mbar_init(&S.stage_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * nbins;     // 256 * 49 floats: 16-byte aligned
-    const float4* s4 = reinterpret_cast<const float4*>(S.u.stage);
-#pragma unroll 2
-    for (int e = tid; e < 256 * nbins / 4; e += kPxThreads) stg_cs_v4(dst + (size_t)e * 4, s4[e]);
+    const int first = blockIdx.x, step = gridDim.x;
+
+    if (warp < kWsBuilders) {
+        // ------------------------------------------------------------------ builders
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsRegsBuild));
+        const int btid = warp * 32 + lane;
+        int it = 0;
+        for (int i = first; i < K; i += step, it++) {
+            const int buf = it & 1;
+            const int roi = order ? order[i] : i;
+            const RoiGeom g = geoms[roi];
+            const int H = L.H[g.level], W = L.W[g.level];
+            if (it >= 2) ws_mbar_wait(&S.empty[buf], ((it >> 1) - 1) & 1);   // the gatherers are done with this buffer
+            if (btid == 0) {
+                S.box[0] = 0x7fffffff; S.box[1] = -1; S.box[2] = 0x7fffffff; S.box[3] = -1;
+                S.feat[buf] = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWsBuilders * 32) : "memory");   // also: previous RoI's rows have read the taps
+            {
+                int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
+                for (int sidx = btid; sidx < kPxBins * 4; sidx += kWsBuilders * 32) px_sample(g, L.version, H, W, sidx, S.taps, x0, x1, y0, y1);
+                x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+                y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+                if (lane == 0 && x1 >= 0) { atomicMin(&S.box[0], x0); atomicMax(&S.box[1], x1); atomicMin(&S.box[2], y0); atomicMax(&S.box[3], y1); }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWsBuilders * 32) : "memory");
+            for (int row = warp; row < kPxRows; row += kWsBuilders) {
+                px_build_row(S.taps, S.row[warp], S.lists[buf], row, lane, W, S.box);
+                __syncwarp();
+            }
+            if (lane == 0) ws_mbar_arrive(&S.full[buf]);
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsRegsGather));
+        const int row = warp - kWsBuilders;
+        if (row < kPxRows) {
+            // -------------------------------------------------------------- gatherers
+            int it = 0;
+            for (int i = first; i < K; i += step, it++) {
+                const int buf = it & 1;
+                ws_mbar_wait(&S.full[buf], (it >> 1) & 1);
+                const float* __restrict__ feat = S.feat[buf] + lane * 4;
+                px_gather_row<PB>(S.lists[buf], feat, (unsigned)C * 4u, S.stage, row, lane, it >= 1 ? &S.stage_free : nullptr,
+                                  (unsigned)((it - 1) & 1));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { ws_mbar_arrive(&S.empty[buf]); ws_mbar_arrive(&S.stage_full); }
+            }
+        } else if (lane == 0) {
+            // -------------------------------------------------------------- storer
+            int it = 0;
+            for (int i = first; i < K; i += step, it++) {
+                ws_mbar_wait(&S.stage_full, it & 1);
+                const int roi = order ? order[i] : i;
+                float* dst = out + ((size_t)roi * C + chunk0) * kPxBins;
+                bulk_store_evict_first(dst, S.stage, 256u * kPxBins * 4u);   // returns once the block has been read
+                ws_mbar_arrive(&S.stage_free);
+            }
+        }
+    }
 }
 
 // cudaFuncSetAttribute is per device: remember what was set for each one (a process may drive several GPUs)
@@ -844,7 +1033,8 @@ static void set_dyn_smem(const void* func, size_t bytes) {
     cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// 0 = pixel-major (default), 1 = bin-major register path, 2 = TMA gather4.  Only builds made with
+// 0 = row windows, persistent warp-specialised (default), 1 = bin-major register path, 2 = TMA gather4,
+// 3 = row windows, one CTA per RoI.  Only builds made with
 // -DRSDET_TUNING (profiling / A-B measurements) read the environment; the shipped library always returns 0.
 static int roi_path_choice() {
 #ifdef RSDET_TUNING
@@ -1329,10 +1519,18 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
         count_launch();
     }
-    if (px_path_ok(cfg) && roi_path_choice() == 0) {
-        set_dyn_smem((const void*)roi_align_fwd_px_kernel, sizeof(PxSmem));
-        dim3 pgrid(num_rois, cfg->channels / 256), pblock(32, kPxRows, 1);
-        roi_align_fwd_px_kernel<<<pgrid, pblock, sizeof(PxSmem), st>>>(L, order, geoms, num_rois, out);
+    if (px_path_ok(cfg) && (roi_path_choice() == 0 || roi_path_choice() == 3)) {
+        const int chunks = cfg->channels / 256;
+        if (roi_path_choice() == 3) {   // one CTA per RoI
+            dim3 pgrid(num_rois, chunks), pblock(32, kPxRows, 1);
+            set_dyn_smem((const void*)roi_align_fwd_px_kernel<4>, sizeof(PxSmem));
+            roi_align_fwd_px_kernel<4><<<pgrid, pblock, sizeof(PxSmem), st>>>(L, order, geoms, num_rois, out);
+        } else {                        // persistent, warp-specialised: two CTAs per SM
+            const int ctas = num_rois < 2 * kNumSMs ? num_rois : 2 * kNumSMs;
+            dim3 pgrid(ctas, chunks), pblock(32, kWsWarps, 1);
+            set_dyn_smem((const void*)roi_align_fwd_ws_kernel<4>, sizeof(WsSmem));
+            roi_align_fwd_ws_kernel<4><<<pgrid, pblock, sizeof(WsSmem), st>>>(L, order, geoms, num_rois, out);
+        }
         count_launch();
         return cuda_status();
     }

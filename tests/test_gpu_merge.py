@@ -111,3 +111,26 @@ def test_merge_py_hbb_nms(cuda, oracle):
     b = np.concatenate([xy, xy + wh, W.distinct_scores(n, 8).astype(np.float64)[:, None]], 1)
     for thr in (0.625, 0.3):
         assert np.array_equal(nms(b, thr), oracle.hbb_nms(b, thr))
+
+
+def test_merge_sharded_single_rank_matches_unsharded(cuda, oracle):
+    """rs_detection_b200.merge.merge_sharded on one rank (no process group): same survivors as the single-launch
+    engine call, in the canonical (class, scene, score) order; no host synchronisation before `.indices()`."""
+    from rs_detection_b200.jdet.data.devkits.result_merge import merge_detections, nms_threshold_1
+    from rs_detection_b200.merge import merge_sharded
+    sc = W.merge_scene(num_objects=900, scene=4000, seed=12)
+    thr = [nms_threshold_1[c] for c in W.FAIR1M_CLASSES]
+    p, s, l = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (sc["polys"], sc["scores"], sc["labels"])]
+    counts = np.bincount(sc["labels"], minlength=10).tolist()
+    res = merge_sharded(p, s, l, class_thr=thr, class_counts=counts)
+    kept = res.indices().cpu().numpy()
+    want = merge_detections(p, s, l, group_thresh=thr).cpu().numpy()
+    assert sorted(kept.tolist()) == sorted(want.tolist()) and 0 < kept.size < s.numel()
+    lab, scr = sc["labels"][kept], sc["scores"][kept]
+    assert np.all(np.diff(lab) >= 0)
+    assert all(np.all(np.diff(scr[lab == c]) <= 0) for c in range(10))
+    # against the oracle, class by class
+    for c in (1, 2):
+        idx = np.nonzero(sc["labels"] == c)[0]
+        dets = np.concatenate([sc["polys"][idx], sc["scores"][idx, None]], 1)
+        assert [int(idx[k]) for k in oracle.py_cpu_nms_poly_fast(dets, thr[c])] == kept[lab == c].tolist()

@@ -126,3 +126,31 @@ def test_large_nms_properties(cuda):
     iou = core.box_iou_rotated(d[supp], d[keep], 0)
     higher = s[keep][None, :] > s[supp][:, None]
     assert bool(((iou > thr) & higher).any(1).all())                               # (c)
+
+
+@pytest.mark.parametrize("K,C,score_thr", [(4000, 10, 0.001), (2000, 15, 0.05)])
+def test_multiclass_nms_rotated_baseline_sizes(cuda, oracle, ref, K, C, score_thr):
+    """BASELINE config 2 (K=4000, 10 classes, score_thr 0.001: ~40k candidates, 63-block staged scan, pair queue near
+    capacity) and config 1 (K=2000, 15 classes, 0.05) -- the exact tiles bench.py times -- against the oracle, and
+    per class against the reference's own NMS source compiled for the host (oracle/_ref)."""
+    import bench as B
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    boxes = W.rotated_boxes(K, 500)                                   # = bench.tile_inputs(0) boxes for K = 4000
+    scores = W.class_scores(K, C, 0, logit_scale=1.0)
+    if K == B.K_ROIS and C == B.NUM_CLASSES:
+        _, _, b0, s0 = B.tile_inputs(0)
+        assert np.array_equal(b0, boxes) and np.array_equal(s0, scores)
+    wd, wl = oracle.multiclass_nms_rotated(boxes, scores, score_thr, dict(iou_thr=0.1), 2000)
+    gd, gl = multiclass_nms_rotated(_t(boxes), _t(scores), score_thr, dict(type='nms_rotated', iou_thr=0.1), 2000)
+    assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+    # per-class keep sets through the reference's CUDA-rule NMS source (the label gate of ml_nms_rotated = one NMS per class)
+    gd_all, gl_all = multiclass_nms_rotated(_t(boxes), _t(scores), score_thr, dict(type='nms_rotated', iou_thr=0.1), -1)
+    gl_all = gl_all.cpu().numpy()
+    total = 0
+    for c in range(C):
+        m = scores[:, c + 1] > np.float32(score_thr)
+        sc = scores[m, c + 1]
+        order = np.argsort(-sc.astype(np.float64), kind="stable").astype(np.int32)
+        total += int(ref.nms_keep(boxes[m], order, 0.1, 5, ge=False).sum())
+    assert total - 1 == gd_all.shape[0]      # max_num=-1 drops the last detection (nms_rotated.py:590-591)
+    print(f"K={K} C={C}: {int((scores[:, 1:] > score_thr).sum())} candidates -> {total} kept")

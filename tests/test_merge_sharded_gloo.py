@@ -1,7 +1,7 @@
 """N>1 path of the merge stage on CPU: world_size 2 over gloo.  The host logic under test (class-shard
-plan, padded all-gather of survivors, canonical ordering) is the product's; the per-shard NMS is
-injected and played by the CPU oracle here (on the GPU box the default is the CUDA engine, covered by
-tests/test_gpu_merge.py)."""
+plan, sync-free shard selection, the single fixed-capacity all-gather of survivors, canonical ordering) is the
+product's; the per-shard NMS is injected and played by the CPU oracle here (on the GPU box the default is the
+CUDA engine, covered by tests/test_gpu_merge.py)."""
 import os
 import socket
 
@@ -24,7 +24,9 @@ def _oracle_nms(polys, scores, groups, thr, group_thr):
         dets = np.concatenate([p[idx], s[idx, None]], 1)
         keep += [int(idx[k]) for k in O.py_cpu_nms_poly_fast(dets, t)]
     keep.sort(key=lambda i: -s[i])
-    return torch.tensor(keep, dtype=torch.int64)
+    out = torch.full((len(s),), 12345, dtype=torch.int64)        # garbage tail like the engine's fixed-size output
+    out[: len(keep)] = torch.tensor(keep, dtype=torch.int64)
+    return out, torch.tensor([len(keep)], dtype=torch.int32)
 
 
 def _worker(rank, world, port, q):
@@ -36,9 +38,21 @@ def _worker(rank, world, port, q):
     sc = W.merge_scene(num_objects=250, scene=2500, seed=6)
     thr = [nms_threshold_1[c] for c in W.FAIR1M_CLASSES]
     scene_ids = torch.from_numpy((np.arange(sc["scores"].size) % 2).astype(np.int64))  # two scenes in one call
-    kept = merge_sharded(torch.from_numpy(sc["polys"]), torch.from_numpy(sc["scores"]), torch.from_numpy(sc["labels"]),
-                         scene_ids, class_thr=thr, num_classes=10, nms_fn=_oracle_nms)
+    counts = np.bincount(sc["labels"], minlength=10).tolist()    # host knowledge in the pipeline (per-class files)
+    calls = []
+    real = dist.all_gather_into_tensor
+    dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    res = merge_sharded(torch.from_numpy(sc["polys"]), torch.from_numpy(sc["scores"]), torch.from_numpy(sc["labels"]),
+                        scene_ids, class_thr=thr, nms_fn=_oracle_nms, class_counts=counts, num_scenes=2)
+    dist.all_gather_into_tensor = real
+    assert len(calls) == 1, "the merge stage must use exactly one collective"
+    kept = res.indices()
+    assert int((res.padded >= 0).sum()) == int(res.count) == kept.numel()
     q.put((rank, kept.tolist()))
+    # without the host-side hints the result is the same (one histogram copy instead)
+    res2 = merge_sharded(torch.from_numpy(sc["polys"]), torch.from_numpy(sc["scores"]), torch.from_numpy(sc["labels"]),
+                         scene_ids, class_thr=thr, num_classes=10, nms_fn=_oracle_nms)
+    assert res2.indices().tolist() == kept.tolist()
     dist.barrier()
     dist.destroy_process_group()
 

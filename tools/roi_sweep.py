@@ -40,8 +40,12 @@ def run():
 
 
 ref = None
-for path in [int(p) for p in a.paths.split(",")]:
+for spec in a.paths.split(","):      # "<path>" or "<path>:<pixels per batch>" (row-window kernel: 4 or 8)
+    path, _, pxb = spec.partition(":")
+    path = int(path)
     os.environ["RSDET_ROI_PATH"] = str(path)
+    if pxb:
+        os.environ["RSDET_ROI_PXB"] = pxb
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -51,7 +55,7 @@ for path in [int(p) for p in a.paths.split(",")]:
         run()
     e1.record()
     torch.cuda.synchronize()
-    msg = f"path {path}: {e0.elapsed_time(e1) / (8 * a.reps) * 1000:.1f} us per 4000-RoI tile (geometry + order + gather kernels)"
+    msg = f"path {spec}: {e0.elapsed_time(e1) / (8 * a.reps) * 1000:.1f} us per 4000-RoI tile (geometry + order + gather kernels)"
     if a.check:
         o = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
         if ref is None:
