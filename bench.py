@@ -114,14 +114,14 @@ _REF_FEATS = None  # set before the worker pool forks, so the 89 MB pyramid is i
 def _ref_roi_chunk(args):
     from oracle import ref as R
     level, rois, scale = args
-    return R.roi_fwd(_REF_FEATS[level], rois, (7, 7), scale, 2, 1)
+    return R.roi_fwd(_REF_FEATS[level], rois, (7, 7), scale, 2, 1, fast=True)   # -O3 build: timing, not parity
 
 
 def _ref_nms_class(args):
     from oracle import ref as R
     boxes, scores, thr = args
     order = np.argsort(-scores.astype(np.float64), kind="stable").astype(np.int32)
-    return R.nms_keep(boxes, order, thr, 5, ge=False)  # the CUDA path's `>` rule
+    return R.nms_keep(boxes, order, thr, 5, ge=False, fast=True)  # the CUDA path's `>` rule; -O3 build: timing, not parity
 
 
 def reference_tile(nproc, inputs):
@@ -162,6 +162,11 @@ def run_reference(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
     nproc = os.cpu_count() or 1
+    # the worker processes are forked and terminated; load the reference libraries in the parent as well so that the
+    # driver's loaded-library record of this process shows what actually ran
+    for name in ("ref_roi_v1_fast", "ref_nms5_fast", "ref_roi_v1", "ref_nms5"):
+        if R.available(name):
+            R._lib(name)
     inputs = tile_inputs(0)
     args.steps = min(args.steps, 20)  # ~0.5 s per 1-tile step on 16 cores: keeps the arm within a minute
     for _ in range(args.warmup_ref):
@@ -174,7 +179,10 @@ def run_reference(args, rank, world):
     sample = f"1 tile per step (the GPU arm runs {TILES_PER_GPU}/GPU), {args.steps} steps, {nproc} worker processes"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "tiles_per_gpu": TILES_PER_GPU, "rois_per_tile": K_ROIS,
+                       "nms_candidates_per_tile": K_ROIS * NUM_CLASSES, "tiles_per_step_this_arm": 1,
+                       "build": "reference kernel source, g++ -O3 -march=x86-64-v3 (oracle/build_ref.py `_fast`)"},
             "cpu_baseline": {"value": v, "unit": "tiles/s", "cores": nproc, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -193,6 +193,10 @@ FLAVOURS = {
     "": ["-O2", "-ffp-contract=off"],
     # what nvcc does by default on the device (FMA contraction); used to size the 1e-6 band
     "_fma": ["-O2", "-mfma", "-ffp-contract=fast"],
+    # the TIMED CPU arm of bench.py (never used for parity): what Jittor's JIT would build, `-O3 -march=native`
+    # (SURVEY 8d).  The libraries are built in this container and run on the GPU box's host, so `native` is
+    # replaced by its portable equivalent x86-64-v3 (AVX2 + FMA + BMI2: every CPU that hosts a B200).
+    "_fast": ["-O3", "-march=x86-64-v3", "-ffp-contract=fast"],
 }
 
 

@@ -64,8 +64,16 @@ def box_iou(boxes1, boxes2, version=0, cudasort=False, fma=False):
     return out
 
 
-def nms_keep(dets, order, thr, box_len=5, ge=True, cudasort=False, fma=False):
-    name = f"ref_nms{box_len}" + ("_cudasort" if cudasort else "") + ("_fma" if fma else "")
+def _flavour(fma, fast):
+    """'' = parity build (-O2, no contraction); '_fma' sizes the 1e-6 band; '_fast' (-O3 -march=x86-64-v3) is the
+    timed CPU arm of bench.py and is never used for parity.  Falls back to the parity build if absent."""
+    return "_fast" if fast else ("_fma" if fma else "")
+
+
+def nms_keep(dets, order, thr, box_len=5, ge=True, cudasort=False, fma=False, fast=False):
+    name = f"ref_nms{box_len}" + ("_cudasort" if cudasort else "") + _flavour(fma, fast)
+    if fast and not available(name):
+        name = name[:-5]
     L = _lib(name)
     L.ref_nms_greedy.argtypes = [_pf, _pi, C.c_int, C.c_float, C.c_int, _pu8]
     d = _c32(dets).reshape(-1, box_len)
@@ -76,8 +84,11 @@ def nms_keep(dets, order, thr, box_len=5, ge=True, cudasort=False, fma=False):
     return keep.astype(bool)
 
 
-def roi_fwd(feat, rois, output_size, spatial_scale, sampling_ratio, version=1, fma=False):
-    L = _lib(f"ref_roi_v{version}" + ("_fma" if fma else ""))
+def roi_fwd(feat, rois, output_size, spatial_scale, sampling_ratio, version=1, fma=False, fast=False):
+    name = f"ref_roi_v{version}" + _flavour(fma, fast)
+    if fast and not available(name):
+        name = name[:-5]
+    L = _lib(name)
     L.ref_roi_fwd.argtypes = [_pf, _pf] + [C.c_int] * 4 + [C.c_float] + [C.c_int] * 3 + [_pf]
     feat, rois = _c32(feat), _c32(rois).reshape(-1, 6)
     N, Cc, H, W = feat.shape

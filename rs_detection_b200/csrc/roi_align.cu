@@ -45,7 +45,7 @@ struct LevelSet {
     int num_levels, batch, C;
     int PH, PW, sampling_ratio, version;
     float extend_w, extend_h, finest_scale;
-    int dbg_skip_main;  // profiling aid (RSDET_ROI_DBG_SKIP_MAIN=1): tap lists are built, then treated as empty
+    int dbg_skip_main;  // profiling aid (RSDET_ROI_DBG_SKIP_MAIN=1, RSDET_TUNING builds only): tap lists are built, then treated as empty
 };
 
 // ---------------------------------------------------------------------------------- transposes
@@ -586,9 +586,10 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
 constexpr int kPxRows = 7, kPxCols = 7;
 constexpr int kPxBins = kPxRows * kPxCols;
 constexpr int kPxMaxTaps = 16 * kPxCols;             // taps of one bin row
-constexpr int kPxEntPitch = kPxMaxTaps + 3 * kPxCols + 3 + 8;  // entries per row: <= one per tap, windows 4-aligned, batch over-read -> 144
+constexpr int kPxEntPitch = kPxMaxTaps + 3 * kPxCols + 3;  // entries per row: <= one per tap, window starts 4-aligned (batches of 4) -> 136
 constexpr int kPxBmWords = 128;                      // dedupe bitmap: boxes of up to 4096 pixels
-constexpr int kPxPixPad = 128;                       // per-pixel arrays (<= 112 pixels per row)
+constexpr int kPxPixPad = 128;                       // per-tap / per-pixel arrays (<= 112 taps per row)
+constexpr int kPxWtRows = 88;                        // distinct pixels per row handled by the shared-pixel lists (1 % of rows have more)
 
 struct alignas(16) PxLists {                         // what the gather reads: one RoI
     unsigned pix[kPxRows][kPxEntPitch];              // pixel index (y * W + x) per entry
@@ -604,7 +605,7 @@ struct alignas(16) PxTaps {                          // A1 output: (y << 16 | x,
 struct alignas(16) PxRowScratch {                    // per-row build scratch
     unsigned bm[kPxBmWords];
     int wpre[kPxBmWords];
-    float wt[kPxMaxTaps * 8];                        // [pixel rank][bin column]
+    float wt[kPxWtRows * 8];                         // [pixel rank][bin column]; rows with more distinct pixels go DIRECT
     unsigned pid[kPxPixPad];                         // its pixel index
     unsigned char rk[kPxPixPad];                     // pixel rank of every tap of the row
 };
@@ -626,12 +627,19 @@ __device__ __forceinline__ void ws_mbar_init(unsigned long long* b, unsigned cou
 __device__ __forceinline__ void ws_mbar_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void ws_mbar_wait(unsigned long long* b, unsigned parity) {
+__device__ __forceinline__ bool ws_mbar_try(unsigned long long* b, unsigned parity) {
+    unsigned ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tWS_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WS_DONE_%=;\n\tbra WS_WAIT_%=;\n\tWS_DONE_%=:\n\t}"
-        ::"r"(ws_smem_u32(b)), "r"(parity) : "memory");
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(ws_smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// `sleep_ns` > 0: back off between polls (a role that is far ahead must not burn the issue slots the others need)
+__device__ __forceinline__ void ws_mbar_wait(unsigned long long* b, unsigned parity, unsigned sleep_ns = 0) {
+    while (!ws_mbar_try(b, parity))
+        if (sleep_ns) __nanosleep(sleep_ns);
 }
 
 // A1 for sample s (= bin * 4 + q): the four bilinear taps of make_taps, kept as (x, y) keys; updates the caller's
@@ -689,7 +697,7 @@ __device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, P
         R.bm[lane + 32 * i] = 0u;
     }
     __syncwarp();
-    int npix;
+    int npix = kPxWtRows + 1;
     if (dedupe) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -708,15 +716,26 @@ __device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, P
 #pragma unroll
         for (int i = 0; i < 4; i++)
             rank[i] = val[i] ? R.wpre[loc[i] >> 5] + __popc(R.bm[loc[i] >> 5] & ((1u << (loc[i] & 31)) - 1u)) : 0;
-    } else {
-        int base = 0;
+    }
+    if (npix > kPxWtRows) {
+        // DIRECT mode -- the box exceeds the bitmap (long diagonal RoI) or the row touches more than 88 distinct
+        // pixels (large bins: little to share): one entry per tap, in window (bin, bin + 1) with the second weight 0
+        int acc = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const unsigned bal = __ballot_sync(0xffffffffu, val[i]);
-            rank[i] = base + __popc(bal & ((1u << lane) - 1u));
-            base += __popc(bal);
+        for (int w = 0; w < kPxCols; w++) {
+            const int i = w >> 1;                                     // taps of bin column w: slot i, lane half w & 1
+            const bool has = val[i] && (lane >> 4) == (w & 1);
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int idx = acc + __popc(bal & ((1u << lane) - 1u));
+                Lst.pix[row][idx] = (unsigned)((key[i] >> 16) * W + (key[i] & 0xffff));
+                Lst.wa[row][idx] = wgt[i];
+                Lst.wb[row][idx] = 0.f;
+            }
+            if (lane == 0) { Lst.wbeg[row][w] = acc; Lst.wcnt[row][w] = __popc(bal); }
+            acc += (__popc(bal) + 3) & ~3;
         }
-        npix = base;
+        return;
     }
     // pixel index per rank; tap -> rank table for the rounds below
 #pragma unroll
@@ -742,29 +761,27 @@ __device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, P
         }
     }
     // window lists: count, lay out (4-aligned starts), fill -- all in pixel (rank) order.  The bins a pixel feeds are
-    // the non-zero cells of its weight row (weights are positive, sums cannot cancel).
-    const int nchunk = (npix + 31) >> 5;
-    unsigned ew[4], pm[4];
-    float wv[4][8];
+    // the non-zero cells of its weight row (weights are positive, sums cannot cancel).  npix <= 88: three pixels per lane.
+    constexpr int kChunks = (kPxWtRows + 31) / 32;
+    unsigned ew[kChunks], pm[kChunks];
+    float wv[kChunks][8];
     int cnt[kPxCols];
 #pragma unroll
     for (int w = 0; w < kPxCols; w++) cnt[w] = 0;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        ew[c] = 0u; pm[c] = 0u;
-        if (c < nchunk) {
-            const int r = c * 32 + lane;
-            const bool live = r < npix;
-            const float4 lo = live ? *reinterpret_cast<const float4*>(R.wt + r * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 hi = live ? *reinterpret_cast<const float4*>(R.wt + r * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            wv[c][0] = lo.x; wv[c][1] = lo.y; wv[c][2] = lo.z; wv[c][3] = lo.w;
-            wv[c][4] = hi.x; wv[c][5] = hi.y; wv[c][6] = hi.z; wv[c][7] = 0.f;
+    for (int c = 0; c < kChunks; c++) {
+        const int r = c * 32 + lane;
+        const bool live = r < npix;
+        const float4 lo = live ? *reinterpret_cast<const float4*>(R.wt + r * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 hi = live ? *reinterpret_cast<const float4*>(R.wt + r * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[c][0] = lo.x; wv[c][1] = lo.y; wv[c][2] = lo.z; wv[c][3] = lo.w;
+        wv[c][4] = hi.x; wv[c][5] = hi.y; wv[c][6] = hi.z; wv[c][7] = 0.f;
+        pm[c] = 0u;
 #pragma unroll
-            for (int w = 0; w < kPxCols; w++) pm[c] |= wv[c][w] != 0.f ? 1u << w : 0u;
-            ew[c] = px_windows(pm[c]);
+        for (int w = 0; w < kPxCols; w++) pm[c] |= wv[c][w] != 0.f ? 1u << w : 0u;
+        ew[c] = px_windows(pm[c]);
 #pragma unroll
-            for (int w = 0; w < kPxCols; w++) cnt[w] += __popc(__ballot_sync(0xffffffffu, (ew[c] >> w) & 1u));
-        }
+        for (int w = 0; w < kPxCols; w++) cnt[w] += __popc(__ballot_sync(0xffffffffu, (ew[c] >> w) & 1u));
     }
     int beg[kPxCols];
     {
@@ -780,22 +797,20 @@ __device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, P
         Lst.wcnt[row][lane] = csel;
     }
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        if (c < nchunk) {
-            const int r = c * 32 + lane;
-            const unsigned P = r < npix ? R.pid[r] : 0u;
+    for (int c = 0; c < kChunks; c++) {
+        const int r = c * 32 + lane;
+        const unsigned P = r < npix ? R.pid[r] : 0u;
 #pragma unroll
-            for (int w = 0; w < kPxCols; w++) {
-                const bool has = (ew[c] >> w) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, has);
-                if (has) {
-                    const int idx = beg[w] + __popc(bal & ((1u << lane) - 1u));
-                    Lst.pix[row][idx] = P;
-                    Lst.wa[row][idx] = wv[c][w];
-                    Lst.wb[row][idx] = ((pm[c] >> (w + 1)) & 1u) ? wv[c][w + 1] : 0.f;
-                }
-                beg[w] += __popc(bal);
+        for (int w = 0; w < kPxCols; w++) {
+            const bool has = (ew[c] >> w) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int idx = beg[w] + __popc(bal & ((1u << lane) - 1u));
+                Lst.pix[row][idx] = P;
+                Lst.wa[row][idx] = wv[c][w];
+                Lst.wb[row][idx] = ((pm[c] >> (w + 1)) & 1u) ? wv[c][w + 1] : 0.f;
             }
+            beg[w] += __popc(bal);
         }
     }
 }
@@ -803,7 +818,7 @@ __device__ __forceinline__ void px_build_row(const PxTaps& T, PxRowScratch& R, P
 // One warp gathers bin row `row`: windows (w, w+1), PB pixels (2 x PB LDG.128) in flight per thread; finished bins go
 // to the [c][bin] staging block (conflict-free component rotation, see rot4).  `feat` already points at this lane's
 // first channel quad of the RoI's image.
-template <int PB>
+template <int PB>   // pixels per load batch; kPxEntPitch is sized for 4
 __device__ __forceinline__ void px_gather_row(const PxLists& Lst, const float* __restrict__ feat, unsigned rowbytes,
                                               float* __restrict__ stage, int row, int lane,
                                               unsigned long long* stage_free = nullptr, unsigned free_parity = 0) {
@@ -844,7 +859,7 @@ __device__ __forceinline__ void px_gather_row(const PxLists& Lst, const float* _
                     B1.x = fmaf(b, v[k][1].x, B1.x); B1.y = fmaf(b, v[k][1].y, B1.y); B1.z = fmaf(b, v[k][1].z, B1.z); B1.w = fmaf(b, v[k][1].w, B1.w);
                 }
         }
-        if (w == 0 && stage_free) ws_mbar_wait(stage_free, free_parity);   // the previous block has left shared memory
+        if (w == 0 && stage_free) ws_mbar_wait(stage_free, free_parity, 100);   // the previous block has left shared memory
         const int b = row * kPxCols + w;       // bin (row, w) is complete
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -860,6 +875,10 @@ __device__ __forceinline__ void px_gather_row(const PxLists& Lst, const float* _
         A0 = B0; A1 = B1;
     }
 }
+
+#ifdef RSDET_PROF
+__device__ unsigned long long* g_px_prof = nullptr;   // set through rsdet_tuning_set_prof (profiling builds only)
+#endif
 
 // ---- one CTA per RoI (7 warps = 7 bin rows; build, barrier, gather, bulk store).  Kept for small calls and as the
 // A/B reference of the persistent kernel below.
@@ -887,6 +906,9 @@ roi_align_fwd_px_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
     const RoiGeom g = geoms[roi];
     const int H = L.H[g.level], W = L.W[g.level];
 
+#ifdef RSDET_PROF
+    long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
+#endif
     if (tid == 0) { S.box[0] = 0x7fffffff; S.box[1] = -1; S.box[2] = 0x7fffffff; S.box[3] = -1; }
     __syncthreads();
     {
@@ -897,31 +919,54 @@ roi_align_fwd_px_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
         if (lane == 0 && x1 >= 0) { atomicMin(&S.box[0], x0); atomicMax(&S.box[1], x1); atomicMin(&S.box[2], y0); atomicMax(&S.box[3], y1); }
     }
     __syncthreads();
+#ifdef RSDET_PROF
+    tk1 = clock64();
+#endif
+    const float* __restrict__ feat_img = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0;
     px_build_row(S.u.b.taps, S.u.b.row[row], S.lists, row, lane, W, S.box);
+#ifdef RSDET_PROF
+    tk2 = clock64();
+#endif
     __syncthreads();   // the build scratch becomes the staging block
-    const float* __restrict__ feat = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0 + lane * 4;
-    px_gather_row<PB>(S.lists, feat, (unsigned)C * 4u, S.u.stage, row, lane);
+#ifdef RSDET_PROF
+    tk3 = clock64();
+#endif
+    px_gather_row<PB>(S.lists, feat_img + lane * 4, (unsigned)C * 4u, S.u.stage, row, lane);
+#ifdef RSDET_PROF
+    tk4 = clock64();
+#endif
     // the staged block IS the RoI's output block: one bulk copy shared -> global through the async proxy (TMA),
     // which keeps the 50 KB read-out and the stores off the LSU data pipe the gather is bound by
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+#ifdef RSDET_PROF
+    const long long tk5 = clock64();
+#endif
     if (tid == 0) {
         float* dst = out + ((size_t)roi * C + chunk0) * kPxBins;            // 256 * 49 floats: 16-byte aligned
         bulk_store_evict_first(dst, S.u.stage, 256u * kPxBins * 4u);
     }
+#ifdef RSDET_PROF
+    if (g_px_prof && lane == 0) {   // per-phase cycle sums over all row warps (tools/roi_sweep.py --prof)
+        atomicAdd(&g_px_prof[0], (unsigned long long)(tk1 - tk0)); atomicAdd(&g_px_prof[1], (unsigned long long)(tk2 - tk1));
+        atomicAdd(&g_px_prof[2], (unsigned long long)(tk3 - tk2)); atomicAdd(&g_px_prof[3], (unsigned long long)(tk4 - tk3));
+        atomicAdd(&g_px_prof[4], (unsigned long long)(tk5 - tk4)); atomicAdd(&g_px_prof[5], (unsigned long long)(clock64() - tk5));
+        atomicAdd(&g_px_prof[6], 1ull);
+    }
+#endif
 }
 
 // ---- persistent, warp-specialised form (the default).  Each CTA loops over RoIs i = blockIdx.x, + gridDim.x, ...
 // of the locality order with three roles that only meet at mbarriers:
-//   builders  (warps 0-3):  sampling grid + window lists of RoI i+1 into the other list buffer, while
-//   gatherers (warps 4-10): one warp per bin row stream RoI i's pixels (nothing but loads + FMAs + staging stores),
-//   storer    (warp 11):    hands the finished 50 KB block to the TMA (bulk copy shared -> global) and frees it.
-// Register budget is rebalanced with setmaxnreg (builders 64, gather group 88 per thread).  In the one-CTA-per-RoI
+//   builders  (warps 0-7):  sampling grid + window lists (one warp per bin row) of RoI i+1 into the other list buffer, while
+//   gatherers (warps 8-14): one warp per bin row stream RoI i's pixels (nothing but loads + FMAs + staging stores),
+//   storer    (warp 15):    hands the finished 50 KB block to the TMA (bulk copy shared -> global) and frees it.
+// Register budget is rebalanced with setmaxnreg (builders 48, gather group 80 per thread).  In the one-CTA-per-RoI
 // kernel above the list construction (~40 % of a CTA's life) overlaps other CTAs' gathers only by chance; here
 // the memory pipe of an SM always has its gather warps issuing.
-constexpr int kWsBuilders = 4, kWsGatherWarps = 8;   // gather group = 7 row warps + the storer
+constexpr int kWsBuilders = 8, kWsGatherWarps = 8;   // 7 row builders (+1 that only helps with the sampling grid); gather group = 7 row warps + the storer
 constexpr int kWsWarps = kWsBuilders + kWsGatherWarps;
-constexpr int kWsRegsLaunch = 80, kWsRegsBuild = 64, kWsRegsGather = 88;  // 128*64 + 256*88 = 384*80
+constexpr int kWsRegsLaunch = 64, kWsRegsBuild = 48, kWsRegsGather = 80;  // 256*48 + 256*80 = 512*64
 
 struct WsSmem {
     PxLists lists[2];
@@ -930,7 +975,7 @@ struct WsSmem {
     int pad_[2];
     unsigned long long full[2], empty[2], stage_full, stage_free;   // mbarriers
     PxTaps taps;
-    PxRowScratch row[kWsBuilders];
+    PxRowScratch row[kPxRows];
     alignas(16) float stage[256 * kPxBins];
 };
 
@@ -944,7 +989,7 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
     const int C = L.C;
     const int chunk0 = blockIdx.y * 256;
     if (warp == 0 && lane == 0) {
-        ws_mbar_init(&S.full[0], kWsBuilders); ws_mbar_init(&S.full[1], kWsBuilders);
+        ws_mbar_init(&S.full[0], kPxRows); ws_mbar_init(&S.full[1], kPxRows);
         ws_mbar_init(&S.empty[0], kPxRows); ws_mbar_init(&S.empty[1], kPxRows);
         ws_mbar_init(&S.stage_full, kPxRows); ws_mbar_init(&S.stage_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -962,10 +1007,11 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
             const int roi = order ? order[i] : i;
             const RoiGeom g = geoms[roi];
             const int H = L.H[g.level], W = L.W[g.level];
-            if (it >= 2) ws_mbar_wait(&S.empty[buf], ((it >> 1) - 1) & 1);   // the gatherers are done with this buffer
+            if (it >= 2) ws_mbar_wait(&S.empty[buf], ((it >> 1) - 1) & 1, 500);   // the gatherers are done with this buffer
+            const float* __restrict__ feat_img = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0;
             if (btid == 0) {
                 S.box[0] = 0x7fffffff; S.box[1] = -1; S.box[2] = 0x7fffffff; S.box[3] = -1;
-                S.feat[buf] = L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0;
+                S.feat[buf] = feat_img;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kWsBuilders * 32) : "memory");   // also: previous RoI's rows have read the taps
             {
@@ -976,11 +1022,11 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
                 if (lane == 0 && x1 >= 0) { atomicMin(&S.box[0], x0); atomicMax(&S.box[1], x1); atomicMin(&S.box[2], y0); atomicMax(&S.box[3], y1); }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kWsBuilders * 32) : "memory");
-            for (int row = warp; row < kPxRows; row += kWsBuilders) {
-                px_build_row(S.taps, S.row[warp], S.lists[buf], row, lane, W, S.box);
+            if (warp < kPxRows) {
+                px_build_row(S.taps, S.row[warp], S.lists[buf], warp, lane, W, S.box);
                 __syncwarp();
+                if (lane == 0) ws_mbar_arrive(&S.full[buf]);
             }
-            if (lane == 0) ws_mbar_arrive(&S.full[buf]);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsRegsGather));
@@ -990,7 +1036,7 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
             int it = 0;
             for (int i = first; i < K; i += step, it++) {
                 const int buf = it & 1;
-                ws_mbar_wait(&S.full[buf], (it >> 1) & 1);
+                ws_mbar_wait(&S.full[buf], (it >> 1) & 1, 100);
                 const float* __restrict__ feat = S.feat[buf] + lane * 4;
                 px_gather_row<PB>(S.lists[buf], feat, (unsigned)C * 4u, S.stage, row, lane, it >= 1 ? &S.stage_free : nullptr,
                                   (unsigned)((it - 1) & 1));
@@ -1002,7 +1048,7 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
             // -------------------------------------------------------------- storer
             int it = 0;
             for (int i = first; i < K; i += step, it++) {
-                ws_mbar_wait(&S.stage_full, it & 1);
+                ws_mbar_wait(&S.stage_full, it & 1, 200);
                 const int roi = order ? order[i] : i;
                 float* dst = out + ((size_t)roi * C + chunk0) * kPxBins;
                 bulk_store_evict_first(dst, S.stage, 256u * kPxBins * 4u);   // returns once the block has been read
@@ -1622,6 +1668,13 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
     }
     return cuda_status();
 }
+
+#ifdef RSDET_PROF
+// profiling builds only: device buffer of 8 counters filled by roi_align_fwd_px_kernel (per-phase cycle sums)
+extern "C" int rsdet_tuning_set_prof(unsigned long long* dev_counters) {
+    return (int)cudaMemcpyToSymbol(g_px_prof, &dev_counters, sizeof(dev_counters));
+}
+#endif
 
 extern "C" int rsdet_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
     if (!src || !dst || n < 1 || c < 1 || h < 1 || w < 1) return RSDET_EINVAL;

@@ -22,13 +22,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--paths", default="0,1")
 ap.add_argument("--check", action="store_true", help="compare every path's output with path 1 (bin-major)")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--prof", action="store_true", help="RSDET_TUNING builds: per-phase cycle sums of the one-CTA-per-RoI kernel")
+ap.add_argument("--tiles", type=int, default=8, help="distinct tiles cycled (1: the 89 MB pyramid stays L2-resident)")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
 shapes = W.fpn_shapes()
 cfg = core.make_roi_cfg(shapes, [1.0 / s for s in W.STRIDES], 7, 2, 1, B.EXTEND, 56.0, channels_last=True)
 tiles = []
-for t in range(8):
+for t in range(a.tiles):
     fs, r, b, s = B.tile_inputs(t)
     tiles.append(([core.nchw_to_nhwc(torch.from_numpy(f).to(dev)) for f in fs], torch.from_numpy(r).to(dev)))
 out = torch.empty((B.K_ROIS, W.CHANNELS, 7, 7), device=dev)
@@ -39,13 +41,22 @@ def run():
         core.roi_align_rotated_forward(cfg, f, r, out=out)
 
 
+prof = None
+if a.prof:
+    import ctypes
+    from rs_detection_b200 import _lib
+    L = _lib.load()
+    prof = torch.zeros(8, dtype=torch.int64, device=dev)
+    fn = ctypes.CDLL(_lib.LIB_PATH if hasattr(_lib, "LIB_PATH") else os.path.join(ROOT, "rs_detection_b200", "librsdet.so")).rsdet_tuning_set_prof
+    fn.argtypes = [ctypes.c_void_p]
+    assert fn(prof.data_ptr()) == 0
+
 ref = None
-for spec in a.paths.split(","):      # "<path>" or "<path>:<pixels per batch>" (row-window kernel: 4 or 8)
-    path, _, pxb = spec.partition(":")
+for spec in a.paths.split(","):      # "<path>" or "<path>:<prefetch 0/1>" (row-window kernels)
+    path, _, pf = spec.partition(":")
     path = int(path)
     os.environ["RSDET_ROI_PATH"] = str(path)
-    if pxb:
-        os.environ["RSDET_ROI_PXB"] = pxb
+    os.environ["RSDET_ROI_PF"] = pf or "0"
     for _ in range(3):
         run()
     torch.cuda.synchronize()
@@ -55,7 +66,7 @@ for spec in a.paths.split(","):      # "<path>" or "<path>:<pixels per batch>" (
         run()
     e1.record()
     torch.cuda.synchronize()
-    msg = f"path {spec}: {e0.elapsed_time(e1) / (8 * a.reps) * 1000:.1f} us per 4000-RoI tile (geometry + order + gather kernels)"
+    msg = f"path {spec}: {e0.elapsed_time(e1) / (a.tiles * a.reps) * 1000:.1f} us per 4000-RoI tile (geometry + order + gather kernels)"
     if a.check:
         o = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
         if ref is None:
@@ -63,3 +74,11 @@ for spec in a.paths.split(","):      # "<path>" or "<path>:<pixels per batch>" (
             ref = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
         msg += f"; max |diff| vs bin-major {float((o - ref).abs().max()):.3g} (scale {float(ref.abs().max()):.3g})"
     print(msg, flush=True)
+    if prof is not None and path == 3:
+        prof.zero_()
+        run()
+        torch.cuda.synchronize()
+        c = prof.cpu().numpy().astype(float)
+        n = max(c[6], 1.0)
+        names = ["A1 + barriers", "row build", "wait at build barrier", "gather", "wait at final barrier", "bulk store (tid 0 waits)"]
+        print("    per row-warp cycles: " + ", ".join(f"{nm} {c[i] / n:.0f}" for i, nm in enumerate(names)) + f" (total {c[:6].sum() / n:.0f}, {n:.0f} warps)")
