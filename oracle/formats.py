@@ -49,7 +49,7 @@ def write_before_nms(results, save_path, classes):
             f.write(''.join(lines))
 
 
-def mergesingle(dstpath, fullname, nms_threshold_type=0, nms="poly"):
+def mergesingle(dstpath, fullname, nms_threshold_type=0, nms="poly", stable_ties=False):
     """nms = "poly": py_cpu_nms_poly_fast (mergebypoly); "rec": py_cpu_nms on 4-coordinate rows (mergebyrec :273-283)."""
     name = os.path.basename(os.path.splitext(fullname)[0])
     by_scene = {}
@@ -68,13 +68,13 @@ def mergesingle(dstpath, fullname, nms_threshold_type=0, nms="poly"):
     os.makedirs(dstpath, exist_ok=True)
     with open(os.path.join(dstpath, name + '.txt'), 'w') as out:
         for scene, dets in by_scene.items():
-            fn = O.py_cpu_nms_poly_fast if nms == "poly" else O.py_cpu_nms
-            for k in fn(np.array(dets), thr):
+            keep = O.py_cpu_nms_poly_fast(np.array(dets), thr, stable_ties) if nms == "poly" else O.py_cpu_nms(np.array(dets), thr)
+            for k in keep:
                 d = dets[k]
                 out.write(scene + ' ' + str(d[-1]) + ' ' + ' '.join(str(v) for v in d[:-1]) + '\n')
 
 
-def merge_file(src_file, dst_path, nms_thr=0.1):
+def merge_file(src_file, dst_path, nms_thr=0.1, stable_ties=False):
     os.makedirs(dst_path, exist_ok=True)
     by_scene = {}
     with open(src_file) as f:
@@ -85,7 +85,7 @@ def merge_file(src_file, dst_path, nms_thr=0.1):
     with open(os.path.join(dst_path, os.path.split(src_file)[-1]), 'w') as out:
         for scene, dets in by_scene.items():
             arr = np.array(dets)
-            for d in arr[O.py_cpu_nms_poly_fast(arr, nms_thr)].tolist():
+            for d in arr[O.py_cpu_nms_poly_fast(arr, nms_thr, stable_ties)].tolist():
                 out.write(scene + ' ' + str(d[-1]) + ' ' + ' '.join(str(v) for v in d[:-1]) + '\n')
 
 

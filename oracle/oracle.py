@@ -357,7 +357,7 @@ def score_order(scores, stable_ties=False):
     """`scores.argsort()[::-1]` as the reference's merge paths write it.  numpy's default argsort is not stable
     (and since 2.0 vectorised), so the order of EQUAL scores is an artefact of the numpy build; `stable_ties`
     gives the well-defined variant `argsort(kind='stable')[::-1]` (higher index first), which is the device
-    engine's tie rule for the float64 merge kinds and what numpy itself does for n <= 16."""
+    engine's tie rule for the float64 merge kinds."""
     s = np.asarray(scores)
     return np.ascontiguousarray((s.argsort(kind="stable") if stable_ties else s.argsort())[::-1], np.int32)
 

@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -133,6 +134,16 @@ class NmsResult:
     def score_idx(self) -> torch.Tensor:
         return self._score[: self.count]
 
+    @property
+    def score_idx_padded(self) -> torch.Tensor:
+        """(n,) kept indices in descending score order followed by an undefined tail; no synchronisation"""
+        return self._score
+
+    @property
+    def num_keep(self) -> torch.Tensor:
+        """(1,) int32 device counter; no synchronisation"""
+        return self._num
+
 
 def nms(kind: int, dets: torch.Tensor, scores: torch.Tensor, thr: float, labels: Optional[torch.Tensor] = None,
         thr_per_label: Optional[torch.Tensor] = None, want_mask=True, want_sorted=True, want_score=False,
@@ -159,6 +170,49 @@ def nms(kind: int, dets: torch.Tensor, scores: torch.Tensor, thr: float, labels:
     check(L.rsdet_nms(kind, ptr(d), ptr(s), ptr(lab), n, float(thr), ptr(tpl), 0 if tpl is None else tpl.numel(), ptr(mask),
                       ptr(sidx), ptr(cidx), ptr(num), ptr(ws), ws.numel(), stream_ptr()), "nms")
     return NmsResult(n, mask, sidx, cidx, num)
+
+
+MAX_NMS_ROWS = 1 << 18        # engine limit per call (include/rsdet.h)
+
+
+def nms_grouped(kind: int, dets: torch.Tensor, scores: torch.Tensor, group_ids, thr: float,
+                thr_per_label: Optional[torch.Tensor] = None, max_rows: int = 1 << 17, ws_tag: str = "merge") -> np.ndarray:
+    """Greedy NMS inside every group for ANY number of rows: `group_ids` (host int array, one id per row; a group is a
+    (file, scene) pair in the merge stage) are independent NMS problems, so when the rows exceed what one engine call
+    takes (n <= 2^18, and a dense-fallback workspace that grows with n^2/8 bytes) they are split BY GROUP into several
+    calls of at most `max_rows` rows each (a group larger than that goes alone).  A full FAIR1M / DOTA `before_nms`
+    dump at a low score threshold has more than 2^18 rows; the reference (one NMS per file and scene) has no such limit.
+    Returns the kept ORIGINAL row indices (numpy int64); rows of one group come out in descending score order."""
+    g = np.ascontiguousarray(np.asarray(group_ids), dtype=np.int64)
+    n = g.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int64)
+
+    def one(idx_t, lab_np):
+        d = dets if idx_t is None else dets[idx_t]
+        sc = scores if idx_t is None else scores[idx_t]
+        res = nms(kind, d, sc, thr, labels=torch.from_numpy(lab_np.astype(np.int32)).to(dets.device), thr_per_label=thr_per_label,
+                  want_mask=False, want_sorted=False, want_score=True, ws_tag=ws_tag)
+        return res.score_idx.cpu().numpy()
+
+    if n <= max_rows:
+        return one(None, g)
+    perm = np.argsort(g, kind="stable")               # rows by group, original order inside a group (tie rule intact)
+    gs = g[perm]
+    starts = np.flatnonzero(np.r_[True, gs[1:] != gs[:-1]])
+    ends = np.r_[starts[1:], n]
+    kept, lo = [], 0
+    while lo < len(starts):
+        hi = lo + 1
+        while hi < len(starts) and ends[hi] - starts[lo] <= max_rows:
+            hi += 1
+        rows = perm[starts[lo]:ends[hi - 1]]
+        if rows.shape[0] > MAX_NMS_ROWS:
+            raise RuntimeError(f"merge NMS: one group holds {rows.shape[0]} rows; the engine takes at most {MAX_NMS_ROWS} per group")
+        k = one(torch.from_numpy(rows).to(dets.device), g[rows])
+        kept.append(rows[k])
+        lo = hi
+    return np.concatenate(kept)
 
 
 def multiclass_nms_rotated(multi_bboxes: torch.Tensor, multi_scores: torch.Tensor, score_thr: float, iou_thr: float,

@@ -62,9 +62,7 @@ struct TransposeJob {
 // source's contiguous dimension, scatters it into a padded shared tile, and writes a float4 along the
 // destination's contiguous dimension.  Falls back to scalar accesses at ragged edges / unaligned bases.
 template <bool TO_NHWC>
-__global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
-    __shared__ float tile[64][65];
-    int t = blockIdx.x;
+__device__ __forceinline__ void transpose_tile(const TransposeJob& job, int t, float (*tile)[65]) {
     int l = 0;
     while (l + 1 < job.num_levels && t >= job.tile_begin[l + 1]) l++;
     t -= job.tile_begin[l];
@@ -115,23 +113,22 @@ __global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
     }
 }
 
-static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
-                            int C, cudaStream_t st) {
-    TransposeJob job;
-    job.num_levels = L; job.N = N; job.C = C;
-    int total = 0;
-    for (int l = 0; l < L; l++) {
-        job.src[l] = src[l]; job.dst[l] = dst[l]; job.HW[l] = H[l] * W[l];
-        job.tile_begin[l] = total;
-        total += N * ceil_div(job.HW[l], 64) * ceil_div(C, 64);
-    }
-    job.tile_begin[L] = total;
-    if (total == 0) return RSDET_OK;
-    if (to_nhwc) transpose_kernel<true><<<total, 256, 0, st>>>(job);
-    else transpose_kernel<false><<<total, 256, 0, st>>>(job);
-    count_launch();
-    return cuda_status();
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
+    __shared__ float tile[64][65];
+    transpose_tile<TO_NHWC>(job, blockIdx.x, tile);
 }
+
+struct LevelSet;
+struct RoiGeom;
+struct PrepArgs {                 // order block riding along with the NCHW->NHWC transpose (see roi_order_block)
+    const float* rois;
+    int K;
+    const RoiGeom* geoms;
+    int* order;
+};
+static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
+                            int C, cudaStream_t st, const PrepArgs* prep = nullptr);
 
 // ---------------------------------------------------------------------------------- geometry
 struct RoiGeom {
@@ -320,6 +317,102 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
         int lvl;
         int bkt = bucket_of(i, lvl);
         order[atomicAdd(&s_hist[bkt], 1)] = i;
+    }
+}
+
+// The locality order of a call (what roi_order_kernel does) as ONE block of any size, so that for NCHW callers it can
+// ride along as an extra block of the NCHW->NHWC transpose: the order kernel is a 7.8 us single-CTA latency chain in
+// front of every gather, the transpose of a 1024^2 pyramid keeps the other SMs busy for 30 us anyway.  (Doing the
+// geometry in the same block as well was measured and dropped: sin/cos/log2 of 4000 RoIs on one SM take longer than
+// the two launches they replace.)  geoms[] must have been written by roi_geometry_kernel.  s_hist: kBuckets ints.
+constexpr int kPrepMaxRois = 16384;
+template <int THREADS>
+__device__ __forceinline__ void roi_order_block(const float* __restrict__ rois, int K, const RoiGeom* __restrict__ geoms,
+                                                int* __restrict__ order, int* s_hist, int* s_warp) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBuckets; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    auto bucket_of = [&](const float* r, int lvl) {
+        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
+        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
+        if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
+        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+    };
+    for (int i = tid; i < K; i += THREADS) {
+        const float* r = rois + (size_t)i * 6;
+        atomicAdd(&s_hist[bucket_of(r, geoms[i].level)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of kBuckets counters, kBuckets / THREADS consecutive ones per thread
+    constexpr int PER = kBuckets / THREADS;
+    int a[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { a[k] = s_hist[PER * tid + k]; sum += a[k]; }
+    int x = sum;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int v = lane < THREADS / 32 ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    int excl = (w ? s_warp[w - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { s_hist[PER * tid + k] = excl; excl += a[k]; }
+    __syncthreads();
+    for (int i = tid; i < K; i += THREADS) {
+        const float* r = rois + (size_t)i * 6;
+        order[atomicAdd(&s_hist[bucket_of(r, geoms[i].level)], 1)] = i;
+    }
+}
+
+// NCHW callers: the pyramid transpose with the order block riding along as block 0
+__global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, const float* __restrict__ rois, int K,
+                                                             const RoiGeom* __restrict__ geoms, int* __restrict__ order) {
+    __shared__ float tile[64][65];
+    static_assert(sizeof(float) * 64 * 65 >= sizeof(int) * (kBuckets + 32), "the prep block borrows the transpose tile");
+    if (blockIdx.x == 0) {
+        int* s_hist = reinterpret_cast<int*>(&tile[0][0]);
+        roi_order_block<256>(rois, K, geoms, order, s_hist, s_hist + kBuckets);
+        return;
+    }
+    transpose_tile<true>(job, blockIdx.x - 1, tile);
+}
+
+static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
+                            int C, cudaStream_t st, const PrepArgs* prep) {
+    TransposeJob job;
+    job.num_levels = L; job.N = N; job.C = C;
+    int total = 0;
+    for (int l = 0; l < L; l++) {
+        job.src[l] = src[l]; job.dst[l] = dst[l]; job.HW[l] = H[l] * W[l];
+        job.tile_begin[l] = total;
+        total += N * ceil_div(job.HW[l], 64) * ceil_div(C, 64);
+    }
+    job.tile_begin[L] = total;
+    if (prep && to_nhwc) {
+        transpose_prep_kernel<<<total + 1, 256, 0, st>>>(job, prep->rois, prep->K, prep->geoms, prep->order);
+        count_launch();
+        return cuda_status();
+    }
+    if (total == 0) return RSDET_OK;
+    if (to_nhwc) transpose_kernel<true><<<total, 256, 0, st>>>(job);
+    else transpose_kernel<false><<<total, 256, 0, st>>>(job);
+    count_launch();
+    return cuda_status();
+}
+
+// geometry (+ locality order for calls of >= 256 RoIs) of a call
+static void launch_prep(const LevelSet& L, const float* rois, int K, RoiGeom* geoms, int* order, int32_t* levels_out, cudaStream_t st,
+                        bool order_rides_with_transpose = false) {
+    roi_geometry_kernel<<<ceil_div(K, 128), 128, 0, st>>>(L, rois, K, geoms, levels_out);
+    count_launch();
+    if (order && !order_rides_with_transpose) {
+        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, K, order, nullptr);
+        count_launch();
     }
 }
 
@@ -563,6 +656,7 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     }
 }
 
+#ifdef RSDET_TUNING   // measured alternatives of the forward gather (A/B builds only, see roi_path_choice)
 // ---------------------------------------------------------------------------------- forward (row windows)
 // The default forward path for the Oriented R-CNN geometry (7x7 bins, 2x2 samples per bin, C % 256 == 0).
 //
@@ -1058,6 +1152,8 @@ roi_align_fwd_ws_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom
     }
 }
 
+#endif  // RSDET_TUNING (row-window kernels)
+
 // cudaFuncSetAttribute is per device: remember what was set for each one (a process may drive several GPUs)
 static void set_dyn_smem(const void* func, size_t bytes) {
     struct Slot { const void* f; size_t b; };
@@ -1079,22 +1175,24 @@ static void set_dyn_smem(const void* func, size_t bytes) {
     cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-// 0 = row windows, persistent warp-specialised (default), 1 = bin-major register path, 2 = TMA gather4,
-// 3 = row windows, one CTA per RoI.  Only builds made with
-// -DRSDET_TUNING (profiling / A-B measurements) read the environment; the shipped library always returns 0.
+// Forward path: 1 = bin-major register kernel + TMA bulk store (the default and the only path of the shipped library:
+// fastest measured, profiles/README.md "round 2"), and -- in RSDET_TUNING builds only, selected through RSDET_ROI_PATH
+// for A/B measurements -- 0 = row windows, persistent warp-specialised, 3 = row windows, one CTA per RoI, 2 = TMA gather4.
 static int roi_path_choice() {
 #ifdef RSDET_TUNING
     if (const char* e = getenv("RSDET_ROI_PATH")) return atoi(e);
 #endif
-    return 0;
+    return 1;
 }
 
+#ifdef RSDET_TUNING
 static bool px_path_ok(const rsdet_roi_align_cfg* c) {
     if (c->pooled_h != kPxRows || c->pooled_w != kPxCols || c->sampling_ratio != 2 || c->channels % 256 != 0) return false;
     for (int l = 0; l < c->num_levels; l++)   // pixel keys are (y << 16 | x); pixel indices 32-bit
         if (c->height[l] >= 32768 || c->width[l] >= 65536 || (long long)c->height[l] * c->width[l] >= (1ll << 31)) return false;
     return true;
 }
+#endif
 
 // ---------------------------------------------------------------------------------- forward (TMA gather4)
 // Same decomposition (one CTA per RoI, merged tap lists, warp = bin group), but the feature rows are no
@@ -1550,21 +1648,24 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
             L.feat[l] = dst[l];
         }
         if (!ws.ok()) return RSDET_EWORKSPACE;
-        rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st);
+    }
+    // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
+    int* order = num_rois >= 256 && order_ws ? order_ws : nullptr;
+    const bool ride = !cfg->channels_last && order && num_rois <= kPrepMaxRois;
+    launch_prep(L, rois, num_rois, geoms, order, levels_out, st, ride);
+    if (!cfg->channels_last) {
+        // NCHW -> NHWC copy of the pyramid; the locality-order block rides along as block 0 of the same launch
+        const PrepArgs prep = {rois, num_rois, geoms, order};
+        float* dst[RSDET_MAX_LEVELS];
+        for (int l = 0; l < cfg->num_levels; l++) dst[l] = const_cast<float*>(L.feat[l]);
+        rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st,
+                              ride ? &prep : nullptr);
         if (rc != RSDET_OK) return rc;
     }
     size_t smem = fwd_smem_bytes(cfg);
     set_dyn_smem((const void*)roi_align_fwd_kernel<1>, smem);
     set_dyn_smem((const void*)roi_align_fwd_kernel<2>, smem);
-    // locality order (needs the int[K] slot at the start of the workspace; skipped for tiny calls)
-    roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, levels_out);
-    count_launch();
-    int* order = nullptr;
-    if (num_rois >= 256 && order_ws) {
-        order = order_ws;
-        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
-        count_launch();
-    }
+#ifdef RSDET_TUNING
     if (px_path_ok(cfg) && (roi_path_choice() == 0 || roi_path_choice() == 3)) {
         const int chunks = cfg->channels / 256;
         if (roi_path_choice() == 3) {   // one CTA per RoI
@@ -1580,6 +1681,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         count_launch();
         return cuda_status();
     }
+#endif
     if (tma_path_ok(cfg)) {
         TmaMaps maps;
         bool ok = true;
@@ -1647,14 +1749,8 @@ extern "C" int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, 
             size_t smem = fwd_smem_bytes(cfg);
             set_dyn_smem((const void*)roi_align_bwd_kernel<1>, smem);
             set_dyn_smem((const void*)roi_align_bwd_kernel<2>, smem);
-            roi_geometry_kernel<<<ceil_div(num_rois, 128), 128, 0, st>>>(L, rois, num_rois, geoms, nullptr);
-            count_launch();
-            int* order = nullptr;
-            if (num_rois >= 256) {
-                order = order_ws;
-                roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, num_rois, order, nullptr);
-                count_launch();
-            }
+            int* order = num_rois >= 256 ? order_ws : nullptr;
+            launch_prep(L, rois, num_rois, geoms, order, nullptr, st);
             int Q = quads_per_chunk(cfg->channels);
             dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
             if (cfg->channels % 256 == 0) roi_align_bwd_kernel<2><<<grid, kRoiThreads, smem, st>>>(L, rois, order, geoms, num_rois, grad_out);

@@ -161,7 +161,8 @@ def read_tile_detections(fullname, ncoord=8):
 
 
 def _merge_files(files, dstpath, thresholds, kind=NMS_MERGE):
-    """Shared body of mergesingle / mergebase / mergebypoly / mergebyrec: all files, all scenes, one NMS launch."""
+    """Shared body of mergesingle / mergebase / mergebypoly / mergebyrec: all files and scenes in one NMS launch (several
+    when the dump holds more rows than an engine call takes, core.nms_grouped)."""
     require_cuda()
     recs = [read_tile_detections(f, 4 if kind == NMS_HBB_P1_F64 else 8) for f in files]
     gid_of, rows_gid, thr = {}, [], []
@@ -177,15 +178,13 @@ def _merge_files(files, dstpath, thresholds, kind=NMS_MERGE):
         polys = torch.from_numpy(np.concatenate([r[2] for r in recs])).cuda()
         offs = torch.from_numpy(np.concatenate([r[3] for r in recs])).cuda()
         scores = torch.from_numpy(np.concatenate([r[4] for r in recs])).cuda()
-        gids = torch.from_numpy(np.concatenate(rows_gid)).cuda()
         if polys.shape[1] == 8:
             orig = core.poly2origpoly(polys, offs)
         else:  # (n,4) boxes: the same (p + offset) / rate map on two points
             orig = core.poly2origpoly(torch.cat([polys, polys], 1), offs)[:, :4].contiguous()
-        res = core.nms(kind, orig, scores, nms_threshold_0, labels=gids,
-                       thr_per_label=torch.tensor(thr, dtype=torch.float64, device=orig.device), want_mask=False,
-                       want_sorted=False, want_score=True, ws_tag="merge")
-        kept_rows = res.score_idx.cpu().numpy()
+        # (file, scene) groups are independent: one launch when the rows fit an engine call, else split by group
+        kept_rows = core.nms_grouped(kind, orig, scores, np.concatenate(rows_gid), nms_threshold_0,
+                                     thr_per_label=torch.tensor(thr, dtype=torch.float64, device=orig.device))
         scene_polys = orig.cpu().numpy()
     all_scores = np.concatenate([r[4] for r in recs]) if n else np.zeros((0,))
     all_gids = np.concatenate(rows_gid) if n else np.zeros((0,), np.int32)

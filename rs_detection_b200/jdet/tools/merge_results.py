@@ -55,9 +55,7 @@ def _merge(files, dst_path, nms_op, nms_thr):
     if dets.shape[0]:
         g = np.concatenate(gids)
         t = torch.from_numpy(dets).cuda()
-        res = core.nms(NMS_MERGE, t[:, :8], t[:, 8], float(nms_thr), labels=torch.from_numpy(g).cuda(), want_mask=False,
-                       want_sorted=False, want_score=True, ws_tag="merge")
-        for r in res.score_idx.cpu().tolist():
+        for r in core.nms_grouped(NMS_MERGE, t[:, :8].contiguous(), t[:, 8].contiguous(), g, float(nms_thr)).tolist():
             per_gid[g[r]].append(r)
     for fi, f in enumerate(files):
         with open(os.path.join(dst_path, os.path.split(f)[-1]), "w") as fo:

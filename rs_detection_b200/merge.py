@@ -67,7 +67,7 @@ def _device_nms(polys, scores, groups, thr, group_thr):
     from ._lib import NMS_MERGE
     res = core.nms(NMS_MERGE, polys, scores, float(thr), labels=groups, thr_per_label=group_thr, want_mask=False,
                    want_sorted=False, want_score=True, ws_tag="merge")
-    return res.score_idx, res.num_keep
+    return res.score_idx_padded, res.num_keep
 
 
 def merge_sharded(polys: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, scene_ids: Optional[torch.Tensor] = None,

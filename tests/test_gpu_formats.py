@@ -57,7 +57,9 @@ def test_merge_results_tool_byte_exact(cuda, tmp_path):
     merge_files(str(tmp_path / "cat"), str(tmp_path / "got"), nms_thr=0.1)
     for f in os.listdir(tmp_path / "cat"):
         assert not f.startswith("Task1_")
-        F.merge_file(str(tmp_path / "cat" / f), str(tmp_path / "want"), 0.1)
+        # the two runs share four-decimal score values: ties -> the well-defined rule argsort(kind='stable')[::-1]
+        # (numpy's default argsort order of equal scores is an artefact of the numpy build, oracle.score_order)
+        F.merge_file(str(tmp_path / "cat" / f), str(tmp_path / "want"), 0.1, stable_ties=True)
     _same_dir(tmp_path / "want", tmp_path / "got")
 
 

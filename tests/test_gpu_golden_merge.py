@@ -30,10 +30,6 @@ def test_hbb_nms_vs_reference(cuda, oracle, g):
         for tag in "bc":                                                                       # ties, NaN pairs
             b = g[f"nms_{tag}_boxes"]
             assert np.array_equal(PM.nms(b, thr), oracle.hbb_nms(b, thr, stable_ties=True)), (tag, thr)
-    # n <= 16: numpy's argsort is an insertion sort (stable), so even tied inputs match the reference itself
-    b = g["nms_c_boxes"][:16].copy()
-    b[:, 4] = np.round(b[:, 4], 1)
-    assert np.array_equal(PM.nms(b, 0.3), oracle.hbb_nms(b, 0.3))
 
 
 def test_ensemble_vs_reference(cuda, oracle, g):

@@ -134,3 +134,28 @@ def test_merge_sharded_single_rank_matches_unsharded(cuda, oracle):
         idx = np.nonzero(sc["labels"] == c)[0]
         dets = np.concatenate([sc["polys"][idx], sc["scores"][idx, None]], 1)
         assert [int(idx[k]) for k in oracle.py_cpu_nms_poly_fast(dets, thr[c])] == kept[lab == c].tolist()
+
+
+def test_merge_more_rows_than_one_engine_call(cuda, oracle):
+    """a `before_nms` dump with more than 2^18 rows.  core.nms_grouped splits the (file, scene) groups over
+    several engine calls; every group must come out exactly as one reference-style call per group gives it."""
+    from rs_detection_b200 import core
+    from rs_detection_b200._lib import NMS_MERGE
+    rng = np.random.default_rng(5)
+    G, per = 2750, 100                                    # 275 000 rows > 2^18
+    base = W.obb_to_poly64(W.rotated_boxes(per, 3, canvas=300, smin=8, smax=40, dtype=np.float64))
+    polys = np.round(np.concatenate([base + rng.normal(0, 0.6, base.shape) for _ in range(G)]), 4)
+    gids = np.repeat(np.arange(G), per)
+    perm = rng.permutation(G * per)                        # groups interleaved like tiles in a file
+    polys, gids = polys[perm], gids[perm]
+    scores = rng.permutation(G * per).astype(np.float64) / (G * per)
+    assert polys.shape[0] > core.MAX_NMS_ROWS
+    kept = core.nms_grouped(NMS_MERGE, torch.from_numpy(polys).cuda(), torch.from_numpy(scores).cuda(), gids, 0.3)
+    assert len(set(kept.tolist())) == kept.size
+    for gsel in rng.choice(G, 40, replace=False):
+        idx = np.nonzero(gids == gsel)[0]
+        want = [int(idx[k]) for k in oracle.py_cpu_nms_poly_fast(np.concatenate([polys[idx], scores[idx, None]], 1), 0.3)]
+        got = kept[gids[kept] == gsel].tolist()
+        assert got == want
+    with pytest.raises(RuntimeError, match="at most"):
+        core.nms_grouped(NMS_MERGE, torch.from_numpy(polys).cuda(), torch.from_numpy(scores).cuda(), np.zeros(G * per, np.int64), 0.3)
