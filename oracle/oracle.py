@@ -36,6 +36,24 @@ def build(force: bool = False) -> str:
     return _SO
 
 
+def flop_census(boxes1, boxes2, version: int = 1):
+    """FLOPs the reference's rotated-IoU algorithm spends on `boxes1 x boxes2` (every pair, no early exit), counted by
+    a -DORC_COUNT_FLOPS build of the same C restatement.  Returns (flops, pairs)."""
+    so = _SO.replace(".so", "_count.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fno-fast-math", "-DORC_COUNT_FLOPS", "-shared",
+                               "-fPIC", _SRC, "-o", so, "-lm"])
+    L = C.CDLL(so)
+    L.orc_flops_read.restype = C.c_ulonglong
+    L.orc_pairs_read.restype = C.c_ulonglong
+    L.orc_box_iou_rotated.argtypes = [_pf, C.c_int, _pf, C.c_int, C.c_int, C.c_int, _pf]
+    b1, b2 = _c32(boxes1).reshape(-1, 5), _c32(boxes2).reshape(-1, 5)
+    out = np.zeros((b1.shape[0], b2.shape[0]), np.float32)
+    L.orc_flops_reset()
+    L.orc_box_iou_rotated(_fp(b1), b1.shape[0], _fp(b2), b2.shape[0], version, 0, _fp(out))
+    return int(L.orc_flops_read()), int(L.orc_pairs_read())
+
+
 _lib = None
 
 

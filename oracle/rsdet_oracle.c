@@ -26,6 +26,19 @@
 
 typedef struct { float x, y; } pt;
 
+/* FLOP census of the reference's rotated-IoU algorithm ("pin the per-pair figure by instrumenting the CPU
+ * restatement"): built with -DORC_COUNT_FLOPS (oracle.build(count_flops=True) -> a second library), every float add,
+ * subtract, multiply, divide and each sin / cos counts 1; comparisons, fabs and moves count 0.  Read with
+ * orc_flops_read(), reset with orc_flops_reset().  The default library compiles the macro away. */
+#ifdef ORC_COUNT_FLOPS
+static unsigned long long g_orc_flops = 0, g_orc_pairs = 0;
+#define FL(n) (g_orc_flops += (unsigned long long)(n))
+unsigned long long orc_flops_read(void) { return g_orc_flops; }
+unsigned long long orc_pairs_read(void) { return g_orc_pairs; }
+void orc_flops_reset(void) { g_orc_flops = 0; g_orc_pairs = 0; }
+#else
+#define FL(n) ((void)0)
+#endif
 static inline float cross2(pt a, pt b) { return a.x * b.y - b.x * a.y; } /* box_iou_rotated.py:47-50 */
 static inline float dot2(pt a, pt b) { return a.x * b.x + a.y * b.y; }   /* box_iou_rotated.py:42-45 */
 static inline pt sub2(pt a, pt b) { pt r = { a.x - b.x, a.y - b.y }; return r; }
@@ -35,6 +48,7 @@ static inline pt sub2(pt a, pt b) { pt r = { a.x - b.x, a.y - b.y }; return r; }
 static void rotated_vertices(float xc, float yc, float w, float h, float a, int version, pt p[4])
 {
     double theta = a;
+    FL(2 + 2 + 16 + 8);  /* sin, cos; two halvings; vertices 0/1: 8 mul + 8 add; vertices 2/3: 4 mul + 4 sub */
     float c2 = (float)cos(theta) * 0.5f;
     float s2 = (float)sin(theta) * 0.5f;
     if (version == 0) {
@@ -59,24 +73,29 @@ static int intersection_points(const pt p1[4], const pt p2[4], pt out[24])
 {
     pt v1[4], v2[4];
     int num = 0;
+    FL(16);
     for (int i = 0; i < 4; i++) {
         v1[i] = sub2(p1[(i + 1) % 4], p1[i]);
         v2[i] = sub2(p2[(i + 1) % 4], p2[i]);
     }
     for (int i = 0; i < 4; i++) {
         for (int j = 0; j < 4; j++) {
+            FL(3);
             float det = cross2(v2[j], v1[i]);
             if (fabs((double)det) <= 1e-14) continue;
+            FL(2 + 4 + 4);
             pt v12 = sub2(p2[j], p1[i]);
             float t1 = cross2(v2[j], v12) / det;
             float t2 = cross2(v1[i], v12) / det;
             if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
+                FL(4);
                 out[num].x = p1[i].x + v1[i].x * t1;
                 out[num].y = p1[i].y + v1[i].y * t1;
                 num++;
             }
         }
     }
+    FL(2 * (6 + 4 * 9));   /* both corner-in-rectangle loops: two squared lengths, per corner 2 subs + 2 dots + 1 negation */
     {   /* corners of box 1 inside box 2 */
         pt AB = v2[0], DA = v2[3];
         float ABdotAB = dot2(AB, AB), ADdotAD = dot2(DA, DA);
@@ -105,8 +124,9 @@ static int intersection_points(const pt p1[4], const pt p2[4], pt out[24])
 /* comparator of the CPU flavour, box_iou_rotated.py:316-325 */
 static int hull_less(pt A, pt B)
 {
+    FL(3);
     float t = cross2(A, B);
-    if (fabs((double)t) < 1e-6) return dot2(A, A) < dot2(B, B);
+    if (fabs((double)t) < 1e-6) { FL(6); return dot2(A, A) < dot2(B, B); }
     return t > 0;
 }
 
@@ -124,6 +144,7 @@ static int convex_hull(const pt p[24], int n, pt q[24], int sort_kind)
     for (int i = 1; i < n; i++)
         if (p[i].y < p[t].y || (p[i].y == p[t].y && p[i].x < p[t].x)) t = i;
     pt start = p[t];
+    FL(2 * n + 3 * n);
     for (int i = 0; i < n; i++) q[i] = sub2(p[i], start);
     { pt tmp = q[0]; q[0] = q[t]; q[t] = tmp; }
     for (int i = 0; i < n; i++) dist[i] = dot2(q[i], q[i]);
@@ -138,6 +159,7 @@ static int convex_hull(const pt p[24], int n, pt q[24], int sort_kind)
     } else {
         for (int i = 1; i < n - 1; i++)
             for (int j = i + 1; j < n; j++) {
+                FL(3);
                 float cp = cross2(q[i], q[j]);
                 if (cp < -1e-6 || (fabs((double)cp) < 1e-6 && dist[i] > dist[j])) {
                     pt tq = q[i]; q[i] = q[j]; q[j] = tq;
@@ -152,7 +174,8 @@ static int convex_hull(const pt p[24], int n, pt q[24], int sort_kind)
     q[1] = q[k];
     int m = 2;
     for (int i = k + 1; i < n; i++) {
-        while (m > 1 && cross2(sub2(q[i], q[m - 2]), sub2(q[m - 1], q[m - 2])) >= 0) m--;
+        FL(7);
+        while (m > 1 && cross2(sub2(q[i], q[m - 2]), sub2(q[m - 1], q[m - 2])) >= 0) { m--; FL(7); }
         q[m++] = q[i];
     }
     return m; /* shift_to_zero == true at the only call site (:276) */
@@ -163,6 +186,7 @@ static float polygon_area(const pt q[24], int m)
 {
     if (m <= 2) return 0;
     float area = 0;
+    FL(8 * (m - 2) + 1);
     for (int i = 1; i < m - 1; i++)
         area += (float)fabs((double)cross2(sub2(q[i], q[0]), sub2(q[i + 1], q[0])));
     return (float)(area / 2.0);
@@ -174,6 +198,10 @@ static float polygon_area(const pt q[24], int m)
 float orc_rotated_iou_pair(const float* b1, const float* b2, int box_len, int version, int sort_kind)
 {
     if (box_len == 6 && b1[5] != b2[5]) return 0.0f;
+#ifdef ORC_COUNT_FLOPS
+    g_orc_pairs++;
+#endif
+    FL(4 + 4 + 2 + 3);   /* midpoint, shifted centres, two areas, final iou */
     double sx = (b1[0] + b2[0]) / 2.0;
     double sy = (b1[1] + b2[1]) / 2.0;
     float x1 = (float)(b1[0] - sx), y1 = (float)(b1[1] - sy);

@@ -43,7 +43,6 @@ constexpr size_t kCubTempBytes = 8u << 20;
 constexpr int kFastSegs = 2048;  // segment starts collected with atomics + one in-CTA bitonic sort
 
 // ----------------------------------------------------------------------------- predicates
-struct PolyBox { float p[8]; };
 struct HBox { double x1, y1, x2, y2; };
 
 template <int KIND> struct Traits;
@@ -69,13 +68,16 @@ template <> struct Traits<RSDET_NMS_ROTATED_GE> : Traits<RSDET_NMS_ROTATED> {
 };
 template <> struct Traits<RSDET_NMS_POLY> {
     using Box = PolyBox; using Raw = float; using Thr = float;
-    static constexpr int kRow = 8; static constexpr bool kScratch = false;
-    __device__ static Box prep(const Raw* r) { Box b; for (int i = 0; i < 8; i++) b.p[i] = r[i]; return b; }
+    static constexpr int kRow = 8; static constexpr bool kScratch = true;   // 2 x 10 polygon slots per thread
+    __device__ static Box prep(const Raw* r) { return prep_polybox(r); }
     static constexpr bool kRefine = false;
-    __device__ static bool cheap(const Box&, const Box&) { return true; }  // see poly_iou.cuh
+    // the only pairs dropped before the exact evaluation are those whose 16 fan terms are provably all zero
+    __device__ static bool cheap(const Box& a, const Box& b) { return !poly_pair_is_zero(a, b); }
     __device__ static bool refine1(const Box&, const Box&, Thr) { return true; }
     __device__ static bool refine2(const Box&, const Box&, Thr) { return true; }
-    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2*) { return poly_iou_f32(a.p, b.p) > thr; }
+    __device__ static bool suppress(const Box& a, const Box& b, Thr thr, float2* q) {
+        return poly_iou_f32<kNmsThreads>(a, b, q) > thr;
+    }
 };
 template <> struct Traits<RSDET_NMS_MERGE> {
     using Box = MBox; using Raw = double; using Thr = double;

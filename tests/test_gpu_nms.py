@@ -154,3 +154,43 @@ def test_multiclass_nms_rotated_baseline_sizes(cuda, oracle, ref, K, C, score_th
         total += int(ref.nms_keep(boxes[m], order, 0.1, 5, ge=False).sum())
     assert total - 1 == gd_all.shape[0]      # max_num=-1 drops the last detection (nms_rotated.py:590-591)
     print(f"K={K} C={C}: {int((scores[:, 1:] > score_thr).sum())} candidates -> {total} kept")
+
+
+def test_poly_nms_exact_zero_skip_adversarial(cuda, oracle):
+    """csrc/poly_iou.cuh drops pairs whose 16 fan terms are provably exactly zero (angular sectors, seen from the
+    origin, disjoint by a safety margin).  The oracle evaluates every pair literally; threshold 0 turns ANY non-zero
+    cancellation noise into a suppression, so the keep lists agree only if the skipped pairs really are exact zeros.
+    Layouts: a fan of boxes around the origin with gaps down to the margin, boxes with radial edges, boxes that contain
+    or touch the origin, the reference's class-offset layout far from the origin, integer coordinates (exact ties in
+    the cross products)."""
+    from rs_detection_b200.jdet.ops.nms_poly import poly_nms
+    rng = np.random.default_rng(123)
+    sets = []
+    # (a) fan around the origin: radius 40..3000, angular pitch barely above / below the box's own angular width
+    for R, npts, jitter in ((60.0, 90, 0.002), (400.0, 300, 0.0005), (3000.0, 400, 0.0002)):
+        ang = np.linspace(0, 2 * np.pi, npts, endpoint=False) + rng.normal(0, jitter, npts)
+        w = 2 * np.pi * R / npts * rng.uniform(0.6, 1.3, npts)
+        h = rng.uniform(4, 30, npts)
+        th = ang + np.pi / 2 + rng.normal(0, 0.2, npts)          # tangential boxes, some rotated
+        th[::7] = ang[::7]                                        # radial boxes: edge lines through the origin region
+        obb = np.stack([R * np.cos(ang), R * np.sin(ang), w, h, th], 1).astype(np.float32)
+        sets.append(oracle.obb2poly(obb))
+    # (b) boxes containing / touching the origin and tiny boxes next to it
+    obb = W.rotated_boxes(150, 9, canvas=80, smin=2, smax=60)
+    obb[:, :2] -= 40
+    sets.append(oracle.obb2poly(obb))
+    # (c) class-offset layout of multiclass_poly_nms (nms_poly.py:235-237), far from the origin
+    obb = W.rotated_boxes(500, 10, canvas=500, smin=8, smax=90)
+    p = oracle.obb2poly(obb)
+    lab = rng.integers(0, 6, 500)
+    sets.append((p + (lab * (float(p.max() - p.min()) + 1))[:, None]).astype(np.float32))
+    # (d) integer coordinates
+    sets.append(np.round(oracle.obb2poly(W.rotated_boxes(300, 11, canvas=300, smin=8, smax=60))).astype(np.float32) + 1000)
+    for k, pp in enumerate(sets):
+        pp = np.ascontiguousarray(pp, np.float32)
+        sc = W.distinct_scores(pp.shape[0], 60 + k)
+        b9 = np.concatenate([pp, sc[:, None]], 1)
+        for thr in (0.0, 0.02, 0.3):
+            got = poly_nms(_t(b9), thr).cpu().numpy()
+            want = oracle.poly_nms(b9, thr)
+            assert np.array_equal(got, want), (k, thr, len(got), len(want))
