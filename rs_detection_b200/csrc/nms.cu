@@ -1232,14 +1232,52 @@ __device__ __forceinline__ float ord_f32_inv(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// ctl[5], ctl[6]: float bits of the largest hbb height / width (positive floats order like ints)
-__global__ void sp_extent_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+// What the sparse path needs to know about a box type: an axis-aligned extent (sweep order / bands), the candidate
+// test of the sweep (cheap, exact: it may only drop pairs that cannot suppress) and the suppression predicate.
+template <int KIND> struct SpAdapt;
+template <> struct SpAdapt<RSDET_NMS_MERGE> {
+    using Box = MBox;
+    static constexpr int kScratchSlots = 0;
+    __device__ static double x1(const Box& b) { return b.x1; }
+    __device__ static double x2(const Box& b) { return b.x2; }
+    __device__ static double y1(const Box& b) { return b.y1; }
+    __device__ static double y2(const Box& b) { return b.y2; }
+    __device__ static bool cand(const Box& a, const Box& b, double) { return merge_hbb_overlap(a, b); }
+    // survivors are `iou <= thr` (result_merge.py:118)
+    __device__ static bool sup(const Box& a, const Box& b, double thr, float2*) { return !(iou_poly_d(a, b) <= thr); }
+};
+// rotated boxes (dense single-stage candidates, BASELINE config 4): extent = the square around the bounding circle;
+// candidates = circles overlap and the axis-aligned upper bound of the IoU does not already rule the pair out;
+// predicate = strip bound, then the exact clipper (the same cascade as mask_tiles_kernel, so decisions are identical)
+template <bool GE> struct SpAdaptRot {
+    using Box = RBox;
+    static constexpr int kScratchSlots = 24;
+    __device__ static double x1(const Box& b) { return (double)b.x - (double)fmaxf(b.r, 0.f); }
+    __device__ static double x2(const Box& b) { return (double)b.x + (double)fmaxf(b.r, 0.f); }
+    __device__ static double y1(const Box& b) { return (double)b.y - (double)fmaxf(b.r, 0.f); }
+    __device__ static double y2(const Box& b) { return (double)b.y + (double)fmaxf(b.r, 0.f); }
+    __device__ static bool cand(const Box& a, const Box& b, double thr) {
+        return rbox_may_overlap(a, b) && !rbox_iou_below(a, b, (float)thr);
+    }
+    __device__ static bool sup(const Box& a, const Box& b, double thr, float2* q) {
+        if (rbox_iou_below_strips(a, b, (float)thr)) return false;
+        const float iou = rotated_iou_pair<kNmsThreads>(a, b, q);
+        return GE ? iou >= (float)thr : iou > (float)thr;
+    }
+};
+template <> struct SpAdapt<RSDET_NMS_ROTATED> : SpAdaptRot<false> {};
+template <> struct SpAdapt<RSDET_NMS_ROTATED_GE> : SpAdaptRot<true> {};
+
+// ctl[5], ctl[6]: float bits of the largest extent height / width (positive floats order like ints)
+template <int KIND>
+__global__ void sp_extent_kernel(const typename SpAdapt<KIND>::Box* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+    using A = SpAdapt<KIND>;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_eff = min(tb.hdr[1], n_max);
     float h = 0.f, wd = 0.f;
     if (p < n_eff) {
-        h = __double2float_ru(boxes[p].y2 - boxes[p].y1);
-        wd = __double2float_ru(boxes[p].x2 - boxes[p].x1);
+        h = __double2float_ru(A::y2(boxes[p]) - A::y1(boxes[p]));
+        wd = __double2float_ru(A::x2(boxes[p]) - A::x1(boxes[p]));
     }
     for (int o = 16; o; o >>= 1) {
         h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
@@ -1260,7 +1298,9 @@ __device__ __forceinline__ unsigned int sp_band(double y, double band_h) {
 }
 __device__ __forceinline__ double sp_band_h(const SparseWs& w) { return fmax((double)__int_as_float(w.ctl[5]) * 1.000001, 1e-6); }
 
-__global__ void sp_keys_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+template <int KIND>
+__global__ void sp_keys_kernel(const typename SpAdapt<KIND>::Box* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+    using A = SpAdapt<KIND>;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p > n_max) return;
     if (p == n_max) { w.cnt[p] = 0; w.indeg[p] = 0; return; }
@@ -1275,33 +1315,78 @@ __global__ void sp_keys_kernel(const MBox* __restrict__ boxes, SegTable tb, int 
     }
     w.seg_of[p] = lo;
     // (group | y band | x1 rounded DOWN: never right of the true x1)
-    w.keyA[p] = ((unsigned long long)lo << (32 + kBandBits)) | ((unsigned long long)sp_band(boxes[p].y1, sp_band_h(w)) << 32) |
-                ord_f32(__double2float_rd(boxes[p].x1));
+    w.keyA[p] = ((unsigned long long)lo << (32 + kBandBits)) | ((unsigned long long)sp_band(A::y1(boxes[p]), sp_band_h(w)) << 32) |
+                ord_f32(__double2float_rd(A::x1(boxes[p])));
+}
+
+// How many neighbours the sweep below would VISIT in total (two binary searches per detection instead of the walk):
+// the sparse path pays off when the overlap graph is sparse -- a 10k x 10k scene, dense single-stage candidates on a
+// large canvas -- and loses against the dense tiles in a crowd where every box's x extent covers thousands of
+// others (100k boxes on a 1024^2 canvas: 2600 visits per box).  ctl[7] accumulates visits / 64 per warp; the sweep
+// hands the call to the dense kernels (gate ctl[0]) when the mean exceeds kSparseMaxVisits per box.
+constexpr int kSparseMaxVisits = 640;
+template <int KIND>
+__global__ void sp_estimate_kernel(const typename SpAdapt<KIND>::Box* __restrict__ boxes, SegTable tb, int n_max,
+                                   const unsigned long long* __restrict__ key, const int* __restrict__ val, SparseWs w) {
+    using A = SpAdapt<KIND>;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_eff = min(tb.hdr[1], n_max);
+    unsigned visits = 0;
+    if (q < n_eff) {
+        const unsigned long long kq = key[q];
+        const unsigned int run = (unsigned int)(kq >> 32);
+        const auto bi = boxes[val[q]];
+        const unsigned int x2k = ord_f32(__double2float_ru(A::x2(bi)));
+        auto first_at_or_after = [&](unsigned long long k, int lo) {      // first r >= lo with key[r] >= k
+            int hi = n_eff;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < k) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        visits = (unsigned)(first_at_or_after(((unsigned long long)run << 32) | x2k, q + 1) - (q + 1));
+        const double band_h = sp_band_h(w);
+        const unsigned int band = run & ((1u << kBandBits) - 1u);
+        if (band + 1 < (1u << kBandBits) && sp_band(A::y2(bi), band_h) > band) {
+            const float maxw = __int_as_float(w.ctl[6]);
+            const unsigned long long lo = ((unsigned long long)(run + 1) << 32) | ord_f32(__double2float_rd(A::x1(bi) - (double)maxw * 1.000001));
+            const int a = first_at_or_after(lo, q + 1);
+            visits += (unsigned)(first_at_or_after(((unsigned long long)(run + 1) << 32) | x2k, a) - a);
+        }
+    }
+    for (int o = 16; o; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+    if ((threadIdx.x & 31) == 0 && visits) atomicAdd((unsigned int*)w.ctl + 7, (visits + 63) >> 6);
 }
 
 // FILL = false: count the candidate pairs of each sorted detection; FILL = true: write them at the prefix offsets.
 // Candidates of detection i: later members of its own (group, band) run whose x1 is left of x2_i, and -- when i
 // reaches into the next band -- the members of that run whose x1 lies in (x1_i - widest hbb, x2_i).
-template <bool FILL>
-__global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, const unsigned long long* __restrict__ key,
-                                const int* __restrict__ val, SparseWs w) {
+template <int KIND, bool FILL>
+__global__ void sp_sweep_kernel(const typename SpAdapt<KIND>::Box* __restrict__ boxes, SegTable tb, int n_max,
+                                const unsigned long long* __restrict__ key, const int* __restrict__ val, SparseWs w) {
+    using A = SpAdapt<KIND>;
+    using Box = typename A::Box;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_eff = min(tb.hdr[1], n_max);
     if (q >= n_eff) return;
+    if ((unsigned long long)(unsigned int)w.ctl[7] * 64ull > (unsigned long long)kSparseMaxVisits * (unsigned long long)n_eff + 4096ull) {
+        if (q == 0) w.ctl[0] = 1;   // a crowd: the dense kernels take the call
+        return;
+    }
     if (FILL && (long long)w.cnt[n_max] > w.capC) { if (q == 0) w.ctl[0] = 1; return; }
     const unsigned long long kq = key[q];
     const unsigned int run = (unsigned int)(kq >> 32);
     const int i = val[q];
-    const MBox bi = boxes[i];
+    const Box bi = boxes[i];
+    const double bx1 = A::x1(bi), bx2 = A::x2(bi), by2 = A::y2(bi);
+    const double thr = tb.seg_thr[w.seg_of[i]];
     int found = 0;
     long long out = FILL ? (long long)w.cnt[q] : 0;
     auto visit = [&](int r0, unsigned int want_run) {
         for (int r = r0; r < n_eff; r++) {
             const unsigned long long kr = key[r];
             if ((unsigned int)(kr >> 32) != want_run) break;
-            if (!((double)ord_f32_inv((unsigned int)kr) < bi.x2)) break;  // every later x1 is at or right of my x2
+            if (!((double)ord_f32_inv((unsigned int)kr) < bx2)) break;  // every later x1 is at or right of my x2
             const int j = val[r];
-            if (merge_hbb_overlap(bi, boxes[j])) {
+            if (A::cand(bi, boxes[j], thr)) {
                 if (FILL) {
                     const int src = min(i, j), dst = max(i, j);  // lower sorted position = higher score
                     w.cand[out++] = ((unsigned long long)dst << 32) | (unsigned int)src;
@@ -1313,10 +1398,10 @@ __global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int
     visit(q + 1, run);
     const double band_h = sp_band_h(w);
     const unsigned int band = run & ((1u << kBandBits) - 1u);
-    if (band + 1 < (1u << kBandBits) && sp_band(bi.y2, band_h) > band) {
+    if (band + 1 < (1u << kBandBits) && sp_band(by2, band_h) > band) {
         const unsigned int next_run = run + 1;
         const float maxw = __int_as_float(w.ctl[6]);
-        const unsigned long long lokey = ((unsigned long long)next_run << 32) | ord_f32(__double2float_rd(bi.x1 - (double)maxw * 1.000001));
+        const unsigned long long lokey = ((unsigned long long)next_run << 32) | ord_f32(__double2float_rd(bx1 - (double)maxw * 1.000001));
         int lo = q + 1, hi = n_eff;  // first r with key[r] >= lokey (the next band sorts after mine)
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -1327,14 +1412,18 @@ __global__ void sp_sweep_kernel(const MBox* __restrict__ boxes, SegTable tb, int
     if (!FILL) w.cnt[q] = found;
 }
 
-__global__ void sp_iou_kernel(const MBox* __restrict__ boxes, SegTable tb, int n_max, SparseWs w) {
+template <int KIND>
+__global__ void __launch_bounds__(kNmsThreads) sp_iou_kernel(const typename SpAdapt<KIND>::Box* __restrict__ boxes, SegTable tb,
+                                                             int n_max, SparseWs w) {
+    using A = SpAdapt<KIND>;
+    __shared__ float2 s_pts[A::kScratchSlots ? A::kScratchSlots * kNmsThreads : 1];
     const long long total = w.cnt[n_max];
     if (total > w.capC || w.ctl[0]) return;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const unsigned long long c = w.cand[e];
         const int src = (int)(unsigned int)c, dst = (int)(c >> 32);
         const double thr = tb.seg_thr[w.seg_of[src]];
-        const bool sup = !(iou_poly_d(boxes[src], boxes[dst]) <= thr);  // survivors are `iou <= thr` (result_merge.py:118)
+        const bool sup = A::sup(boxes[src], boxes[dst], thr, s_pts + (A::kScratchSlots ? threadIdx.x : 0));
         w.flag[e] = sup ? 1 : 0;
         if (sup) atomicAdd(&w.indeg[dst], 1);
     }
@@ -1466,6 +1555,29 @@ static void dispatch_kind(const NmsArgs& a, const int* idx, void* boxes, int32_t
         case RSDET_NMS_HBB_P1_F64: launch_kind<RSDET_NMS_HBB_P1_F64>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
         default: launch_kind<RSDET_NMS_HBB>(a, idx, boxes, label_sorted, tb, mask, st, mask_phase, starts_unsorted, gate); break;
     }
+}
+
+constexpr int kSparseMinRotated = 32768;  // below this the dense tiles + staged scan are faster (tools/sweep.py)
+
+template <int KIND>
+static void sp_launch_kind(int step, const void* boxes, SegTable tb, int n, const unsigned long long* key, const int* val,
+                           const SparseWs& w, cudaStream_t st) {
+    using Box = typename SpAdapt<KIND>::Box;
+    const Box* b = (const Box*)boxes;
+    switch (step) {
+        case 0: sp_extent_kernel<KIND><<<ceil_div(n, 256), 256, 0, st>>>(b, tb, n, w); break;
+        case 1: sp_keys_kernel<KIND><<<ceil_div(n + 1, 256), 256, 0, st>>>(b, tb, n, w); break;
+        case 5: sp_estimate_kernel<KIND><<<ceil_div(n, 128), 128, 0, st>>>(b, tb, n, key, val, w); break;
+        case 2: sp_sweep_kernel<KIND, false><<<ceil_div(n, 128), 128, 0, st>>>(b, tb, n, key, val, w); break;
+        case 3: sp_sweep_kernel<KIND, true><<<ceil_div(n, 128), 128, 0, st>>>(b, tb, n, key, val, w); break;
+        default: sp_iou_kernel<KIND><<<kNumSMs * 8, kNmsThreads, 0, st>>>(b, tb, n, w); break;
+    }
+}
+static void sp_launch(int kind, int step, const void* boxes, SegTable tb, int n, const unsigned long long* key, const int* val,
+                      const SparseWs& w, cudaStream_t st) {
+    if (kind == RSDET_NMS_MERGE) sp_launch_kind<RSDET_NMS_MERGE>(step, boxes, tb, n, key, val, w, st);
+    else if (kind == RSDET_NMS_ROTATED_GE) sp_launch_kind<RSDET_NMS_ROTATED_GE>(step, boxes, tb, n, key, val, w, st);
+    else sp_launch_kind<RSDET_NMS_ROTATED>(step, boxes, tb, n, key, val, w, st);
 }
 
 int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -1624,7 +1736,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     // 4'. large merge calls: sparse path first; the dense kernels below then run only if it raised the gate
     const int* gate = nullptr;
     const size_t mask_cap = a.mask_words ? a.mask_words : N * ((N + 63) / 64);
-    if (a.kind == RSDET_NMS_MERGE && n >= kSparseMinBoxes) {
+    const bool sparse_kind = a.kind == RSDET_NMS_MERGE || ((a.kind == RSDET_NMS_ROTATED || a.kind == RSDET_NMS_ROTATED_GE) && !a.labels);
+    if (sparse_kind && n >= (a.kind == RSDET_NMS_MERGE ? kSparseMinBoxes : kSparseMinRotated)) {
         Workspace mw(mask, mask_cap * sizeof(unsigned long long));
         SparseWs w;
         w.keyA = mw.take<unsigned long long>(N);
@@ -1639,7 +1752,7 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         w.ctl = cnt_scratch + 40;
         const size_t left = mw.used < mw.size ? mw.size - mw.used : 0;
         long long cap = (long long)(left / 14);              // 8 (cand) + 1 (flag) + 4 (adj) bytes per entry, + alignment slack
-        if (cap > 32ll * n) cap = 32ll * n;
+        if (cap > 128ll * n) cap = 128ll * n;
         if (cap > 0x3fffffffll) cap = 0x3fffffffll;
         if (cap >= 8ll * n) {
             w.capC = cap;
@@ -1649,12 +1762,11 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
             w.adj = mw.take<int>((size_t)cap);
         }
         if (cap >= 8ll * n && mw.ok()) {
-            const MBox* mb = (const MBox*)boxes;
             int nbits = 1;
             while ((1ll << nbits) < (long long)n + 1) nbits++;
             cudaMemsetAsync(w.ctl, 0, 8 * sizeof(int), st);
-            sp_extent_kernel<<<ceil_div(n, 256), 256, 0, st>>>(mb, tb, n, w);
-            sp_keys_kernel<<<ceil_div(n + 1, 256), 256, 0, st>>>(mb, tb, n, w);
+            sp_launch(a.kind, 0, boxes, tb, n, nullptr, nullptr, w, st);   // extents
+            sp_launch(a.kind, 1, boxes, tb, n, nullptr, nullptr, w, st);   // keys
             cub::DoubleBuffer<unsigned long long> dk(w.keyA, w.keyB);
             cub::DoubleBuffer<int> dv(w.valA, w.valB);
             size_t need = 0;
@@ -1664,13 +1776,14 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
             cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, dv, n, 0, kbits, st);
             const unsigned long long* key = dk.Current();
             const int* val = dv.Current();
-            sp_sweep_kernel<false><<<ceil_div(n, 128), 128, 0, st>>>(mb, tb, n, key, val, w);
+            sp_launch(a.kind, 5, boxes, tb, n, key, val, w, st);           // sparse enough?
+            sp_launch(a.kind, 2, boxes, tb, n, key, val, w, st);           // sweep: count
             need = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, need, w.cnt, w.cnt, n + 1, st);
             if (need > cub_bytes) return RSDET_EWORKSPACE;
             cub::DeviceScan::ExclusiveSum(cub_tmp, need, w.cnt, w.cnt, n + 1, st);
-            sp_sweep_kernel<true><<<ceil_div(n, 128), 128, 0, st>>>(mb, tb, n, key, val, w);
-            sp_iou_kernel<<<kNumSMs * 8, 128, 0, st>>>(mb, tb, n, w);
+            sp_launch(a.kind, 3, boxes, tb, n, key, val, w, st);           // sweep: fill
+            sp_launch(a.kind, 4, boxes, tb, n, key, val, w, st);           // predicate on the candidates
             cub::DeviceScan::ExclusiveSum(cub_tmp, need, w.indeg, w.indeg, n + 1, st);
             sp_fill_kernel<<<kNumSMs * 8, 256, 0, st>>>(n, w);
             {   // grid barrier inside: cooperative launch = the driver guarantees the 148 CTAs are co-resident even when

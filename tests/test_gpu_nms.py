@@ -194,3 +194,19 @@ def test_poly_nms_exact_zero_skip_adversarial(cuda, oracle):
             got = poly_nms(_t(b9), thr).cpu().numpy()
             want = oracle.poly_nms(b9, thr)
             assert np.array_equal(got, want), (k, thr, len(got), len(want))
+
+
+@pytest.mark.parametrize("n,canvas,thr", [(40000, 1024, 0.1), (40000, 4096, 0.5), (100000, 2048, 0.3)])
+def test_sparse_rotated_path_equals_dense_engine(cuda, n, canvas, thr):
+    """n >= 32768 unlabelled rotated boxes take the sparse path (sweep-and-prune candidates, CSR of suppressing pairs,
+    fixed-point greedy); the same call WITH (all-equal) labels stays on the dense tiles + scan.  Both apply the same
+    exact filter cascade and clipper, so the keep sets must be identical."""
+    from rs_detection_b200 import core
+    from rs_detection_b200._lib import NMS_ROTATED, NMS_ROTATED_GE
+    d = _t(W.rotated_boxes(n, n + 3, canvas=canvas, smin=8, smax=128))
+    s = _t(W.distinct_scores(n, n + 3))
+    for kind in (NMS_ROTATED, NMS_ROTATED_GE):
+        sparse = core.nms(kind, d, s, thr)
+        dense = core.nms(kind, d, s, thr, labels=torch.zeros(n, dtype=torch.int32, device="cuda"))
+        assert torch.equal(sparse.keep_mask, dense.keep_mask)
+        assert torch.equal(sparse.sorted_idx, dense.sorted_idx) and 0 < sparse.count < n
