@@ -1020,7 +1020,8 @@ reduce_ov_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, 
 template <int NCH, bool IDENT>  // NCH 64-word chunks per row: 1 (<= 4096 columns) or 2 (<= 8192)
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov_base,
-                        int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted, const int* __restrict__ gate) {
+                        int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted, const int* __restrict__ gate,
+                        const int* __restrict__ seg_count = nullptr) {
     if (gate && *gate == 0) return;
     extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][partials: 4 x Ts][rows: 2 x 64 x Ts][cand: n_boxes ints]
     __shared__ __align__(8) unsigned short s_col16[256];  // s_col16[4j + q]: rows i in quarter q (i < j) that suppress j
@@ -1029,7 +1030,7 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
     const int nseg = tb.hdr[0];
     for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
         const int st = tb.seg_start[s];
-        const int ns_all = tb.seg_start[s + 1] - st;
+        const int ns_all = seg_count ? seg_count[s] : tb.seg_start[s + 1] - st;   // seg_count: fixed-stride segments (fast multiclass path)
         const int n_boxes = IDENT ? ns_all : n_boxes_arg;
         const int ns = min(ns_all, n_boxes);            // shared matrix: one candidate per (box, class), ns <= n_boxes
         const int nblk = (ns + 63) >> 6;
@@ -1580,6 +1581,48 @@ static void sp_launch(int kind, int step, const void* boxes, SegTable tb, int n,
     else sp_launch_kind<RSDET_NMS_ROTATED>(step, boxes, tb, n, key, val, w, st);
 }
 
+// One directed n x n decision matrix "a suppresses b" for class-agnostic boxes (shared by every class): RBox prep, filter
+// cascade into a global pair queue, exact clipper over the queue, flagged-tile fallback.  mask: nb x pitch words followed
+// by the tile flags and the pair queue (mask_cap words in total); cnt_scratch[32..33]: queue counters.
+static void launch_ov_matrix(const float* shared_boxes, int nb, float thr, bool ge, RBox* sb, unsigned long long* mask, size_t mask_cap,
+                             int* cnt_scratch, cudaStream_t st) {
+        const int Tov = (nb + 63) / 64;
+        const int pitch = (Tov + 1) & ~1;
+        prep_shared_kernel<<<ceil_div(nb, 256), 256, 0, st>>>(shared_boxes, nb, sb);
+        cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * pitch, st);
+        long long tiles = (long long)Tov * (Tov + 1) / 2;
+        int grid = (int)(tiles < (1ll << 22) ? tiles : (1ll << 22));
+        // the part of the mask buffer the n x pitch matrix does not use holds the tile flags and the pair queue
+        const size_t used = (size_t)nb * pitch, flag_words = ((size_t)tiles + 7) / 8 + 1;
+        const bool split = grid == tiles && mask_cap > used + flag_words + 4096;
+        if (split) {
+            uint8_t* tile_flags = (uint8_t*)(mask + used);
+            int2* pairs = (int2*)(mask + used + flag_words);
+            const size_t capz = mask_cap - used - flag_words;
+            const unsigned int cap = (unsigned int)(capz < 0x7fffffffull ? capz : 0x7fffffffull);
+            unsigned int* pair_count = (unsigned int*)(cnt_scratch + 32);
+            cudaMemsetAsync(tile_flags, 0, flag_words * 8, st);
+            cudaMemsetAsync(pair_count, 0, 2 * sizeof(int), st);
+            // one pair per thread when the survivors fit (CTAs past the count exit at once); fallback: few CTAs scan the flags
+            const int cgrid = (int)(tiles < (long long)kNumSMs * 8 ? (long long)kNumSMs * 8 : (tiles < (long long)kNumSMs * 64 ? tiles : (long long)kNumSMs * 64));
+            const int fgrid = (int)(tiles < (long long)kNumSMs * 2 ? tiles : (long long)kNumSMs * 2);
+            if (ge) {
+                ov_filter_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, thr, pairs, cap, pair_count, tile_flags);
+                ov_clip_kernel<true><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, thr, mask, pitch);
+                ov_tiles_kernel<true><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, thr, mask, pitch, tile_flags, pair_count + 1);
+            } else {
+                ov_filter_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, thr, pairs, cap, pair_count, tile_flags);
+                ov_clip_kernel<false><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, thr, mask, pitch);
+                ov_tiles_kernel<false><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, thr, mask, pitch, tile_flags, pair_count + 1);
+            }
+            count_launch(2);
+        } else if (ge) {
+            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, thr, mask, pitch, nullptr, nullptr);
+        } else {
+            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, thr, mask, pitch, nullptr, nullptr);
+        }
+}
+
 int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int n = a.n_max;
     if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB_P1_F64) return RSDET_EINVAL;
@@ -1681,40 +1724,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         const int nb = a.n_shared, Tov = (nb + 63) / 64;
         const int pitch = (Tov + 1) & ~1;  // even row pitch: 16-byte aligned rows for the staged scan's vector loads
         RBox* sb = (RBox*)boxes;
-        prep_shared_kernel<<<ceil_div(nb, 256), 256, 0, st>>>(a.shared_boxes, nb, sb);
-        cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)nb * pitch, st);
-        long long tiles = (long long)Tov * (Tov + 1) / 2;
-        int grid = (int)(tiles < (1ll << 22) ? tiles : (1ll << 22));
-        // the part of the mask buffer the n x pitch matrix does not use holds the tile flags and the pair queue
         const size_t mask_cap = a.mask_words ? a.mask_words : N * ((N + 63) / 64);
-        const size_t used = (size_t)nb * pitch, flag_words = ((size_t)tiles + 7) / 8 + 1;
-        const bool split = grid == tiles && mask_cap > used + flag_words + 4096;
-        if (split) {
-            uint8_t* tile_flags = (uint8_t*)(mask + used);
-            int2* pairs = (int2*)(mask + used + flag_words);
-            const size_t capz = mask_cap - used - flag_words;
-            const unsigned int cap = (unsigned int)(capz < 0x7fffffffull ? capz : 0x7fffffffull);
-            unsigned int* pair_count = (unsigned int*)(cnt_scratch + 32);
-            cudaMemsetAsync(tile_flags, 0, flag_words * 8, st);
-            cudaMemsetAsync(pair_count, 0, 2 * sizeof(int), st);
-            // one pair per thread when the survivors fit (CTAs past the count exit at once); fallback: few CTAs scan the flags
-            const int cgrid = (int)(tiles < (long long)kNumSMs * 8 ? (long long)kNumSMs * 8 : (tiles < (long long)kNumSMs * 64 ? tiles : (long long)kNumSMs * 64));
-            const int fgrid = (int)(tiles < (long long)kNumSMs * 2 ? tiles : (long long)kNumSMs * 2);
-            if (a.kind == RSDET_NMS_ROTATED_GE) {
-                ov_filter_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, pairs, cap, pair_count, tile_flags);
-                ov_clip_kernel<true><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, (float)a.thr, mask, pitch);
-                ov_tiles_kernel<true><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, tile_flags, pair_count + 1);
-            } else {
-                ov_filter_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, pairs, cap, pair_count, tile_flags);
-                ov_clip_kernel<false><<<cgrid, kNmsThreads, 0, st>>>(sb, pairs, cap, pair_count, (float)a.thr, mask, pitch);
-                ov_tiles_kernel<false><<<fgrid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, tile_flags, pair_count + 1);
-            }
-            count_launch(2);
-        } else if (a.kind == RSDET_NMS_ROTATED_GE) {
-            ov_tiles_kernel<true><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, nullptr, nullptr);
-        } else {
-            ov_tiles_kernel<false><<<grid, kNmsThreads, 0, st>>>(sb, nb, (float)a.thr, mask, pitch, nullptr, nullptr);
-        }
+        launch_ov_matrix(a.shared_boxes, nb, (float)a.thr, a.kind == RSDET_NMS_ROTATED_GE, sb, mask, mask_cap, cnt_scratch, st);
         static bool attr2 = false;
         if (!attr2) {
             cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

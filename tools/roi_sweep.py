@@ -74,6 +74,14 @@ for spec in a.paths.split(","):      # "<path>" or "<path>:<prefetch 0/1>" (row-
             ref = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
         msg += f"; max |diff| vs bin-major {float((o - ref).abs().max()):.3g} (scale {float(ref.abs().max()):.3g})"
     print(msg, flush=True)
+    if prof is not None and path in (7, 8):
+        prof.zero_()
+        run()
+        torch.cuda.synchronize()
+        c = prof.cpu().numpy().astype(float)
+        n = max(c[6], 1.0)
+        print(f"    per warp and RoI: record wait {c[0] / n:.0f}, gather {c[1] / n:.0f}, store-drain wait {c[2] / n:.0f}, wait for the slowest warp {c[3] / n:.0f} cycles; "
+              f"{c[4] / n:.1f} batches -> {c[1] / max(c[4], 1):.0f} cycles per batch ({n:.0f} warp-RoIs)")
     if prof is not None and path == 3:
         prof.zero_()
         run()
