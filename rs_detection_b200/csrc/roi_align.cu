@@ -45,6 +45,7 @@ struct LevelSet {
     int num_levels, batch, C;
     int PH, PW, sampling_ratio, version;
     float extend_w, extend_h, finest_scale;
+    unsigned dbg_mask;  // profiling aid (RSDET_ROI_DBG_MASK, RSDET_TUNING builds only): tap offsets are ANDed with it (shrinks the gather's footprint)
     int dbg_skip_main;  // profiling aid (RSDET_ROI_DBG_SKIP_MAIN=1, RSDET_TUNING builds only): tap lists are built, then treated as empty
 };
 
@@ -122,33 +123,37 @@ __global__ void __launch_bounds__(256) transpose_kernel(TransposeJob job) {
 struct LevelSet;
 struct RoiGeom;
 struct PrepArgs {                 // order block riding along with the NCHW->NHWC transpose (see roi_order_block)
+    const LevelSet* L;
     const float* rois;
     int K;
-    const RoiGeom* geoms;
     int* order;
 };
 static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
                             int C, cudaStream_t st, const PrepArgs* prep = nullptr);
 
 // ---------------------------------------------------------------------------------- geometry
-struct RoiGeom {
+struct alignas(16) RoiGeom {   // 48 bytes = three 16-byte words (copied as such by the order kernels)
     int batch, level, gh, gw;
     float cw, ch, bin_h, bin_w, start_h, start_w, cosv, sinv;
 };
 
 // oriented_single_level.py:73-89 (roi_rescale), :53-71 (map_roi_levels); roi_align_rotated_v1.py:85-120
+__device__ __forceinline__ int roi_level(float w, float h, const LevelSet& L) {   // w, h: extended sizes
+    if (L.num_levels <= 1) return 0;
+    float s = sqrtf(__fmul_rn(w, h));
+    float t = floorf(log2f(__fadd_rn(__fdiv_rn(s, L.finest_scale), 1e-6f)));
+    t = fminf(fmaxf(t, 0.f), (float)(L.num_levels - 1));
+    return (int)t;
+}
+__device__ __forceinline__ int roi_level(const float* __restrict__ r, const LevelSet& L) {
+    return roi_level(__fmul_rn(L.extend_w, r[3]), __fmul_rn(L.extend_h, r[4]), L);
+}
 __device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ r, const LevelSet& L) {
     RoiGeom g;
     g.batch = (int)r[0];
     float w = __fmul_rn(L.extend_w, r[3]);
     float h = __fmul_rn(L.extend_h, r[4]);
-    int lvl = 0;
-    if (L.num_levels > 1) {
-        float s = sqrtf(__fmul_rn(w, h));
-        float t = floorf(log2f(__fadd_rn(__fdiv_rn(s, L.finest_scale), 1e-6f)));
-        t = fminf(fmaxf(t, 0.f), (float)(L.num_levels - 1));
-        lvl = (int)t;
-    }
+    const int lvl = roi_level(w, h, L);
     g.level = lvl;
     const float sc = L.scale[lvl];
     if (L.version == 1) {
@@ -222,6 +227,15 @@ __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+template <int FLAVOUR>   // A/B builds: 0 nc, 1 nc + L1::no_allocate, 2 nc + L1::evict_first, 3 plain ld.global.cg
+__device__ __forceinline__ float4 ldg_flavour_v4(const float* p) {
+    float4 r;
+    if (FLAVOUR == 1) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    else if (FLAVOUR == 2) asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    else if (FLAVOUR == 3) asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    else asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void stg_cs_v4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -255,13 +269,17 @@ __host__ __device__ inline int quads_per_chunk(int C) { return (C / 4) < 64 ? (C
 // ---------------------------------------------------------------------------------- per-RoI geometry
 // sin/cos/log2/sqrt and six divisions per RoI: done by K parallel threads here instead of by thread 0 of
 // every RoI's CTA (a ~1.5 us serial chain in front of each CTA's barrier).
-__global__ void roi_geometry_kernel(LevelSet L, const float* __restrict__ rois, int K, RoiGeom* __restrict__ geoms,
-                                    int32_t* __restrict__ levels_out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K) return;
+__global__ void roi_geometry_kernel(LevelSet L, const float* __restrict__ rois, int K, const int* __restrict__ order,
+                                    RoiGeom* __restrict__ geoms, RoiGeom* __restrict__ gsorted, int32_t* __restrict__ levels_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;   // position in processing order
+    if (p >= K) return;
+    const int i = order ? order[p] : p;
     RoiGeom g = roi_geometry(rois + (size_t)i * 6, L);
     geoms[i] = g;
     if (levels_out) levels_out[i] = g.level;
+    // gsorted: the records in processing order with the RoI index in `gh` (the fast kernels know the sampling grid from
+    // the configuration): a gather CTA then starts with ONE global round trip instead of order[blockIdx.x] -> geoms[roi]
+    if (gsorted) { g.gh = i; gsorted[p] = g; }
 }
 
 // ---------------------------------------------------------------------------------- processing order
@@ -273,8 +291,57 @@ constexpr int kCellShift = 7;   // 128-pixel cells in image coordinates
 constexpr int kCellsPerAxis = 16;
 constexpr int kBuckets = RSDET_MAX_LEVELS * kCellsPerAxis * kCellsPerAxis;
 
-__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, const RoiGeom* __restrict__ geoms,
-                                                         int K, int* __restrict__ order, int32_t* __restrict__ levels_out) {
+// The locality order of a call (what roi_order_kernel does) as ONE block of any size, so that for NCHW callers it can
+// ride along as an extra block of the NCHW->NHWC transpose: the order kernel is a 7.8 us single-CTA latency chain in
+// front of every gather, the transpose of a 1024^2 pyramid keeps the other SMs busy for 30 us anyway.  (Doing the
+// geometry in the same block as well was measured and dropped: sin/cos/log2 of 4000 RoIs on one SM take longer than
+// the two launches they replace.)  geoms[] must have been written by roi_geometry_kernel.  s_hist: kBuckets ints.
+constexpr int kPrepMaxRois = 16384;
+template <int THREADS>
+__device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* __restrict__ rois, int K,
+                                                int* __restrict__ order, int* s_hist, int* s_warp) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBuckets; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    auto bucket_of = [&](const float* r, int lvl) {
+        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
+        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
+        if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
+        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+    };
+    for (int i = tid; i < K; i += THREADS) {
+        const float* r = rois + (size_t)i * 6;
+        atomicAdd(&s_hist[bucket_of(r, roi_level(r, L))], 1);
+    }
+    __syncthreads();
+    // exclusive scan of kBuckets counters, kBuckets / THREADS consecutive ones per thread
+    constexpr int PER = kBuckets / THREADS;
+    int a[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { a[k] = s_hist[PER * tid + k]; sum += a[k]; }
+    int x = sum;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int v = lane < THREADS / 32 ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    int excl = (w ? s_warp[w - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { s_hist[PER * tid + k] = excl; excl += a[k]; }
+    __syncthreads();
+    for (int i = tid; i < K; i += THREADS) {
+        const float* r = rois + (size_t)i * 6;
+        order[atomicAdd(&s_hist[bucket_of(r, roi_level(r, L))], 1)] = i;
+    }
+}
+
+__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, int K,
+                                                         int* __restrict__ order) {
     __shared__ int s_hist[kBuckets];
     __shared__ int s_warp[32];
     const int tid = threadIdx.x;
@@ -282,7 +349,7 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     __syncthreads();
     auto bucket_of = [&](int i, int& lvl) {
         const float* r = rois + (size_t)i * 6;
-        lvl = geoms[i].level;
+        lvl = roi_level(r, L);
         int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
         int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
         // boustrophedon rows: neighbouring buckets are neighbouring cells
@@ -292,7 +359,6 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     for (int i = tid; i < K; i += 1024) {
         int lvl;
         int bkt = bucket_of(i, lvl);
-        if (levels_out) levels_out[i] = lvl;
         atomicAdd(&s_hist[bkt], 1);
     }
     __syncthreads();
@@ -320,63 +386,14 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     }
 }
 
-// The locality order of a call (what roi_order_kernel does) as ONE block of any size, so that for NCHW callers it can
-// ride along as an extra block of the NCHW->NHWC transpose: the order kernel is a 7.8 us single-CTA latency chain in
-// front of every gather, the transpose of a 1024^2 pyramid keeps the other SMs busy for 30 us anyway.  (Doing the
-// geometry in the same block as well was measured and dropped: sin/cos/log2 of 4000 RoIs on one SM take longer than
-// the two launches they replace.)  geoms[] must have been written by roi_geometry_kernel.  s_hist: kBuckets ints.
-constexpr int kPrepMaxRois = 16384;
-template <int THREADS>
-__device__ __forceinline__ void roi_order_block(const float* __restrict__ rois, int K, const RoiGeom* __restrict__ geoms,
-                                                int* __restrict__ order, int* s_hist, int* s_warp) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < kBuckets; i += THREADS) s_hist[i] = 0;
-    __syncthreads();
-    auto bucket_of = [&](const float* r, int lvl) {
-        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
-        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
-        if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
-        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
-    };
-    for (int i = tid; i < K; i += THREADS) {
-        const float* r = rois + (size_t)i * 6;
-        atomicAdd(&s_hist[bucket_of(r, geoms[i].level)], 1);
-    }
-    __syncthreads();
-    // exclusive scan of kBuckets counters, kBuckets / THREADS consecutive ones per thread
-    constexpr int PER = kBuckets / THREADS;
-    int a[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { a[k] = s_hist[PER * tid + k]; sum += a[k]; }
-    int x = sum;
-    const int lane = tid & 31, w = tid >> 5;
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[w] = x;
-    __syncthreads();
-    if (w == 0) {
-        int v = lane < THREADS / 32 ? s_warp[lane] : 0;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += y; }
-        s_warp[lane] = v;
-    }
-    __syncthreads();
-    int excl = (w ? s_warp[w - 1] : 0) + x - sum;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { s_hist[PER * tid + k] = excl; excl += a[k]; }
-    __syncthreads();
-    for (int i = tid; i < K; i += THREADS) {
-        const float* r = rois + (size_t)i * 6;
-        order[atomicAdd(&s_hist[bucket_of(r, geoms[i].level)], 1)] = i;
-    }
-}
-
 // NCHW callers: the pyramid transpose with the order block riding along as block 0
-__global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, const float* __restrict__ rois, int K,
-                                                             const RoiGeom* __restrict__ geoms, int* __restrict__ order) {
+__global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, LevelSet L, const float* __restrict__ rois, int K,
+                                                             int* __restrict__ order) {
     __shared__ float tile[64][65];
     static_assert(sizeof(float) * 64 * 65 >= sizeof(int) * (kBuckets + 32), "the prep block borrows the transpose tile");
     if (blockIdx.x == 0) {
         int* s_hist = reinterpret_cast<int*>(&tile[0][0]);
-        roi_order_block<256>(rois, K, geoms, order, s_hist, s_hist + kBuckets);
+        roi_order_block<256>(L, rois, K, order, s_hist, s_hist + kBuckets);
         return;
     }
     transpose_tile<true>(job, blockIdx.x - 1, tile);
@@ -394,7 +411,7 @@ static int launch_transpose(bool to_nhwc, const float* const* src, float* const*
     }
     job.tile_begin[L] = total;
     if (prep && to_nhwc) {
-        transpose_prep_kernel<<<total + 1, 256, 0, st>>>(job, prep->rois, prep->K, prep->geoms, prep->order);
+        transpose_prep_kernel<<<total + 1, 256, 0, st>>>(job, *prep->L, prep->rois, prep->K, prep->order);
         count_launch();
         return cuda_status();
     }
@@ -405,15 +422,22 @@ static int launch_transpose(bool to_nhwc, const float* const* src, float* const*
     return cuda_status();
 }
 
-// geometry (+ locality order for calls of >= 256 RoIs) of a call
-static void launch_prep(const LevelSet& L, const float* rois, int K, RoiGeom* geoms, int* order, int32_t* levels_out, cudaStream_t st,
-                        bool order_rides_with_transpose = false) {
-    roi_geometry_kernel<<<ceil_div(K, 128), 128, 0, st>>>(L, rois, K, geoms, levels_out);
+// locality order (calls of >= 256 RoIs) and geometry of a call.  The order comes first: the geometry kernel then writes
+// its records in processing order as well (coalesced).  order_rides_with_transpose: the caller's transpose launch
+// produces the order (block 0) and the caller launches the geometry kernel after it.
+static void launch_geometry(const LevelSet& L, const float* rois, int K, const int* order, RoiGeom* geoms, RoiGeom* gsorted,
+                            int32_t* levels_out, cudaStream_t st) {
+    roi_geometry_kernel<<<ceil_div(K, 128), 128, 0, st>>>(L, rois, K, order, geoms, gsorted, levels_out);
     count_launch();
-    if (order && !order_rides_with_transpose) {
-        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, geoms, K, order, nullptr);
+}
+static void launch_prep(const LevelSet& L, const float* rois, int K, RoiGeom* geoms, int* order, int32_t* levels_out, cudaStream_t st,
+                        bool order_rides_with_transpose = false, RoiGeom* gsorted = nullptr) {
+    if (order_rides_with_transpose) return;
+    if (order) {
+        roi_order_kernel<<<1, 1024, 0, st>>>(L, rois, K, order);
         count_launch();
     }
+    launch_geometry(L, rois, K, order, geoms, gsorted, levels_out, st);
 }
 
 // ---------------------------------------------------------------------------------- tap lists
@@ -426,11 +450,14 @@ static void launch_prep(const LevelSet& L, const float* rois, int K, RoiGeom* ge
 //   s_list [nbins*(cap+1)] int2 {offset, weight bits} (bin pitch cap + 1: conflict-free per-bin lanes),
 //   s_cnt [nbins], tmp: 3*nbins*(cap+1) words of scratch.
 //   unit/base: stored offset = base + pixel * unit (unit = C/4 for float4 addressing, 1 for TMA row indices)
+// FIXED = true: the 7x7-bin, 2x2-sample geometry as compile-time constants (roi_align_fwd77_kernel)
+template <int kThreads = kRoiThreads, bool FIXED = false>
 __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet& L, int H, int W, int2* s_list, int* s_cnt,
                                                 float* tmp, int unit, int base) {
     const int tid = threadIdx.x;
-    const int nbins = L.PH * L.PW;
-    const int spb = L.sampling_ratio * L.sampling_ratio;
+    const int PW_ = FIXED ? 7 : L.PW;
+    const int nbins = FIXED ? 49 : L.PH * L.PW;
+    const int spb = FIXED ? 4 : L.sampling_ratio * L.sampling_ratio;
     const int nsamp = nbins * spb, cap = 4 * spb, ntaps = nbins * cap;
     const int C4 = unit;
     int* s_off = reinterpret_cast<int*>(tmp);
@@ -439,9 +466,9 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
     // A1: one thread per sample.  Scratch pitch per bin = cap + 1 words when the per-bin merge below reads it
     // with one lane per bin (lane stride 17 words: conflict-free; 16 would be a 16-way bank conflict).
     const int tp = cap == 16 ? 17 : cap;
-    for (int s = tid; s < nsamp; s += kRoiThreads) {
+    for (int s = tid; s < nsamp; s += kThreads) {
         int b = s / spb, q = s % spb;
-        int ph = b / L.PW, pw = b % L.PW, iy = q / g.gw, ix = q % g.gw;
+        int ph = b / PW_, pw = b % PW_, iy = q / g.gw, ix = q % g.gw;
         float x, y;
         sample_xy(g, L.version, ph, pw, iy, ix, x, y);
         const Taps t = make_taps(H, W, y, x);
@@ -459,7 +486,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         // of the gather loads, profiles/README.md).  Same arithmetic: a tap is a LEADER if its weight is
         // non-zero and no earlier live tap of the bin hits the same pixel; a leader adds the weights of its
         // later duplicates in tap order; leaders are compacted in tap order.
-        for (int b = tid; b < nbins; b += kRoiThreads) {
+        for (int b = tid; b < nbins; b += kThreads) {
             int o[16];
             float w[16];
 #pragma unroll
@@ -488,9 +515,9 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
         // sums the weights of all live lanes on its pixel in lane order; a ballot of the leaders gives each
         // one its slot in the bin's compacted list.
         const int lane = tid & 31;
-        const int rounds = (ntaps + kRoiThreads - 1) / kRoiThreads;
+        const int rounds = (ntaps + kThreads - 1) / kThreads;
         for (int rd = 0; rd < rounds; rd++) {
-            const int t = rd * kRoiThreads + tid;
+            const int t = rd * kThreads + tid;
             const bool in = t < ntaps;
             const int b = in ? t / cap : 0, j = in ? t - b * cap : 0;
             const int o = in ? s_off[t] : -1;
@@ -516,7 +543,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
     }
     // A2a: one thread per tap: a tap is a LEADER if its weight is non-zero and no earlier tap of the bin
     // hits the same pixel; a leader collects the weights of its later duplicates (fixed order).
-    for (int t = tid; t < ntaps; t += kRoiThreads) {
+    for (int t = tid; t < ntaps; t += kThreads) {
         const int b = t / cap, j = t - b * cap;
         const int* ob = s_off + b * cap;
         const float* wb = s_w + b * cap;
@@ -531,7 +558,7 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
     }
     __syncthreads();
     // A2b: compaction (position = number of leaders before me in my bin)
-    for (int t = tid; t < ntaps; t += kRoiThreads) {
+    for (int t = tid; t < ntaps; t += kThreads) {
         const int b = t / cap, j = t - b * cap;
         const float* ws = s_wsum + b * cap;
         const float w = ws[j];
@@ -613,6 +640,10 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
                 int2 en[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) en[k] = lp[min(e + k, cnt - 1)];  // warp-uniform broadcast reads
+#ifdef RSDET_TUNING
+#pragma unroll
+                for (int k = 0; k < 4; k++) en[k].x &= L.dbg_mask;
+#endif
                 float4 v[QPT][4];
 #pragma unroll
                 for (int k = 0; k < 4; k++)
@@ -660,6 +691,100 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
     }
 }
 
+// ---------------------------------------------------------------------------------- forward (7x7 bins, 2x2 samples, 256-channel chunks)
+// The Oriented R-CNN geometry with everything the generic kernel reads at run time fixed at compile time, and the
+// gather loop restructured around what the per-instruction stall samples of the generic kernel showed
+// (profiles/README.md "round 2, second pass"): of its 18 000 warp instructions per RoI only 3 800 were FFMA and 940
+// LDG -- the rest were index clamps, 64-bit address pairs, run-time pitches and the rotate/stage arithmetic -- and a
+// third of the gather's stall samples sat on the LEA that waits for the tap-list LDS, i.e. every batch paid TWO dependent
+// L1 round trips (list entries, then pixels) behind the other CTAs' queued loads.  Here
+//   * the four list entries of the NEXT batch (or of the warp's next bin) are read while the current batch's pixel
+//     loads are in flight, so a batch is one round trip;
+//   * a warp walks its bins as one flat sequence of batches; the [c][bin] staging stores of a finished bin are issued
+//     after the first loads of the next bin, not before them;
+//   * a CTA starts from the geometry record in processing order (one global round trip instead of order -> geoms).
+// Arithmetic and tap order are those of roi_align_fwd_kernel<2>; results are bit-identical.
+template <int WARPS, int FLAVOUR = 0>
+__global__ void __launch_bounds__(32 * WARPS, 4)
+roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, float* __restrict__ out) {
+    constexpr int NB = 49, CAP = 16, PITCH = CAP + 1, THREADS = 32 * WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + list_bytes(NB, CAP));
+    float* s_stage = reinterpret_cast<float*>(smem_raw + list_bytes(NB, CAP) + ((NB * 4 + 15) & ~15));
+    RoiGeom g = gsorted[blockIdx.x];
+    const int roi = g.gh;                                   // processing-order record: gh carries the RoI index
+    g.gh = 2; g.gw = 2;
+    const int C = L.C, chunk0 = blockIdx.y * 256;
+    const int H = L.H[g.level], W = L.W[g.level];
+    build_tap_lists<THREADS, true>(g, L, H, W, s_list, s_cnt, s_stage, C >> 2, 0);   // the scratch (staging block) is dead after its final barrier
+
+    const float4* __restrict__ feat =
+        reinterpret_cast<const float4*>(L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0) + lane;
+    const int oct = (lane >> 3) & 3;
+    // staging slot of component j of a quad: channel 4*lane + ((j + oct) & 3) (conflict-free, see rot4); computed per bin
+    // instead of held in four registers
+    float* const sbase = s_stage + lane * 4 * NB;
+    auto stage = [&](float4 a0, float4 a1, int b) {
+        a0.x *= 0.25f; a0.y *= 0.25f; a0.z *= 0.25f; a0.w *= 0.25f;   // output_val /= count (:143), count = 4: exact
+        a1.x *= 0.25f; a1.y *= 0.25f; a1.z *= 0.25f; a1.w *= 0.25f;
+        const float4 r0 = rot4(a0, oct), r1 = rot4(a1, oct);
+        float* const sb = sbase + b;
+        float* const q0 = sb + ((0 + oct) & 3) * NB;
+        float* const q1 = sb + ((1 + oct) & 3) * NB;
+        float* const q2 = sb + ((2 + oct) & 3) * NB;
+        float* const q3 = sb + ((3 + oct) & 3) * NB;
+        q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
+        q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
+    };
+    // one batch: up to four taps = eight 16-byte loads in flight per thread; the list entries of the following batch
+    // (same bin, or the first four of this warp's next bin) are read while the loads fly
+#define RSDET_ACC(P, WT, VA, VB)                                                                                        \
+        if (P) {                                                                                                        \
+            acc0.x = fmaf(WT, VA.x, acc0.x); acc0.y = fmaf(WT, VA.y, acc0.y); acc0.z = fmaf(WT, VA.z, acc0.z); acc0.w = fmaf(WT, VA.w, acc0.w); \
+            acc1.x = fmaf(WT, VB.x, acc1.x); acc1.y = fmaf(WT, VB.y, acc1.y); acc1.z = fmaf(WT, VB.z, acc1.z); acc1.w = fmaf(WT, VB.w, acc1.w); \
+        }
+    const int2* lp = s_list + warp * PITCH;
+    int2 en0 = lp[0], en1 = lp[1], en2 = lp[2], en3 = lp[3];
+    int cnt = s_cnt[warp];
+#pragma unroll 1
+    for (int b = warp; b < NB; b += WARPS) {
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+        const int nbin = min(b + WARPS, NB - 1);
+        int ncnt = cnt;
+        int e = 0;
+#pragma unroll 1
+        do {
+            const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
+            float4 v00, v01, v10, v11, v20, v21, v30, v31;
+            if (p0) { const float* q = tap_ptr(feat, (unsigned)en0.x); v00 = ldg_flavour_v4<FLAVOUR>(q); v01 = ldg_flavour_v4<FLAVOUR>(q + 128); }
+            if (p1) { const float* q = tap_ptr(feat, (unsigned)en1.x); v10 = ldg_flavour_v4<FLAVOUR>(q); v11 = ldg_flavour_v4<FLAVOUR>(q + 128); }
+            if (p2) { const float* q = tap_ptr(feat, (unsigned)en2.x); v20 = ldg_flavour_v4<FLAVOUR>(q); v21 = ldg_flavour_v4<FLAVOUR>(q + 128); }
+            if (p3) { const float* q = tap_ptr(feat, (unsigned)en3.x); v30 = ldg_flavour_v4<FLAVOUR>(q); v31 = ldg_flavour_v4<FLAVOUR>(q + 128); }
+            const float w0 = __int_as_float(en0.y), w1 = __int_as_float(en1.y), w2 = __int_as_float(en2.y), w3 = __int_as_float(en3.y);
+            e += 4;
+            const bool more = e < cnt;
+            const int2* np = more ? lp + e : s_list + nbin * PITCH;
+            if (!more) ncnt = s_cnt[nbin];
+            en0 = np[0]; en1 = np[1]; en2 = np[2]; en3 = np[3];
+            RSDET_ACC(p0, w0, v00, v01) RSDET_ACC(p1, w1, v10, v11) RSDET_ACC(p2, w2, v20, v21) RSDET_ACC(p3, w3, v30, v31)
+        } while (e < cnt);
+        stage(acc0, acc1, b);
+        lp = s_list + nbin * PITCH;
+        cnt = ncnt;
+    }
+#undef RSDET_ACC
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * NB;
+    if ((((size_t)out) & 15) == 0 && ((C * NB) & 3) == 0) {
+        if (tid == 0) bulk_store_evict_first(dst, s_stage, 256u * NB * 4u);
+    } else {
+        for (int i = tid; i < 256 * NB; i += THREADS) __stcs(dst + i, s_stage[i]);
+    }
+}
+
 // cudaFuncSetAttribute is per device: remember what was set for each one (a process may drive several GPUs)
 static void set_dyn_smem(const void* func, size_t bytes) {
     struct Slot { const void* f; size_t b; };
@@ -693,6 +818,9 @@ static int roi_path_choice() {
 
 static bool fast_path_ok(const rsdet_roi_align_cfg* c);
 static size_t fwd_smem_bytes(const rsdet_roi_align_cfg* c);
+static bool fwd77_ok(const rsdet_roi_align_cfg* c) {
+    return c->pooled_h == 7 && c->pooled_w == 7 && c->sampling_ratio == 2 && c->channels % 256 == 0;
+}
 #ifdef RSDET_TUNING
 #include "roi_align_tuning.cuh"
 #endif
@@ -859,8 +987,10 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
     L.PH = c->pooled_h; L.PW = c->pooled_w; L.sampling_ratio = c->sampling_ratio; L.version = c->version;
     L.extend_w = c->extend_w; L.extend_h = c->extend_h; L.finest_scale = c->finest_scale;
     L.dbg_skip_main = 0;
+    L.dbg_mask = 0xffffffffu;
 #ifdef RSDET_TUNING
     if (const char* e = getenv("RSDET_ROI_DBG_SKIP_MAIN")) L.dbg_skip_main = atoi(e);
+    if (const char* e = getenv("RSDET_ROI_DBG_MASK")) L.dbg_mask = (unsigned)strtoul(e, nullptr, 0);
 #endif
     for (int l = 0; l < RSDET_MAX_LEVELS; l++) {
         L.feat[l] = nullptr; L.grad[l] = nullptr;
@@ -885,7 +1015,7 @@ using namespace rsdet;
 extern "C" size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward) {
     (void)backward;
     if (check_cfg(cfg) != RSDET_OK) return 0;
-    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1) + ws_bytes<RoiGeom>(num_rois > 0 ? num_rois : 1);  // order, geometry
+    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1) + 2 * ws_bytes<RoiGeom>(num_rois > 0 ? num_rois : 1);  // order, geometry, geometry in processing order
 #ifdef RSDET_TUNING
     if (fast_path_ok(cfg) && split_path_ok(cfg))   // tap-list records of the A/B kernels
         b += ws_bytes<unsigned char>((size_t)(num_rois > 0 ? num_rois : 1) *
@@ -924,6 +1054,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     Workspace ws(workspace, workspace_bytes);
     int* order_ws = ws.take<int>(num_rois);
     RoiGeom* geoms = ws.take<RoiGeom>(num_rois);
+    RoiGeom* gsorted = ws.take<RoiGeom>(num_rois);
     if (cfg->channels_last) {
         for (int l = 0; l < cfg->num_levels; l++) L.feat[l] = feats_host[l];
     } else {
@@ -940,17 +1071,21 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     if (getenv("RSDET_ROI_NOORDER")) order = nullptr;
 #endif
     const bool ride = !cfg->channels_last && order && num_rois <= kPrepMaxRois;
-    launch_prep(L, rois, num_rois, geoms, order, levels_out, st, ride);
+    launch_prep(L, rois, num_rois, geoms, order, levels_out, st, ride, gsorted);
     if (!cfg->channels_last) {
         // NCHW -> NHWC copy of the pyramid; the locality-order block rides along as block 0 of the same launch
-        const PrepArgs prep = {rois, num_rois, geoms, order};
+        const PrepArgs prep = {&L, rois, num_rois, order};
         float* dst[RSDET_MAX_LEVELS];
         for (int l = 0; l < cfg->num_levels; l++) dst[l] = const_cast<float*>(L.feat[l]);
         rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st,
                               ride ? &prep : nullptr);
         if (rc != RSDET_OK) return rc;
+        if (ride) launch_geometry(L, rois, num_rois, order, geoms, gsorted, levels_out, st);
     }
     size_t smem = fwd_smem_bytes(cfg);
+#ifdef RSDET_TUNING
+    if (const char* e = getenv("RSDET_ROI_PAD_SMEM")) smem += (size_t)atoi(e) * 1024;   // fewer resident CTAs per SM
+#endif
     set_dyn_smem((const void*)roi_align_fwd_kernel<1>, smem);
     set_dyn_smem((const void*)roi_align_fwd_kernel<2>, smem);
 #ifdef RSDET_TUNING
@@ -959,6 +1094,28 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         if (tuning_forward(cfg, L, ws, rois, order, geoms, num_rois, out, levels_out, st, &trc)) return trc;
     }
 #endif
+    if (fwd77_ok(cfg) && roi_path_choice() == 1) {   // the Oriented R-CNN geometry: specialised kernel
+        int warps = 7;   // one warp per bin row: 7 bins each (eight warps leave one with 7 and seven with 6 bins), 72 registers
+#ifdef RSDET_TUNING
+        if (const char* e = getenv("RSDET_ROI_WARPS")) warps = atoi(e);
+#endif
+#ifdef RSDET_TUNING
+        const int flavour = getenv("RSDET_ROI_LD") ? atoi(getenv("RSDET_ROI_LD")) : 0;
+        dim3 g77(num_rois, cfg->channels / 256);
+        if (flavour == 1) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 1>, smem); roi_align_fwd77_kernel<8, 1><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+        if (flavour == 2) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 2>, smem); roi_align_fwd77_kernel<8, 2><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+        if (flavour == 3) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 3>, smem); roi_align_fwd77_kernel<8, 3><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+#endif
+        if (warps == 7) {
+            set_dyn_smem((const void*)roi_align_fwd77_kernel<7>, smem);
+            roi_align_fwd77_kernel<7><<<dim3(num_rois, cfg->channels / 256), 224, smem, st>>>(L, gsorted, num_rois, out);
+        } else {
+            set_dyn_smem((const void*)roi_align_fwd77_kernel<8>, smem);
+            roi_align_fwd77_kernel<8><<<dim3(num_rois, cfg->channels / 256), 256, smem, st>>>(L, gsorted, num_rois, out);
+        }
+        count_launch();
+        return cuda_status();
+    }
     const int Q = quads_per_chunk(cfg->channels);
     dim3 grid(num_rois, ceil_div(cfg->channels / 4, Q));
     if (cfg->channels % 256 == 0)

@@ -70,9 +70,9 @@ for spec in a.paths.split(","):      # "<path>" or "<path>:<prefetch 0/1>" (row-
     if a.check:
         o = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
         if ref is None:
-            os.environ["RSDET_ROI_PATH"] = "1"
+            os.environ["RSDET_ROI_PATH"] = "9"      # the generic bin-major kernel
             ref = core.roi_align_rotated_forward(cfg, tiles[0][0], tiles[0][1]).clone()
-        msg += f"; max |diff| vs bin-major {float((o - ref).abs().max()):.3g} (scale {float(ref.abs().max()):.3g})"
+        msg += f"; max |diff| vs generic bin-major {float((o - ref).abs().max()):.3g} (scale {float(ref.abs().max()):.3g})"
     print(msg, flush=True)
     if prof is not None and path in (7, 8):
         prof.zero_()
