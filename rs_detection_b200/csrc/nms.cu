@@ -30,6 +30,9 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "nms_engine.cuh"
 #include "poly_iou.cuh"
@@ -1021,7 +1024,8 @@ template <int NCH, bool IDENT>  // NCH 64-word chunks per row: 1 (<= 4096 column
 __global__ void __launch_bounds__(kReduceThreads, 1)
 reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov_base,
                         int pitch_arg, int n_boxes_arg, uint8_t* __restrict__ keep_sorted, const int* __restrict__ gate,
-                        const int* __restrict__ seg_count = nullptr) {
+                        const int* __restrict__ seg_count = nullptr, int* __restrict__ keep_prefix = nullptr,
+                        int* __restrict__ kept_count = nullptr, int* __restrict__ kept_pos = nullptr) {
     if (gate && *gate == 0) return;
     extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][partials: 4 x Ts][rows: 2 x 64 x Ts][cand: n_boxes ints]
     __shared__ __align__(8) unsigned short s_col16[256];  // s_col16[4j + q]: rows i in quarter q (i < j) that suppress j
@@ -1087,6 +1091,7 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
         };
         if (nblk > 0) { fetch(0); stash(0); }
         __syncthreads();
+        int kept_run = 0;   // kept candidates of the blocks before b (fast multiclass path: exclusive prefix for the output ranks)
         for (int b = 0; b < nblk; b++) {
             const int nr = min(64, ns - b * 64);
             const unsigned long long* R = s_rows + (size_t)(b & 1) * 64 * Ts;
@@ -1146,7 +1151,15 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
             }
             __syncthreads();
             const unsigned long long kb = s_keep;
-            if (tid < nr) keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+            if (tid < nr) {
+                keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+                if (keep_prefix) {   // fast multiclass path: exclusive prefix of the keep flags and the compacted kept list
+                    const int pre = kept_run + __popcll(kb & ((1ull << tid) - 1ull));
+                    keep_prefix[st + b * 64 + tid] = pre;
+                    if ((kb >> tid) & 1ull) kept_pos[st + pre] = b * 64 + tid;
+                }
+            }
+            kept_run += __popcll(kb);
             {
                 // partial ORs: row group rg = tid / 64 covers 16 rows, lane column w (+64 for the second chunk)
                 const int jj = tid & 63, rg = tid >> 6;
@@ -1168,6 +1181,7 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
                 s_remv[w] |= s_part[w] | s_part[Ts + w] | s_part[2 * Ts + w] | s_part[3 * Ts + w];
             __syncthreads();  // next block's rows and this block's ORs are in place
         }
+        if (kept_count && tid == 0) kept_count[s] = kept_run;
     }
 }
 
@@ -1623,6 +1637,12 @@ static void launch_ov_matrix(const float* shared_boxes, int nb, float thr, bool 
         }
 }
 
+// cudaFuncSetAttribute is per device and the library may drive several GPUs from several host threads: set the
+// attribute on every call (it is a cheap driver call) instead of caching it in a process-wide flag
+static inline void allow_dyn_smem(const void* func, size_t bytes) {
+    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     const int n = a.n_max;
     if (n < 0 || a.kind < 0 || a.kind > RSDET_NMS_HBB_P1_F64) return RSDET_EINVAL;
@@ -1726,13 +1746,9 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
         RBox* sb = (RBox*)boxes;
         const size_t mask_cap = a.mask_words ? a.mask_words : N * ((N + 63) / 64);
         launch_ov_matrix(a.shared_boxes, nb, (float)a.thr, a.kind == RSDET_NMS_ROTATED_GE, sb, mask, mask_cap, cnt_scratch, st);
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaFuncSetAttribute(reduce_ov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(reduce_ov_staged_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(reduce_ov_staged_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr2 = true;
-        }
+        allow_dyn_smem((const void*)reduce_ov_kernel, 200 * 1024);
+        allow_dyn_smem((const void*)reduce_ov_staged_kernel<1, false>, 200 * 1024);
+        allow_dyn_smem((const void*)reduce_ov_staged_kernel<2, false>, 200 * 1024);
         const size_t Ts = (size_t)(Tov | 1);
         const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)nb;
         if (Tov <= 64 && staged <= 200 * 1024)
@@ -1813,12 +1829,8 @@ int nms_run(const NmsArgs& a, void* workspace, size_t workspace_bytes, cudaStrea
     // 5. greedy scan
     {
         size_t smem = sizeof(unsigned long long) * ((N + 63) / 64);
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(reduce_ov_staged_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_done = true;
-        }
+        allow_dyn_smem((const void*)reduce_kernel, 200 * 1024);
+        allow_dyn_smem((const void*)reduce_ov_staged_kernel<2, true>, 200 * 1024);
         // groups of < kCoopMinBlocks blocks: staged scan (rows through shared memory); larger ones: cooperative phase
         const size_t Tmax = (size_t)(kCoopMinBlocks - 1) | 1;
         reduce_ov_staged_kernel<2, true><<<kNumSMs, kReduceThreads, sizeof(unsigned long long) * (5 * Tmax + 2 * 64 * Tmax), st>>>(
@@ -2034,6 +2046,245 @@ extern "C" int rsdet_nms(int kind, const void* dets, const void* scores, const i
 }
 
 // every class holds at most n candidates -> the block-sparse mask needs at most C * n * ceil(n/64) words
+// ----------------------------------------------------------------------------- multiclass_nms_rotated, fast path
+// Class-agnostic boxes, n <= 8192 (every Oriented R-CNN test config): the generic engine's front end -- expand to n x C
+// candidates, two device-wide radix sorts (score, then label) over all of them, a segment table -- and its back end --
+// scatter to a keep mask, two stream compactions, the output gather -- were 20 launches of mostly latency (78 us of
+// library sort / select kernels per tile in the round-1 launch list).  Here:
+//   mc_class_sort_kernel   one CTA per class: the class's valid candidates as 64-bit keys (descending score, then
+//                          candidate index) sorted in shared memory (bitonic, <= 8192 keys), written as a fixed-stride
+//                          segment (class c at c*n) -> no expand, no device-wide sort, no segment kernel;
+//   launch_ov_matrix       the shared decision matrix (unchanged);
+//   reduce_ov_staged_kernel  the per-class scan (unchanged) also emits the exclusive prefix of its keep flags;
+//   mc_fast_output_kernel  rank of a kept candidate in the global score order = sum over classes of the kept candidates
+//                          with a smaller key (one binary search per class, lanes = classes) -> written straight to its
+//                          output row; no keep mask, no compaction.
+// Same keys, same tie rule (lower candidate index first), same decisions: results are identical to the generic engine's.
+constexpr int kMcFastMaxBoxes = 8192;
+constexpr int kMcFastMaxClasses = 4096;
+
+__global__ void __launch_bounds__(1024)
+mc_class_sort_kernel(const float* __restrict__ scores, const float* __restrict__ factors, int n, int C, float score_thr,
+                     unsigned long long* __restrict__ skey, int* __restrict__ idx_ls, int* __restrict__ seg_count, SegTable tb) {
+    // keys (descending-score bits) and box indices live in two shared arrays (6 bytes per candidate instead of one 64-bit
+    // word: the bitonic network is bound by shared-memory bandwidth); n <= 8192 -> 32 KB + 16 KB
+    extern __shared__ unsigned int s_k32[];          // [Pmax] keys, then [Pmax] unsigned short box indices
+    __shared__ int s_warp_cnt[32], s_base;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int Pmax = 64;
+    while (Pmax < n) Pmax <<= 1;
+    unsigned short* s_i16 = reinterpret_cast<unsigned short*>(s_k32 + Pmax);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    // valid candidates of this class, compacted in index order (ballot ranks; rounds of 1024 boxes)
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        bool valid = false;
+        float sc = 0.f;
+        if (i < n) {
+            sc = scores[(size_t)i * (C + 1) + c + 1];
+            valid = sc > score_thr;                  // nms_rotated.py:562-570: the threshold sees the raw score
+            if (valid && factors) sc = sc * factors[i];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;                         // candidates of earlier rounds
+        for (int w = 0; w < warp; w++) before += s_warp_cnt[w];
+        if (valid) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            s_k32[pos] = desc_key(sc);
+            s_i16[pos] = (unsigned short)i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; w++) t += s_warp_cnt[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    const int cnt = s_base;
+    int P = 2;
+    while (P < cnt) P <<= 1;                         // the network covers the valid candidates only
+    for (int q = cnt + tid; q < P; q += 1024) { s_k32[q] = 0xffffffffu; s_i16[q] = 0xffffu; }   // padding sorts last
+    __syncthreads();
+    // bitonic network.  A warp owns a chunk of P/32 (>= 64) consecutive elements: steps whose partner distance j stays
+    // inside the chunk need only a warp barrier (58 of the 78 steps of a 4096-key sort); steps that cross chunks are
+    // framed by block barriers.
+    const int chunk = P >= 2048 ? P >> 5 : 64, pairs = chunk >> 1, active_warps = P >= 64 ? P / chunk : 1;
+    auto exchange = [&](int t, int j, int k) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+        const unsigned int ka = s_k32[i], kb = s_k32[l];
+        const unsigned short ia = s_i16[i], ib = s_i16[l];
+        const bool gt = ka > kb || (ka == kb && ia > ib);   // equal scores: lower box index first
+        if (gt == ((i & k) == 0)) { s_k32[i] = kb; s_k32[l] = ka; s_i16[i] = ib; s_i16[l] = ia; }
+    };
+    for (int k = 2; k <= P; k <<= 1) {
+        int j = k >> 1;
+        if (j >= chunk) {
+            __syncthreads();                                 // the previous phase ended with warp-local steps
+            for (; j >= chunk; j >>= 1) {
+                for (int t = tid; t < (P >> 1); t += 1024) exchange(t, j, k);
+                __syncthreads();
+            }
+        }
+        if (warp < active_warps)
+            for (; j > 0; j >>= 1) {
+                for (int u = lane; u < pairs && warp * pairs + u < (P >> 1); u += 32) exchange(warp * pairs + u, j, k);
+                __syncwarp();
+            }
+    }
+    __syncthreads();
+    for (int q = tid; q < cnt; q += 1024) {
+        const unsigned e = (unsigned)s_i16[q] * (unsigned)C + (unsigned)c;       // candidate index in the n x C expansion
+        skey[(size_t)c * n + q] = ((unsigned long long)s_k32[q] << 32) | e;
+        idx_ls[(size_t)c * n + q] = (int)e;
+    }
+    if (tid == 0) {
+        seg_count[c] = cnt;
+        tb.seg_start[c] = c * n;
+        if (c == 0) tb.hdr[0] = C;
+        if (c == C - 1) tb.seg_start[C] = C * n;
+    }
+}
+
+// one warp per kept candidate (class cs, r-th kept): lanes = classes, each does one binary search
+__global__ void __launch_bounds__(256)
+mc_fast_output_kernel(const float* __restrict__ bboxes, const float* __restrict__ scores, const float* __restrict__ factors, int n, int C,
+                      const unsigned long long* __restrict__ skey, const int* __restrict__ seg_count, const int* __restrict__ kept_pos,
+                      const int* __restrict__ keep_prefix, const int* __restrict__ kept_count, int max_num,
+                      float* __restrict__ out_dets, int32_t* __restrict__ out_labels, int32_t* __restrict__ out_count) {
+    const int lane = threadIdx.x & 31;
+    const int cs = blockIdx.y, r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= kept_count[cs] && !(r == 0 && cs == 0)) return;
+    int nk = 0;
+    for (int c2 = lane; c2 < C; c2 += 32) nk += kept_count[c2];
+    for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    int cnt = nk;
+    if (nk > max_num) cnt = max_num >= 0 ? max_num : max(nk + max_num, 0);   // python inds[:max_num]
+    if (r == 0 && cs == 0 && lane == 0) *out_count = cnt;
+    if (r >= kept_count[cs]) return;
+    const int qs = kept_pos[(size_t)cs * n + r];
+    const unsigned long long key = skey[(size_t)cs * n + qs];
+    int rank = 0;
+    for (int c2 = lane; c2 < C; c2 += 32) {
+        if (c2 == cs) { rank += r; continue; }
+        const unsigned long long* kk = skey + (size_t)c2 * n;
+        const int len = seg_count[c2];
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (kk[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo < len ? keep_prefix[(size_t)c2 * n + lo] : kept_count[c2];
+    }
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (rank < cnt && lane < 7) {
+        const int e = (int)(unsigned)(key & 0xffffffffull), i = e / C;
+        if (lane < 5) out_dets[(size_t)rank * 6 + lane] = bboxes[(size_t)i * 5 + lane];
+        else if (lane == 5) {
+            float sc = scores[(size_t)i * (C + 1) + cs + 1];
+            if (factors) sc = sc * factors[i];
+            out_dets[(size_t)rank * 6 + 5] = sc;
+        } else out_labels[rank] = cs;
+    }
+}
+
+// The class sort (C CTAs) and the decision matrix (thousands of CTAs) are independent until the scan: the sort runs on a
+// side stream forked from the caller's stream and joined before the scan (events only -- also valid while the caller's
+// stream is being captured into a CUDA graph: the side stream joins the capture at the fork and leaves it at the join).
+// One lane per (device, caller stream); calls on one stream are issued by one host thread at a time, lanes are created
+// under a mutex.
+struct SideLane { cudaStream_t side; cudaEvent_t fork, join; };
+static SideLane* side_lane(cudaStream_t user) {
+    struct Key { int dev; cudaStream_t st; SideLane lane; };
+    static std::vector<Key>* lanes = new std::vector<Key>();
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& k : *lanes)
+        if (k.dev == dev && k.st == user) return &k.lane;
+    if (lanes->size() >= 256) return nullptr;            // callers that churn through streams fall back to one stream
+    if (lanes->capacity() < 256) lanes->reserve(256);   // pointers into the vector stay valid
+    Key k;
+    k.dev = dev; k.st = user;
+    if (cudaStreamCreateWithFlags(&k.lane.side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&k.lane.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&k.lane.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    lanes->push_back(k);
+    return &lanes->back().lane;
+}
+
+static bool mc_force_generic() {   // A/B builds only: RSDET_MC_GENERIC=1 keeps the generic engine for this entry point
+#ifdef RSDET_TUNING
+    return getenv("RSDET_MC_GENERIC") != nullptr;
+#else
+    return false;
+#endif
+}
+static bool mc_fast_ok(int bbox_dim, int n, int C) {
+    return bbox_dim == 5 && n >= 1 && n <= kMcFastMaxBoxes && C <= kMcFastMaxClasses;
+}
+static size_t mc_mask_words(int n, int num_classes);
+
+static int mc_fast_run(const float* bboxes, const float* scores, int n, int C, float score_thr, float iou_thr, int max_num,
+                       const float* factors, float* out_dets, int32_t* out_labels, int32_t* out_count, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+    const size_t cap = (size_t)n * C;
+    Workspace ws(workspace, workspace_bytes);
+    unsigned long long* skey = ws.take<unsigned long long>(cap);
+    int* idx_ls = ws.take<int>(cap);
+    uint8_t* keep_sorted = ws.take<uint8_t>(cap);
+    int* keep_prefix = ws.take<int>(cap);
+    int* kept_pos = ws.take<int>(cap);
+    int* seg_count = ws.take<int>(C);
+    int* kept_count = ws.take<int>(C);
+    int* cnt_scratch = ws.take<int>(64);
+    SegTable tb;
+    tb.hdr = ws.take<int>(64);
+    tb.seg_start = ws.take<int>((size_t)C + 2);
+    tb.tile_pref = nullptr; tb.mask_off = nullptr; tb.seg_thr = nullptr;
+    RBox* sb = ws.take<RBox>(n);
+    const size_t mask_cap = mc_mask_words(n, C);
+    unsigned long long* mask = ws.take<unsigned long long>(mask_cap);
+    if (!ws.ok()) return RSDET_EWORKSPACE;
+    int P = 64;
+    while (P < n) P <<= 1;
+    const size_t sort_smem = (sizeof(unsigned int) + sizeof(unsigned short)) * (size_t)P;
+    allow_dyn_smem((const void*)mc_class_sort_kernel, sort_smem);
+    SideLane* sl = side_lane(st);
+    if (sl && cudaEventRecord(sl->fork, st) == cudaSuccess && cudaStreamWaitEvent(sl->side, sl->fork, 0) == cudaSuccess) {
+        mc_class_sort_kernel<<<C, 1024, sort_smem, sl->side>>>(scores, factors, n, C, score_thr, skey, idx_ls, seg_count, tb);
+        cudaEventRecord(sl->join, sl->side);
+    } else {
+        cudaGetLastError();
+        sl = nullptr;
+        mc_class_sort_kernel<<<C, 1024, sort_smem, st>>>(scores, factors, n, C, score_thr, skey, idx_ls, seg_count, tb);
+    }
+    const int Tov = (n + 63) / 64, pitch = (Tov + 1) & ~1;
+    launch_ov_matrix(bboxes, n, iou_thr, false, sb, mask, mask_cap, cnt_scratch, st);
+    if (sl) cudaStreamWaitEvent(st, sl->join, 0);
+    const size_t Ts = (size_t)(Tov | 1);
+    const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)n;
+    const int grid = C < kNumSMs ? C : kNumSMs;
+    if (Tov <= 64) {
+        allow_dyn_smem((const void*)reduce_ov_staged_kernel<1, false>, 200 * 1024);
+        reduce_ov_staged_kernel<1, false><<<grid, kReduceThreads, staged, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, nullptr, seg_count,
+                                                                              keep_prefix, kept_count, kept_pos);
+    } else {
+        allow_dyn_smem((const void*)reduce_ov_staged_kernel<2, false>, 200 * 1024);
+        reduce_ov_staged_kernel<2, false><<<grid, kReduceThreads, staged, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, nullptr, seg_count,
+                                                                              keep_prefix, kept_count, kept_pos);
+    }
+    mc_fast_output_kernel<<<dim3((unsigned)((n + 7) / 8), (unsigned)C), 256, 0, st>>>(bboxes, scores, factors, n, C, skey, seg_count, kept_pos,
+                                                                                     keep_prefix, kept_count, max_num, out_dets, out_labels,
+                                                                                     out_count);
+    count_launch(8);
+    return cuda_status();
+}
+
 static size_t mc_mask_words(int n, int num_classes) {
     size_t N = (size_t)(n > 0 ? n : 1);
     return (size_t)(num_classes > 0 ? num_classes : 1) * N * ((N + 63) / 64 + 1);  // + 1: the shared matrix uses an even row pitch
@@ -2063,6 +2314,9 @@ extern "C" int rsdet_multiclass_nms_rotated(const float* multi_bboxes, int bbox_
     if (capll > (1 << 20) || n > kMaxNmsBoxes) return RSDET_ELIMIT;
     int cap = (int)capll;
     if (workspace_bytes < rsdet_multiclass_nms_rotated_workspace_bytes(n, num_classes)) return RSDET_EWORKSPACE;
+    if (mc_fast_ok(bbox_dim, n, num_classes) && !mc_force_generic())
+        return mc_fast_run(multi_bboxes, multi_scores, n, num_classes, score_thr, iou_thr, max_num, score_factors, out_dets, out_labels,
+                           out_count, workspace, workspace_bytes, st);
     Workspace ws(workspace, workspace_bytes);
     float* cbox = ws.take<float>((size_t)cap * 5);
     float* cscore = ws.take<float>(cap);

@@ -299,7 +299,7 @@ constexpr int kBuckets = RSDET_MAX_LEVELS * kCellsPerAxis * kCellsPerAxis;
 constexpr int kPrepMaxRois = 16384;
 template <int THREADS>
 __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* __restrict__ rois, int K,
-                                                int* __restrict__ order, int* s_hist, int* s_warp) {
+                                                int* __restrict__ order, int* s_hist, int* s_warp, unsigned short* s_bkt, int bkt_cap) {
     const int tid = threadIdx.x;
     for (int i = tid; i < kBuckets; i += THREADS) s_hist[i] = 0;
     __syncthreads();
@@ -309,9 +309,11 @@ __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* 
         if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
         return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
     };
-    for (int i = tid; i < K; i += THREADS) {
+    for (int i = tid; i < K; i += THREADS) {   // s_bkt: the buckets of the first bkt_cap RoIs are kept for the scatter pass
         const float* r = rois + (size_t)i * 6;
-        atomicAdd(&s_hist[bucket_of(r, roi_level(r, L))], 1);
+        const int bkt = bucket_of(r, roi_level(r, L));
+        if (i < bkt_cap) s_bkt[i] = (unsigned short)bkt;
+        atomicAdd(&s_hist[bkt], 1);
     }
     __syncthreads();
     // exclusive scan of kBuckets counters, kBuckets / THREADS consecutive ones per thread
@@ -336,7 +338,8 @@ __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* 
     __syncthreads();
     for (int i = tid; i < K; i += THREADS) {
         const float* r = rois + (size_t)i * 6;
-        order[atomicAdd(&s_hist[bucket_of(r, roi_level(r, L))], 1)] = i;
+        const int bkt = i < bkt_cap ? (int)s_bkt[i] : bucket_of(r, roi_level(r, L));
+        order[atomicAdd(&s_hist[bkt], 1)] = i;
     }
 }
 
@@ -393,7 +396,10 @@ __global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, L
     static_assert(sizeof(float) * 64 * 65 >= sizeof(int) * (kBuckets + 32), "the prep block borrows the transpose tile");
     if (blockIdx.x == 0) {
         int* s_hist = reinterpret_cast<int*>(&tile[0][0]);
-        roi_order_block<256>(L, rois, K, order, s_hist, s_hist + kBuckets);
+        static_assert(kBuckets <= 65536, "bucket ids are cached as unsigned short");
+        unsigned short* s_bkt = reinterpret_cast<unsigned short*>(s_hist + kBuckets + 32);
+        const int bkt_cap = (int)((sizeof(float) * 64 * 65 - sizeof(int) * (kBuckets + 32)) / sizeof(unsigned short));
+        roi_order_block<256>(L, rois, K, order, s_hist, s_hist + kBuckets, s_bkt, bkt_cap);
         return;
     }
     transpose_tile<true>(job, blockIdx.x - 1, tile);
