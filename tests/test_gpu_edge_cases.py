@@ -100,3 +100,38 @@ def test_multiclass_dense_cluster_overflows_pair_queue(cuda, oracle):
     want_d, want_l = oracle.multiclass_nms_rotated(b, s, 0.01, dict(iou_thr=0.6), 1000)
     assert np.array_equal(got_d.cpu().numpy(), want_d) and np.array_equal(got_l.cpu().numpy(), want_l)
     assert 0 < want_d.shape[0] < 1000
+
+
+@pytest.mark.parametrize("n,C", [(8192, 3), (8193, 2), (63, 5), (1, 4)])
+def test_multiclass_fast_path_boundaries(cuda, oracle, n, C):
+    """The fast multiclass path (class-agnostic boxes, n <= 8192: per-class shared-memory sort, fixed-stride segments,
+    rank-by-binary-search output) at its limits: 8192 boxes = the two-chunk staged scan and the largest in-CTA sort,
+    8193 = first size handled by the generic engine, and sizes below one scan block.  Classes with no candidate, score
+    factors and the max_num quirk included."""
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    bb = W.rotated_boxes(n, 77, canvas=2048 if n > 1000 else 256, smin=16, smax=120)
+    sc = W.class_scores(n, C, 5, logit_scale=1.5)
+    sc[:, 2] = 0.0                                    # class 1 has no candidate above the threshold
+    fac = np.random.default_rng(4).uniform(0.5, 1.0, n).astype(np.float32)
+    for max_num, sf in ((-1, None), (100, fac), (10 ** 6, None)):
+        wd, wl = oracle.multiclass_nms_rotated(bb, sc, 0.05, dict(iou_thr=0.1), max_num, sf)
+        gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 0.05, dict(type='nms_rotated', iou_thr=0.1), max_num,
+                                        None if sf is None else _t(sf))
+        assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+
+
+def test_multiclass_fast_path_score_ties(cuda, oracle):
+    """Quantised scores: many exact ties inside a class and across classes.  Inside a class the lower box index goes
+    first (the keep set depends on it); the output order of tied scores follows the candidate index (box * C + class),
+    like the generic engine's stable sort -- compared with the oracle as sets per score value."""
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    n, C = 3000, 6
+    bb = W.rotated_boxes(n, 21, canvas=1024, smin=16, smax=100)
+    sc = np.round(W.class_scores(n, C, 11, logit_scale=1.0), 2).astype(np.float32)
+    wd, wl = oracle.multiclass_nms_rotated(bb, sc, 0.05, dict(iou_thr=0.1), 10 ** 6)
+    gd, gl = multiclass_nms_rotated(_t(bb), _t(sc), 0.05, dict(type='nms_rotated', iou_thr=0.1), 10 ** 6)
+    gd, gl = gd.cpu().numpy(), gl.cpu().numpy()
+    assert gd.shape == wd.shape and len(np.unique(wd[:, 5])) < 120
+    assert np.all(np.diff(gd[:, 5]) <= 0)
+    rows = lambda d, l: sorted(map(tuple, np.concatenate([d, l[:, None].astype(np.float32)], 1).tolist()))
+    assert rows(gd, gl) == rows(wd, wl)
