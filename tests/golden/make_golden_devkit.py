@@ -7,6 +7,8 @@ from /root/reference, nothing copied:
                                                mergebyrec                                            (rows a11, a12)
     tools/merge_results.py                     merge_file, merge_files                               (row a13)
     python/jdet/data/devkits/voc_eval.py       voc_eval_dota, voc_ap                                 (row f3)
+    python/jdet/data/devkits/data_merge.py     flip_box, prepare_data (the before_nms writer), data_merge
+                                               (= prepare_data + mergebypoly through its 16-process pool)   (row f4)
 
 Their third-party imports are played by shims: `jittor` by tests/jittor_shim, `shapely.geometry.Polygon` by
 tests/shapely_shim (exact rational quadrilateral clipping rounded once to float64 -- GEOS itself is not installable;
@@ -73,6 +75,12 @@ RM = load("jdet.data.devkits.result_merge", os.path.join(REF, "data/devkits/resu
 load("jdet.data.devkits.dota_to_fair", os.path.join(REF, "data/devkits/dota_to_fair.py"))
 VE = load("jdet.data.devkits.voc_eval", os.path.join(REF, "data/devkits/voc_eval.py"))
 MR = load("ref_tools_merge_results", os.path.join(REFROOT, "tools/merge_results.py"))
+load("jdet.config.constant", os.path.join(REF, "config/constant.py"))
+load("jdet.models.boxes.box_ops", os.path.join(REF, "models/boxes/box_ops.py"))
+if not hasattr(jt, "load"):
+    import pickle
+    jt.load = lambda path: pickle.load(open(path, "rb"))     # jt.load of a results pickle
+DM = load("jdet.data.devkits.data_merge", os.path.join(REF, "data/devkits/data_merge.py"))
 
 g = {}
 
@@ -129,6 +137,25 @@ with tempfile.TemporaryDirectory() as tmp:
     dst = os.path.join(tmp, "tool_out")
     MR.merge_files(os.path.join(tmp, "after_nms_0"), dst, nms_thr=0.05, process_num=1)
     g["tool_merge_files_thr005"] = json.dumps(read_dir(dst))
+
+# ---- data_merge.py: the runner's result list -> before_nms text -> merged files (prepare_data :29-48, data_merge :50-54)
+with tempfile.TemporaryDirectory() as tmp:
+    import pickle
+    res2 = W.tile_results(150, 10, 2400, 2, seed=9)
+    # flipped tiles: `w - box[i]` (data_merge.py:14-27) is float64 arithmetic under the reference's NumPy 1.x (python int
+    # with a float32 scalar) and float32 arithmetic under NumPy >= 2 (NEP 50) -- this container has NumPy 2.  The
+    # flipped tiles therefore carry coordinates on a 1/16 grid, where both are exact; product and oracle follow the
+    # NumPy 1.x rule (float64) for anything else.
+    for t, mode in ((3, "H"), (5, "HV")):
+        (polys, sc, lab), target = res2[t]
+        res2[t] = ((np.round(polys * 16) / 16).astype(np.float32), sc, lab), dict(target, flip_mode=mode, ori_img_size=(1024, 1024))
+    pickle.dump(res2, open(os.path.join(tmp, "res.pkl"), "wb"))
+    g["results_pkl"] = np.frombuffer(pickle.dumps(res2), np.uint8)
+    CFG.merge_nms_threshold_type = 0
+    DM.data_merge(os.path.join(tmp, "res.pkl"), os.path.join(tmp, "before"), os.path.join(tmp, "after"), "FAIR1M_1_5")
+    g["dm_before_nms"] = json.dumps(read_dir(os.path.join(tmp, "before")))
+    g["dm_after_nms"] = json.dumps(read_dir(os.path.join(tmp, "after")))
+    g["dm_classes"] = json.dumps(list(sys.modules["jdet.config.constant"].get_classes_by_name("FAIR1M_1_5")))
 
 # ---- array level: keep lists + decision margins
 d = []

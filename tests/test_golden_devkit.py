@@ -86,3 +86,22 @@ def test_oracle_voc_eval_vs_reference(oracle, g, thr):
     assert np.array_equal(rec, g["voc_%g_area_rec" % thr]) and np.array_equal(prec, g["voc_%g_area_prec" % thr])
     assert voc_ap(rec, prec, False) == float(g["voc_%g_area_ap" % thr])
     assert voc_ap(rec, prec, True) == float(g["voc_%g_07_ap" % thr])
+
+
+def test_before_nms_writer_vs_reference(tmp_path, g):
+    """data_merge.prepare_data (data_merge.py:29-48) was RUN on a pickled result list (incl. H and HV flipped tiles):
+    the oracle's writer and the product's host-side writer reproduce its files byte for byte."""
+    import pickle
+    import workloads as W
+    from rs_detection_b200.jdet.data.devkits.data_merge import get_classes_by_name, prepare_data
+    res = pickle.loads(g["results_pkl"].tobytes())
+    classes = json.loads(str(g["dm_classes"]))
+    assert classes == list(W.FAIR1M_CLASSES) == list(get_classes_by_name("FAIR1M_1_5"))
+    F.write_before_nms(res, tmp_path / "o", classes)
+    assert _read(tmp_path / "o") == json.loads(str(g["dm_before_nms"]))
+    prepare_data(res, tmp_path / "p", classes)
+    assert _read(tmp_path / "p") == json.loads(str(g["dm_before_nms"]))
+    # and the merge of those files (the reference ran mergebypoly through its 16-process pool)
+    for f in os.listdir(tmp_path / "o"):
+        F.mergesingle(tmp_path / "m", str(tmp_path / "o" / f))
+    assert _read(tmp_path / "m") == json.loads(str(g["dm_after_nms"]))

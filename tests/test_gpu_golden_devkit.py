@@ -71,3 +71,14 @@ def test_voc_eval_vs_reference(cuda, g, thr):
     assert np.array_equal(rec, g["voc_%g_area_rec" % thr]) and np.array_equal(prec, g["voc_%g_area_prec" % thr])
     assert ap == float(g["voc_%g_area_ap" % thr])
     assert voc_eval_dota(g["voc_dets"], gts, None, thr, True)[2] == float(g["voc_%g_07_ap" % thr])
+
+
+def test_data_merge_vs_reference(cuda, tmp_path, g):
+    """data_merge.data_merge (data_merge.py:50-54) end to end: result list -> before_nms -> after_nms, against the files
+    the reference's own data_merge wrote."""
+    import pickle
+    from rs_detection_b200.jdet.data.devkits.data_merge import data_merge
+    res = pickle.loads(g["results_pkl"].tobytes())
+    data_merge(res, str(tmp_path / "before"), str(tmp_path / "after"), "FAIR1M_1_5")
+    assert _read(tmp_path / "before") == json.loads(str(g["dm_before_nms"]))
+    assert _read(tmp_path / "after") == json.loads(str(g["dm_after_nms"]))
