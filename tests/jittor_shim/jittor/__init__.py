@@ -53,6 +53,13 @@ class Var(torch.Tensor):
         dim = kw.get("dims", dim)
         return torch.Tensor.min(self) if dim is None else torch.Tensor.min(self, dim=dim, keepdim=keepdims)[0]
 
+    def argsort(self, dim=-1, descending=False):
+        v, i = torch.sort(self, dim=dim, descending=descending, stable=True)   # Jittor: (index, sorted values); ties: lower index first
+        return _v(i), _v(v)
+
+    def astype(self, dtype):
+        return _v(self.to(_dt(dtype)))
+
     def clamp(self, min_v=None, max_v=None):
         return torch.Tensor.clamp(self, min=min_v, max=max_v)
 
@@ -145,6 +152,12 @@ def full(shape, val, dtype=None):
     if dtype is None:
         dtype = torch.int32 if isinstance(val, int) else torch.float32
     return Var(torch.full(tuple(shape), val, dtype=_dt(dtype)))
+
+
+def arange(start=0, end=None, step=1, dtype=None):
+    if end is None:
+        start, end = 0, start
+    return _v(torch.arange(start, end, step, dtype=_dt(dtype)))
 
 
 def zeros_like(x):
