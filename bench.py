@@ -419,8 +419,14 @@ def run_ours(args, rank, world, local_rank):
     ms_ext = timed(lambda: [core.roi_align_rotated_forward(cfg, f, r, out=out_buf) for f, r, _, _ in tiles], reps) / TILES_PER_GPU
     ms_nms = timed(lambda: [core.multiclass_nms_rotated(b, s, SCORE_THR, IOU_THR, MAX_NUM) for _, _, b, s in tiles], reps) / TILES_PER_GPU
     feats_cl = [[core.nchw_to_nhwc(f) for f in fs] for fs, _, _, _ in tiles]
-    ms_fwd_kernel = timed(lambda: [core.roi_align_rotated_forward(cfg_cl, fcl, t[1], out=out_buf) for fcl, t in zip(feats_cl, tiles)],
-                          reps) / TILES_PER_GPU
+    ms_fwd_call = timed(lambda: [core.roi_align_rotated_forward(cfg_cl, fcl, t[1], out=out_buf) for fcl, t in zip(feats_cl, tiles)],
+                        reps) / TILES_PER_GPU              # geometry + order + gather kernels of a channels-last call
+    # the gather kernel alone: events recorded by the library around that kernel on its own stream, the 8 distinct tiles
+    # cycled (713 MB of pyramids > L2), averaged over every launch
+    for fcl, t in zip(feats_cl, tiles):
+        core.roi_gather_kernel_ms(cfg_cl, fcl, t[1], out_buf)
+    ks = [core.roi_gather_kernel_ms(cfg_cl, fcl, t[1], out_buf) for _ in range(reps) for fcl, t in zip(feats_cl, tiles)]
+    ms_fwd_kernel = float(np.mean(ks))
     # training-side figures (config 3): fwd+bwd on 512 sampled RoIs, IoU 512x2000 + assignment
     rois512 = tiles[0][1][:512].contiguous()
     gout = torch.randn((512, W.CHANNELS, 7, 7), device=dev)
@@ -457,9 +463,10 @@ def run_ours(args, rank, world, local_rank):
     U = float(np.mean([touched_pixels(t[1]) for t in tiles_np[:2]]))
     algo_bytes = 4.0 * K_ROIS * W.CHANNELS * 49 + 24.0 * K_ROIS + 4.0 * W.CHANNELS * U
     achieved = algo_bytes / (ms_fwd_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "roi_align_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "roi_align_fwd77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": ms_fwd_kernel, "touched_pixels": U}
+                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": ms_fwd_kernel, "launches_timed": len(ks),
+                "call_ms_with_geometry_and_order_kernels": ms_fwd_call, "touched_pixels": U}
     prof = os.path.join(ROOT, "profiles", "roi_fwd_traffic.json")
     if os.path.exists(prof):
         try:
@@ -612,7 +619,7 @@ def run_ours(args, rank, world, local_rank):
             "components": {
                 "merge": merge_comp, "fp32": fp32,
                 "roi_extractor_fwd_ms_per_tile": ms_ext, "roi_extractor_fwd_rois_per_s": K_ROIS / (ms_ext * 1e-3),
-                "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel,
+                "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel, "roi_fwd_call_channels_last_ms_per_tile": ms_fwd_call,
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
                 "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3),

@@ -145,6 +145,12 @@ int rsdet_roi_align_rotated_backward(const rsdet_roi_align_cfg* cfg, const float
                                      int num_rois, float* const* grad_feats_host, void* workspace,
                                      size_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's roofline): arm two cudaEvent_t (created with timing enabled by the caller).  The NEXT
+ * rsdet_roi_align_rotated_forward call issued by this host thread records `start_event` right before and `stop_event`
+ * right after its gather kernel on the call's stream (the geometry / order / transpose kernels of the call stay outside),
+ * then disarms.  Pass NULLs to disarm.  No reference counterpart. */
+int rsdet_roi_align_profile_events(void* start_event, void* stop_event);
+
 /* NCHW <-> NHWC transposes of one fp32 map (exposed so a caller can keep a channels-last pyramid). */
 int rsdet_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream);
 int rsdet_nhwc_to_nchw(const float* src, int n, int c, int h, int w, float* dst, void* stream);

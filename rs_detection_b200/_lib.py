@@ -72,6 +72,7 @@ SIGNATURES = {
     "rsdet_rpn_proposals_workspace_bytes": (C.c_size_t, [C.POINTER(RpnCfg)]),
     "rsdet_rpn_proposals": (C.c_int, [C.POINTER(RpnCfg), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, C.c_size_t, _vp]),
+    "rsdet_roi_align_profile_events": (C.c_int, [_vp, _vp]),
     "rsdet_nchw_to_nhwc": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rsdet_nhwc_to_nchw": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
 }

@@ -291,6 +291,17 @@ def roi_align_rotated_forward(cfg: RoiAlignCfg, feats: Sequence[torch.Tensor], r
     return (out, lv) if want_levels else out
 
 
+def roi_gather_kernel_ms(cfg: RoiAlignCfg, feats: Sequence[torch.Tensor], rois: torch.Tensor, out: torch.Tensor) -> float:
+    """Duration (ms) of the gather kernel alone of one forward call: CUDA events recorded by the library right before
+    and after that kernel on the launching stream (`rsdet_roi_align_profile_events`).  Synchronises."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); b.record()                       # materialise the cudaEvent_t handles
+    check(load().rsdet_roi_align_profile_events(C.c_void_p(a.cuda_event), C.c_void_p(b.cuda_event)), "roi_align_profile_events")
+    roi_align_rotated_forward(cfg, feats, rois, out=out)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)
+
+
 def roi_align_rotated_backward(cfg: RoiAlignCfg, grad_out: torch.Tensor, rois: torch.Tensor, feat_shapes):
     g = _f32(grad_out)
     r = _f32(rois)

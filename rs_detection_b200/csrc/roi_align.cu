@@ -359,10 +359,19 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
         if (cy & 1) cx = kCellsPerAxis - 1 - cx;
         return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
     };
-    for (int i = tid; i < K; i += 1024) {
+    int cached[4] = {0, 0, 0, 0};   // buckets of this thread's first four RoIs: the scatter pass reloads nothing for K <= 4096
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int i = tid + 1024 * c;
+        if (i < K) {
+            int lvl;
+            cached[c] = bucket_of(i, lvl);
+            atomicAdd(&s_hist[cached[c]], 1);
+        }
+    }
+    for (int i = tid + 4096; i < K; i += 1024) {
         int lvl;
-        int bkt = bucket_of(i, lvl);
-        atomicAdd(&s_hist[bkt], 1);
+        atomicAdd(&s_hist[bucket_of(i, lvl)], 1);
     }
     __syncthreads();
     // exclusive scan of kBuckets (=2048) counters: 2 per thread
@@ -382,7 +391,12 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     s_hist[2 * tid] = excl;
     s_hist[2 * tid + 1] = excl + a0;
     __syncthreads();
-    for (int i = tid; i < K; i += 1024) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int i = tid + 1024 * c;
+        if (i < K) order[atomicAdd(&s_hist[cached[c]], 1)] = i;
+    }
+    for (int i = tid + 4096; i < K; i += 1024) {
         int lvl;
         int bkt = bucket_of(i, lvl);
         order[atomicAdd(&s_hist[bkt], 1)] = i;
@@ -824,6 +838,18 @@ static int roi_path_choice() {
 
 static bool fast_path_ok(const rsdet_roi_align_cfg* c);
 static size_t fwd_smem_bytes(const rsdet_roi_align_cfg* c);
+// measurement aid (rsdet_roi_align_profile_events): events recorded around the gather kernel of the next forward call
+static thread_local cudaEvent_t t_prof_start = nullptr, t_prof_stop = nullptr;
+struct GatherTimer {       // records on construction / destruction when armed; disarms itself
+    cudaStream_t st;
+    cudaEvent_t stop;
+    explicit GatherTimer(cudaStream_t s) : st(s), stop(t_prof_stop) {
+        if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, st); else stop = nullptr;
+        t_prof_start = t_prof_stop = nullptr;
+    }
+    ~GatherTimer() { if (stop) cudaEventRecord(stop, st); }
+};
+
 static bool fwd77_ok(const rsdet_roi_align_cfg* c) {
     return c->pooled_h == 7 && c->pooled_w == 7 && c->sampling_ratio == 2 && c->channels % 256 == 0;
 }
@@ -1100,6 +1126,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         if (tuning_forward(cfg, L, ws, rois, order, geoms, num_rois, out, levels_out, st, &trc)) return trc;
     }
 #endif
+    GatherTimer gather_timer(st);
     if (fwd77_ok(cfg) && roi_path_choice() == 1) {   // the Oriented R-CNN geometry: specialised kernel
         int warps = 7;   // one warp per bin row: 7 bins each (eight warps leave one with 7 and seven with 6 bins), 72 registers
 #ifdef RSDET_TUNING
@@ -1196,6 +1223,12 @@ extern "C" int rsdet_tuning_set_prof(unsigned long long* dev_counters) {
     return (int)cudaMemcpyToSymbol(g_px_prof, &dev_counters, sizeof(dev_counters));
 }
 #endif
+
+extern "C" int rsdet_roi_align_profile_events(void* start_event, void* stop_event) {
+    t_prof_start = (cudaEvent_t)start_event;
+    t_prof_stop = (cudaEvent_t)stop_event;
+    return RSDET_OK;
+}
 
 extern "C" int rsdet_nchw_to_nhwc(const float* src, int n, int c, int h, int w, float* dst, void* stream) {
     if (!src || !dst || n < 1 || c < 1 || h < 1 || w < 1) return RSDET_EINVAL;
