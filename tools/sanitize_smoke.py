@@ -65,3 +65,14 @@ core.nms(NMS_HBB_P1, t(hb.astype(np.float32)), t(W.distinct_scores(200, 3)), 0.5
 core.nms(NMS_HBB_P1_F64, t(hb), t(W.distinct_scores(200, 3).astype(np.float64)), 0.5, want_score=True).count
 torch.cuda.synchronize()
 print("sanitize smoke done")
+# round 2, second pass: fast multiclass path with the two-chunk scan (n > 4096) and a sort that is not a power of two;
+# specialised 7x7 RoI kernel without a locality order (K < 256) and channels-last
+bb5 = W.rotated_boxes(5000, 8, canvas=2048, smin=8, smax=96)
+core.multiclass_nms_rotated(t(bb5), t(W.class_scores(5000, 3, 4)), 0.05, 0.1, 2000, t(np.random.default_rng(2).uniform(0.5, 1, 5000).astype(np.float32)))[2].item()
+shapes = W.fpn_shapes(1, tile=256, channels=256)
+cfg = core.make_roi_cfg(shapes, [1 / s_ for s_ in W.STRIDES], 7, 2, 1, (1.4, 1.2), channels_last=True)
+feats = [torch.randn((sh[0], sh[2], sh[3], sh[1]), device="cuda") for sh in shapes]
+core.roi_align_rotated_forward(cfg, feats, t(W.proposals(100, 6, canvas=256)))
+core.roi_align_rotated_forward(cfg, feats, t(W.proposals(400, 7, canvas=256)))
+torch.cuda.synchronize()
+print("sanitize_smoke: second-pass paths done")
