@@ -1185,6 +1185,206 @@ reduce_ov_staged_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_pe
     }
 }
 
+// Software-pipelined form of the staged scan for the shared decision matrix (IDENT = false): the column masks of block
+// b+1 do not depend on the running suppression mask, so warps 1-7 extract them (from rows staged one block earlier)
+// WHILE warp 0 resolves block b.  A column mask is read with lanes = rows (odd row pitch: conflict-free, the staged
+// kernel's lanes = candidates read arbitrary columns of one row: 4-5 way bank conflicts) and assembled by two ballots;
+// the kept rows are ORed into the mask with native 32-bit shared-memory atomics, which removes the partial-OR merge
+// pass.  Three row buffers (block b for the OR, b+1 for the extraction, b+2 arriving), two
+// column mask buffers, two block barriers per block instead of four.  Same decisions and outputs as reduce_ov_staged_kernel.
+// column masks of the candidates first, first + STRIDE, ... (< 64) of a block, by one warp: lanes = rows.  All loads of
+// the warp's candidates are issued before the first ballot (two warps per scheduler: latency is hidden by ILP only).
+template <int STRIDE>
+__device__ __forceinline__ void colmask_warp(const unsigned long long* __restrict__ R, int Ts, const int* __restrict__ cand, int nr,
+                                             int first, int lane, unsigned long long* __restrict__ out) {
+    constexpr int MAXJ = (64 + STRIDE - 1) / STRIDE;
+    int c[MAXJ];
+    unsigned long long v0[MAXJ], v1[MAXJ];
+#pragma unroll
+    for (int u = 0; u < MAXJ; u++) {
+        const int j = first + u * STRIDE;
+        c[u] = j < nr ? cand[j] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < MAXJ; u++) {
+        const int w = c[u] >= 0 ? c[u] >> 6 : 0;
+        v0[u] = R[lane * Ts + w];
+        v1[u] = R[(lane + 32) * Ts + w];
+    }
+#pragma unroll
+    for (int u = 0; u < MAXJ; u++) {
+        const int j = first + u * STRIDE;
+        if (j < 64) {                                        // warp-uniform
+            const int sh = c[u] & 63;
+            const unsigned lo = __ballot_sync(0xffffffffu, (v0[u] >> sh) & 1ull);
+            const unsigned hi = __ballot_sync(0xffffffffu, (v1[u] >> sh) & 1ull);
+            unsigned long long m = ((unsigned long long)hi << 32) | lo;
+            m = c[u] >= 0 ? m & ((1ull << j) - 1ull) : 0ull;   // rows i >= j do not count (rows past the block are zero)
+            if (lane == 0) out[j] = m;
+        }
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kReduceThreads, 1)
+reduce_ov_pipe_kernel(SegTable tb, const int* __restrict__ idx_ls, int cand_per_box, const unsigned long long* __restrict__ ov,
+                      int pitch, int n_boxes, uint8_t* __restrict__ keep_sorted, const int* __restrict__ seg_count,
+                      int* __restrict__ keep_prefix, int* __restrict__ kept_count, int* __restrict__ kept_pos) {
+    extern __shared__ unsigned long long s_dyn[];  // [remv: Ts][rows: 3 x 64 x Ts][cand: n_boxes ints]
+    __shared__ unsigned long long s_colmask[2][64];          // [buffer][j]: rows i < j of the block that suppress candidate j
+    __shared__ unsigned long long s_keep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nseg = tb.hdr[0];
+    const int T = (n_boxes + 63) >> 6, Ts = T | 1;
+    unsigned long long* s_remv = s_dyn;
+    unsigned long long* s_rows = s_dyn + Ts;
+    int* s_cand = reinterpret_cast<int*>(s_dyn + Ts + 3 * 64 * (size_t)Ts);
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int st = tb.seg_start[s];
+        const int ns = min(seg_count ? seg_count[s] : tb.seg_start[s + 1] - st, n_boxes);
+        const int nblk = (ns + 63) >> 6;
+        __syncthreads();
+        for (int j = tid; j < Ts; j += kReduceThreads) s_remv[j] = 0ull;
+        for (int p = tid; p < ns; p += kReduceThreads) s_cand[p] = idx_ls[st + p] / cand_per_box;
+        __syncthreads();
+        ulonglong2 nxt[8][NCH];   // warp w: rows w, w+8, ..., w+56 of a block; lane l: words 2l, 2l+1 of every 64-word chunk
+        auto fetch = [&](int b) {
+            const int nr = min(64, ns - b * 64);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = warp + 8 * k;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const int w = ch * 64 + 2 * lane;
+                    nxt[k][ch] = make_ulonglong2(0ull, 0ull);
+                    if (i < nr && w < pitch)
+                        nxt[k][ch] = *reinterpret_cast<const ulonglong2*>(ov + (size_t)s_cand[b * 64 + i] * pitch + w);
+                }
+            }
+        };
+        auto stash = [&](int b) {
+            unsigned long long* dst = s_rows + (size_t)(b % 3) * 64 * Ts;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int i = warp + 8 * k;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const int w = ch * 64 + 2 * lane;
+                    if (w < Ts) dst[i * Ts + w] = nxt[k][ch].x;
+                    if (w + 1 < Ts) dst[i * Ts + w + 1] = nxt[k][ch].y;
+                }
+            }
+        };
+        if (nblk > 0) { fetch(0); stash(0); }
+        if (nblk > 1) { fetch(1); stash(1); }
+        __syncthreads();
+        if (nblk > 0) colmask_warp<kReduceThreads / 32>(s_rows, Ts, s_cand, min(64, ns), warp, lane, s_colmask[0]);
+        if (nblk > 2) fetch(2);                     // in flight during iteration 0
+        __syncthreads();
+        int kept_run = 0;
+#ifdef RSDET_SCAN_PROF
+        long long t_p1 = 0, t_b1 = 0, t_p2a = 0, t_p2b = 0, t_b2 = 0, t0, t1;
+#endif
+        for (int b = 0; b < nblk; b++) {
+            const int nr = min(64, ns - b * 64);
+#ifdef RSDET_SCAN_PROF
+            t0 = clock64();
+#endif
+            if (warp == 0) {
+                // greedy resolve as a fixed point (see reduce_ov_staged_kernel)
+                unsigned long long col[2];
+                bool und[2];
+                unsigned long long dead = 0ull, kept = 0ull;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = lane + 32 * h;
+                    col[h] = s_colmask[b & 1][j];
+                    const int a = j < nr ? s_cand[b * 64 + j] : -1;
+                    const bool rem = a < 0 || ((s_remv[a >> 6] >> (a & 63)) & 1ull);
+                    dead |= (unsigned long long)__ballot_sync(0xffffffffu, rem) << (32 * h);
+                    und[h] = !rem;
+                }
+                while (true) {
+                    bool nd[2], nk[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        nd[h] = und[h] && (col[h] & kept) != 0ull;
+                        nk[h] = und[h] && !nd[h] && (col[h] & ~dead) == 0ull;
+                        und[h] = und[h] && !nd[h] && !nk[h];
+                    }
+                    const unsigned long long d2 = (unsigned long long)__ballot_sync(0xffffffffu, nd[0]) |
+                                                  ((unsigned long long)__ballot_sync(0xffffffffu, nd[1]) << 32);
+                    const unsigned long long k2 = (unsigned long long)__ballot_sync(0xffffffffu, nk[0]) |
+                                                  ((unsigned long long)__ballot_sync(0xffffffffu, nk[1]) << 32);
+                    if ((d2 | k2) == 0ull) break;
+                    dead |= d2;
+                    kept |= k2;
+                }
+                if (lane == 0) s_keep = kept;
+            } else if (b + 1 < nblk) {
+                colmask_warp<kReduceThreads / 32 - 1>(s_rows + (size_t)((b + 1) % 3) * 64 * Ts, Ts, s_cand + (b + 1) * 64,
+                                                      min(64, ns - (b + 1) * 64), warp - 1, lane, s_colmask[(b + 1) & 1]);
+            }
+#ifdef RSDET_SCAN_PROF
+            t1 = clock64(); t_p1 += t1 - t0; t0 = t1;
+#endif
+            __syncthreads();
+#ifdef RSDET_SCAN_PROF
+            t1 = clock64(); t_b1 += t1 - t0; t0 = t1;
+#endif
+            const unsigned long long kb = s_keep;
+            if (tid < nr) {
+                keep_sorted[st + b * 64 + tid] = (uint8_t)((kb >> tid) & 1ull);
+                if (keep_prefix) {
+                    const int pre = kept_run + __popcll(kb & ((1ull << tid) - 1ull));
+                    keep_prefix[st + b * 64 + tid] = pre;
+                    if ((kb >> tid) & 1ull) kept_pos[st + pre] = b * 64 + tid;
+                }
+            }
+            kept_run += __popcll(kb);
+            {
+                // OR of the kept rows into the running mask: row group rg = tid / 64 covers 16 rows, lane column w (+64 for
+                // the second chunk); the four groups meet in native 32-bit shared-memory atomics (a 64-bit OR is a CAS loop)
+                const unsigned long long* R = s_rows + (size_t)(b % 3) * 64 * Ts;
+                const int jj = tid & 63, rg = tid >> 6;
+                const unsigned kb16 = (unsigned)((kb >> (rg * 16)) & 0xffffull);
+                if (kb16) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) {
+                        const int w = ch * 64 + jj;
+                        if (w < Ts) {
+                            unsigned long long acc = 0ull;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) acc |= ((kb16 >> i) & 1u) ? R[(rg * 16 + i) * Ts + w] : 0ull;
+                            unsigned* dst = reinterpret_cast<unsigned*>(&s_remv[w]);
+                            if ((unsigned)acc) atomicOr(dst, (unsigned)acc);
+                            if ((unsigned)(acc >> 32)) atomicOr(dst + 1, (unsigned)(acc >> 32));
+                        }
+                    }
+                }
+            }
+#ifdef RSDET_SCAN_PROF
+            t1 = clock64(); t_p2a += t1 - t0; t0 = t1;
+#endif
+            if (b + 2 < nblk) stash(b + 2);
+            if (b + 3 < nblk) fetch(b + 3);
+#ifdef RSDET_SCAN_PROF
+            t1 = clock64(); t_p2b += t1 - t0; t0 = t1;
+#endif
+            __syncthreads();
+#ifdef RSDET_SCAN_PROF
+            t1 = clock64(); t_b2 += t1 - t0;
+#endif
+        }
+#ifdef RSDET_SCAN_PROF
+        if (s == 0 && (tid == 0 || tid == 32 || tid == 224) && nblk > 0)
+            printf("scan prof tid %d nblk %d: per block cycles: phase1 %lld, barrier1 %lld, keep+OR %lld, stash+fetch %lld, barrier2 %lld\n", tid, nblk,
+                   t_p1 / nblk, t_b1 / nblk, t_p2a / nblk, t_p2b / nblk, t_b2 / nblk);
+#endif
+        if (kept_count && tid == 0) kept_count[s] = kept_run;
+    }
+}
+
 // ----------------------------------------------------------------------------- outputs
 __global__ void scatter_keep_kernel(const uint8_t* __restrict__ keep_sorted, const int* __restrict__ idx, int n_max,
                                     const int* __restrict__ n_dev, uint8_t* __restrict__ keep_mask) {
@@ -2267,12 +2467,19 @@ static int mc_fast_run(const float* bboxes, const float* scores, int n, int C, f
     launch_ov_matrix(bboxes, n, iou_thr, false, sb, mask, mask_cap, cnt_scratch, st);
     if (sl) cudaStreamWaitEvent(st, sl->join, 0);
     const size_t Ts = (size_t)(Tov | 1);
-    const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)n;
+    const size_t piped = sizeof(unsigned long long) * (Ts + 3 * 64 * Ts) + sizeof(int) * (size_t)n;       // three row buffers
+    const size_t staged = sizeof(unsigned long long) * (5 * Ts + 2 * 64 * Ts) + sizeof(int) * (size_t)n;  // two (n close to 8192)
     const int grid = C < kNumSMs ? C : kNumSMs;
-    if (Tov <= 64) {
-        allow_dyn_smem((const void*)reduce_ov_staged_kernel<1, false>, 200 * 1024);
-        reduce_ov_staged_kernel<1, false><<<grid, kReduceThreads, staged, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, nullptr, seg_count,
-                                                                              keep_prefix, kept_count, kept_pos);
+    if (piped + 2048 <= 227 * 1024) {
+        if (Tov <= 64) {
+            allow_dyn_smem((const void*)reduce_ov_pipe_kernel<1>, piped);
+            reduce_ov_pipe_kernel<1><<<grid, kReduceThreads, piped, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, seg_count, keep_prefix,
+                                                                         kept_count, kept_pos);
+        } else {
+            allow_dyn_smem((const void*)reduce_ov_pipe_kernel<2>, piped);
+            reduce_ov_pipe_kernel<2><<<grid, kReduceThreads, piped, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, seg_count, keep_prefix,
+                                                                         kept_count, kept_pos);
+        }
     } else {
         allow_dyn_smem((const void*)reduce_ov_staged_kernel<2, false>, 200 * 1024);
         reduce_ov_staged_kernel<2, false><<<grid, kReduceThreads, staged, st>>>(tb, idx_ls, C, mask, pitch, n, keep_sorted, nullptr, seg_count,

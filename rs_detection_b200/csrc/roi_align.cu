@@ -724,6 +724,7 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
 //     after the first loads of the next bin, not before them;
 //   * a CTA starts from the geometry record in processing order (one global round trip instead of order -> geoms).
 // Arithmetic and tap order are those of roi_align_fwd_kernel<2>; results are bit-identical.
+constexpr size_t kStage77Offset = (8 * 49 * 17 + 15 + ((49 * 4 + 15) & ~15) + 127) & ~(size_t)127;   // lists + counts, rounded up
 template <int WARPS, int FLAVOUR = 0>
 __global__ void __launch_bounds__(32 * WARPS, 4)
 roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, float* __restrict__ out) {
@@ -732,7 +733,8 @@ roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, f
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int2* s_list = reinterpret_cast<int2*>(smem_raw);
     int* s_cnt = reinterpret_cast<int*>(smem_raw + list_bytes(NB, CAP));
-    float* s_stage = reinterpret_cast<float*>(smem_raw + list_bytes(NB, CAP) + ((NB * 4 + 15) & ~15));
+    // staging block on a 128-byte boundary: the bulk store reads it in 128-byte lines
+    float* s_stage = reinterpret_cast<float*>(smem_raw + kStage77Offset);
     RoiGeom g = gsorted[blockIdx.x];
     const int roi = g.gh;                                   // processing-order record: gh carries the RoI index
     g.gh = 2; g.gw = 2;
@@ -1128,6 +1130,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
 #endif
     GatherTimer gather_timer(st);
     if (fwd77_ok(cfg) && roi_path_choice() == 1) {   // the Oriented R-CNN geometry: specialised kernel
+        smem = smem - fwd_smem_bytes(cfg) + kStage77Offset + sizeof(float) * 49 * 256;
         int warps = 7;   // one warp per bin row: 7 bins each (eight warps leave one with 7 and seven with 6 bins), 72 registers
 #ifdef RSDET_TUNING
         if (const char* e = getenv("RSDET_ROI_WARPS")) warps = atoi(e);
