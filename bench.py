@@ -432,6 +432,26 @@ def run_ours(args, rank, world, local_rank):
     gout = torch.randn((512, W.CHANNELS, 7, 7), device=dev)
     ms_fb = timed(lambda: (core.roi_align_rotated_forward(cfg, tiles[0][0], rois512),
                            core.roi_align_rotated_backward(cfg, gout, rois512, shapes)), reps)
+    # backward alone (config 3): algorithmic bytes 4*K*C*49 (gradient in) + 4*C*sum(HW) (dense gradient out) + 8*C*U
+    # (read-modify-write of the touched pixels) + 24*K; the call also zero-fills and transposes the 89 MB
+    # accumulator because the caller's layout is NCHW
+    ms_bwd = timed(lambda: core.roi_align_rotated_backward(cfg, gout, rois512, shapes), reps)
+    U512 = float(touched_pixels(tiles_np[0][1][:512]))
+    bwd_bytes = 4.0 * 512 * W.CHANNELS * 49 + 4.0 * W.CHANNELS * sum(sh[2] * sh[3] for sh in shapes) + 8.0 * W.CHANNELS * U512 + 24.0 * 512
+    # config 1 (the reference's own CPU-runnable case): 2000 proposals, 15 classes, score_thr 0.05, one tile
+    rois_c1 = torch.from_numpy(W.proposals(2000, 1)).to(dev)
+    boxes_c1 = torch.from_numpy(W.rotated_boxes(2000, 501)).to(dev)
+    scores_c1 = torch.from_numpy(W.class_scores(2000, 15, 1, logit_scale=1.0)).to(dev)
+    ms_c1_roi = timed(lambda: core.roi_align_rotated_forward(cfg, tiles[0][0], rois_c1), reps)
+    ms_c1_nms = timed(lambda: core.multiclass_nms_rotated(boxes_c1, scores_c1, 0.05, IOU_THR, MAX_NUM), reps)
+    # config 4 (dense single-stage candidates): unlabelled nms_rotated on 100k boxes of a 4096^2 canvas, and 20k x 20k IoU
+    from rs_detection_b200._lib import NMS_ROTATED
+    b100k = torch.from_numpy(W.rotated_boxes(100000, 7, canvas=4096, smin=8.0, smax=128.0)).to(dev)
+    s100k = torch.from_numpy(W.distinct_scores(100000, 7)).to(dev)
+    ms_nms100k = timed(lambda: core.nms(NMS_ROTATED, b100k, s100k, 0.1), 3)
+    b20k = b100k[:20000].contiguous()
+    ms_iou20k = timed(lambda: core.box_iou_rotated(b20k, b20k, 0), 3)
+    del b100k, s100k, b20k
     gt = torch.from_numpy(W.jittered_copies(tiles_np[0][1][:, 1:], 512, 3)).to(dev)
     props = tiles[0][1][:2000, 1:].contiguous()
     ms_iou = timed(lambda: core.assign_wrt_overlaps(core.box_iou_rotated(gt, props, 1, True), 0.5, 0.5, 0.5, False), reps)
@@ -622,6 +642,14 @@ def run_ours(args, rank, world, local_rank):
                 "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel, "roi_fwd_call_channels_last_ms_per_tile": ms_fwd_call,
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
+                "train_roi_bwd_512": {"ms": ms_bwd, "algorithmic_bytes": bwd_bytes, "achieved_gbs": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
+                                      "hbm_frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / peak,
+                                      "note": "whole call for an NCHW caller: zero-fill + scatter kernel + NHWC->NCHW transpose"},
+                "config1_2000x15": {"roi_extractor_fwd_ms": ms_c1_roi, "multiclass_nms_ms": ms_c1_nms,
+                                    "tile_ms_single_stream": ms_c1_roi + ms_c1_nms},
+                "config4": {"nms_rotated_100k_canvas4096_thr0.1_ms": ms_nms100k, "nms_boxes_per_s": 1e5 / (ms_nms100k * 1e-3),
+                            "box_iou_rotated_20k_x_20k_ms": ms_iou20k, "iou_pairs_per_s": 4e8 / (ms_iou20k * 1e-3),
+                            "iou_fp32_frac": 4e8 * 382.6 / (ms_iou20k * 1e-3) / 1e12 / 74.44992},
                 "iou_512x2000_assign_ms": ms_iou, "iou_pairs_per_s": 512 * 2000 / (ms_iou * 1e-3),
                 "head_tail_4000x10_ms": ms_head, "head_tail_rois_per_s": K_ROIS / (ms_head * 1e-3),
                 "rpn_proposals_262k_anchors_ms": ms_rpn, "rpn_anchors_per_s": 261888 / (ms_rpn * 1e-3)},
