@@ -643,7 +643,7 @@ def run_ours(args, rank, world, local_rank):
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
                 "train_roi_bwd_512": {"ms": ms_bwd, "algorithmic_bytes": bwd_bytes, "achieved_gbs": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
-                                      "hbm_frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / peak,
+                                      "hbm_frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / roofline["peak"],
                                       "note": "whole call for an NCHW caller: zero-fill + scatter kernel + NHWC->NCHW transpose"},
                 "config1_2000x15": {"roi_extractor_fwd_ms": ms_c1_roi, "multiclass_nms_ms": ms_c1_nms,
                                     "tile_ms_single_stream": ms_c1_roi + ms_c1_nms},
