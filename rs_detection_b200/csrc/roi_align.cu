@@ -45,6 +45,7 @@ struct LevelSet {
     int num_levels, batch, C;
     int PH, PW, sampling_ratio, version;
     float extend_w, extend_h, finest_scale;
+    int dbg_drop;       // profiling aid (RSDET_ROI_DBG_DROP, RSDET_TUNING builds only)
     unsigned dbg_mask;  // profiling aid (RSDET_ROI_DBG_MASK, RSDET_TUNING builds only): tap offsets are ANDed with it (shrinks the gather's footprint)
     int dbg_skip_main;  // profiling aid (RSDET_ROI_DBG_SKIP_MAIN=1, RSDET_TUNING builds only): tap lists are built, then treated as empty
 };
@@ -471,7 +472,9 @@ static void launch_prep(const LevelSet& L, const float* rois, int K, RoiGeom* ge
 //   s_cnt [nbins], tmp: 3*nbins*(cap+1) words of scratch.
 //   unit/base: stored offset = base + pixel * unit (unit = C/4 for float4 addressing, 1 for TMA row indices)
 // FIXED = true: the 7x7-bin, 2x2-sample geometry as compile-time constants (roi_align_fwd77_kernel)
-template <int kThreads = kRoiThreads, bool FIXED = false>
+// LPITCH = 18 (roi_align_fwd77_kernel): list pitch of 18 entries, i.e. every bin's list starts on a 16-byte boundary (two
+// entries per LDS.128 in the gather loop) and the bin's count lives in the pad entry 16 instead of s_cnt.
+template <int kThreads = kRoiThreads, bool FIXED = false, int LPITCH = 17>
 __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet& L, int H, int W, int2* s_list, int* s_cnt,
                                                 float* tmp, int unit, int base) {
     const int tid = threadIdx.x;
@@ -522,9 +525,17 @@ __device__ __forceinline__ void build_tap_lists(const RoiGeom& g, const LevelSet
                     acc += same ? w[i] : 0.f;
                     w[i] = same ? 0.f : w[i];
                 }
-                if (w[j] != 0.f) s_list[b * 17 + pos++] = make_int2(o[j], __float_as_int(acc));
+                if (w[j] != 0.f) s_list[b * LPITCH + pos++] = make_int2(o[j], __float_as_int(acc));
             }
-            s_cnt[b] = pos;
+#ifdef RSDET_TUNING   // what-if: 1 of every `dbg_drop` entries removed (wrong results, timing of a deduplicated list)
+            if (L.dbg_drop > 1) {
+                int q = 0;
+                for (int e = 0; e < pos; e++)
+                    if ((e + b) % L.dbg_drop != 0) s_list[b * LPITCH + q++] = s_list[b * LPITCH + e];
+                pos = q;
+            }
+#endif
+            if (LPITCH == 18) s_list[b * 18 + 16] = make_int2(pos, 0); else s_cnt[b] = pos;
         }
         __syncthreads();
         return;
@@ -1022,9 +1033,11 @@ static LevelSet make_levels(const rsdet_roi_align_cfg* c) {
     L.extend_w = c->extend_w; L.extend_h = c->extend_h; L.finest_scale = c->finest_scale;
     L.dbg_skip_main = 0;
     L.dbg_mask = 0xffffffffu;
+    L.dbg_drop = 0;
 #ifdef RSDET_TUNING
     if (const char* e = getenv("RSDET_ROI_DBG_SKIP_MAIN")) L.dbg_skip_main = atoi(e);
     if (const char* e = getenv("RSDET_ROI_DBG_MASK")) L.dbg_mask = (unsigned)strtoul(e, nullptr, 0);
+    if (const char* e = getenv("RSDET_ROI_DBG_DROP")) L.dbg_drop = atoi(e);
 #endif
     for (int l = 0; l < RSDET_MAX_LEVELS; l++) {
         L.feat[l] = nullptr; L.grad[l] = nullptr;
@@ -1141,6 +1154,13 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         if (flavour == 1) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 1>, smem); roi_align_fwd77_kernel<8, 1><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
         if (flavour == 2) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 2>, smem); roi_align_fwd77_kernel<8, 2><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
         if (flavour == 3) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 3>, smem); roi_align_fwd77_kernel<8, 3><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+#endif
+#ifdef RSDET_TUNING
+        if (const char* e = getenv("RSDET_ROI_V8")) {       // A/B: 1 = LDS.128 list reads only, 2 = + 256-bit loads
+            const size_t sm8 = kStage77v8Offset + sizeof(float) * 49 * 256;
+            if (atoi(e) == 1) { set_dyn_smem((const void*)roi_align_fwd77v8_kernel<7, false>, sm8); roi_align_fwd77v8_kernel<7, false><<<g77, 224, sm8, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+            if (atoi(e) == 2) { set_dyn_smem((const void*)roi_align_fwd77v8_kernel<7, true>, sm8); roi_align_fwd77v8_kernel<7, true><<<g77, 224, sm8, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+        }
 #endif
         if (warps == 7) {
             set_dyn_smem((const void*)roi_align_fwd77_kernel<7>, smem);

@@ -3,6 +3,129 @@
 // library contains none of this.  Measurements: profiles/README.md "Round 2".
 #pragma once
 
+// ---------------------------------------------------------------------------------- forward (7x7, 256-bit loads)
+// A/B only (RSDET_ROI_V8 = 1 / 2): measured 137.6 us (LDS.128 list reads alone) and 142.1 us (+ 256-bit loads) per tile against
+// 138.4 us for roi_align_fwd77_kernel<7> in the same build -- neither is a gain, so the shipped kernel stays as it is.
+// Same decomposition as roi_align_fwd77_kernel with two Blackwell-specific changes to the gather loop:
+//   * V8: a tap is ONE 256-bit load per lane (ld.global.nc.v8.f32, SASS LDG.E.ENL2.256; sm_100+): lane l owns channels
+//     8l..8l+7 and a warp instruction covers the pixel's whole 1 KB row -- half the LSU instructions of the 2 x LDG.128 form;
+//   * the bin lists have a pitch of 18 entries (16-byte aligned), so the four entries of a batch are two LDS.128
+//     broadcasts instead of four LDS.64, and the count sits in the pad entry (no s_cnt array).
+// Staging: lane l = 4g + r stores component (j + g) & 7 of its eight channels at step j: word address (8l + m) * 49 + b
+// falls in bank (8r + 17m + b) mod 32, which is distinct for all 32 (r, m) pairs of a warp.  Arithmetic and tap order are
+// those of roi_align_fwd77_kernel; results are bit-identical.
+constexpr size_t kStage77v8Offset = (8 * 49 * 18 + 127) & ~(size_t)127;
+__device__ __forceinline__ void ldg_nc_v8(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+template <int WARPS, bool V8>
+__global__ void __launch_bounds__(32 * WARPS, 4)
+roi_align_fwd77v8_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, float* __restrict__ out) {
+    constexpr int NB = 49, PITCH = 18, THREADS = 32 * WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + kStage77v8Offset);
+    RoiGeom g = gsorted[blockIdx.x];
+    const int roi = g.gh;                                   // processing-order record: gh carries the RoI index
+    g.gh = 2; g.gw = 2;
+    const int C = L.C, chunk0 = blockIdx.y * 256;
+    const int H = L.H[g.level], W = L.W[g.level];
+    build_tap_lists<THREADS, true, PITCH>(g, L, H, W, s_list, nullptr, s_stage, C >> 2, 0);
+
+    // V8: lane owns 8 consecutive channels (32 bytes); else two quads 512 bytes apart as in roi_align_fwd77_kernel
+    const float4* __restrict__ feat =
+        reinterpret_cast<const float4*>(L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0) + (V8 ? 2 * lane : lane);
+    const int rotg = V8 ? (lane >> 2) : ((lane >> 3) & 3);
+    auto stage = [&](float (&a)[8], int b) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] *= 0.25f;              // output_val /= count (:143), count = 4: exact
+        if (V8) {
+            float r[8];
+            // r[j] = a[(j + rotg) & 7]
+            if (rotg & 1) { const float t = a[0]; a[0] = a[1]; a[1] = a[2]; a[2] = a[3]; a[3] = a[4]; a[4] = a[5]; a[5] = a[6]; a[6] = a[7]; a[7] = t; }
+            if (rotg & 2) { const float t0 = a[0], t1 = a[1]; a[0] = a[2]; a[1] = a[3]; a[2] = a[4]; a[3] = a[5]; a[4] = a[6]; a[5] = a[7]; a[6] = t0; a[7] = t1; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = (rotg & 4) ? a[(j + 4) & 7] : a[j];
+            float* const sb = s_stage + lane * 8 * NB + b;
+#pragma unroll
+            for (int j = 0; j < 8; j++) sb[((j + rotg) & 7) * NB] = r[j];
+        } else {
+            const float4 r0 = rot4(make_float4(a[0], a[1], a[2], a[3]), rotg), r1 = rot4(make_float4(a[4], a[5], a[6], a[7]), rotg);
+            float* const sb = s_stage + lane * 4 * NB + b;
+            float* const q0 = sb + ((0 + rotg) & 3) * NB;
+            float* const q1 = sb + ((1 + rotg) & 3) * NB;
+            float* const q2 = sb + ((2 + rotg) & 3) * NB;
+            float* const q3 = sb + ((3 + rotg) & 3) * NB;
+            q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
+            q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
+        }
+    };
+    auto load = [&](unsigned off16, float (&v)[8]) {
+        const float* q = tap_ptr(feat, off16);
+        if (V8) ldg_nc_v8(q, v);
+        else {
+            const float4 x = ldg_nc_v4(q), y = ldg_nc_v4(q + 128);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+        }
+    };
+    const int2* lp = s_list + warp * PITCH;
+    int4 ea = reinterpret_cast<const int4*>(lp)[0], eb = reinterpret_cast<const int4*>(lp)[1];
+    int cnt = lp[16].x;
+#pragma unroll 1
+    for (int b = warp; b < NB; b += WARPS) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+        const int nbin = min(b + WARPS, NB - 1);
+        int ncnt = cnt;
+        int e = 0;
+#pragma unroll 1
+        do {
+            const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
+            float v0[8], v1[8], v2[8], v3[8];
+            if (p0) load((unsigned)ea.x, v0);
+            if (p1) load((unsigned)ea.z, v1);
+            if (p2) load((unsigned)eb.x, v2);
+            if (p3) load((unsigned)eb.z, v3);
+            const float w0 = __int_as_float(ea.y), w1 = __int_as_float(ea.w), w2 = __int_as_float(eb.y), w3 = __int_as_float(eb.w);
+            e += 4;
+            const bool more = e < cnt;
+            const int2* np = more ? lp + e : s_list + nbin * PITCH;
+            if (!more) ncnt = s_list[nbin * PITCH + 16].x;
+            ea = reinterpret_cast<const int4*>(np)[0]; eb = reinterpret_cast<const int4*>(np)[1];
+            if (p0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(w0, v0[j], acc[j]);
+            }
+            if (p1) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(w1, v1[j], acc[j]);
+            }
+            if (p2) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(w2, v2[j], acc[j]);
+            }
+            if (p3) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(w3, v3[j], acc[j]);
+            }
+        } while (e < cnt);
+        stage(acc, b);
+        lp = s_list + nbin * PITCH;
+        cnt = ncnt;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    float* __restrict__ dst = out + ((size_t)roi * C + chunk0) * NB;
+    if ((((size_t)out) & 15) == 0 && ((C * NB) & 3) == 0) {
+        if (tid == 0) bulk_store_evict_first(dst, s_stage, 256u * NB * 4u);
+    } else {
+        for (int i = tid; i < 256 * NB; i += THREADS) __stcs(dst + i, s_stage[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------- forward (channel-split passes)
 // Same tap lists and the same warp = bin gather, but a 256-channel chunk is produced in NP passes of 256/NP channels:
 // the staging block shrinks to 50/NP KB, so four resident CTAs leave most of the SM's 256 KB to L1 -- the pixel rows
