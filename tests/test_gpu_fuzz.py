@@ -1,0 +1,205 @@
+"""GPU parity, randomised: seeded sweeps over shapes and geometries that the fixed-size tests do not enumerate --
+odd channel counts, every pooled size / sampling grid, both angle conventions, RoIs outside the map, degenerate and
+duplicate boxes, box counts around the 64-box block edges, random label and threshold draws.  Every case goes through
+the jdet mirror -> C ABI and is compared with the oracle (oracle/rsdet_oracle.c, bit-pinned to the reference source by
+tests/test_oracle_vs_ref.py).  Contract as in the fixed-size tests: RoIAlign forward 1e-5 / backward 1e-4 of the tensor
+scale, IoU 1e-6 absolute, keep sets exact unless an IoU lies within 1e-6 of the threshold (such draws are skipped and
+counted)."""
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+from helpers import band_pairs, close_report
+
+pytestmark = pytest.mark.gpu
+
+# RSDET_FUZZ_SOAK=<k>: k times as many seeds per family (the default run keeps the whole file under half a minute)
+import os
+SOAK = max(1, int(os.environ.get("RSDET_FUZZ_SOAK", "1")))
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _close(got, want, tol):
+    scale = float(np.abs(want).max()) or 1.0
+    nbad, maxerr, _ = close_report(got, want, tol, tol * scale)
+    return nbad, maxerr, scale
+
+
+def _random_rois(rng, K, batch, Hpx, Wpx):
+    """RoIs in image pixels: most inside the map, some far outside, some tiny, some larger than the map."""
+    r = np.zeros((K, 6), np.float32)
+    r[:, 0] = rng.integers(0, batch, K)
+    r[:, 1] = rng.uniform(-0.2 * Wpx, 1.2 * Wpx, K)
+    r[:, 2] = rng.uniform(-0.2 * Hpx, 1.2 * Hpx, K)
+    r[:, 3] = np.exp(rng.uniform(np.log(0.3), np.log(2.5 * Wpx), K))
+    r[:, 4] = np.exp(rng.uniform(np.log(0.3), np.log(2.5 * Hpx), K))
+    r[:, 5] = rng.uniform(-np.pi, np.pi, K)
+    if K >= 4:
+        r[0, 3:5] = 0.0                         # zero size: clamped to one pixel by v1, not by v0
+        r[1, 1:3] = [-5 * Wpx, -5 * Hpx]        # every sample outside: all zeros
+        r[2, 5] = 0.0
+        r[3, 5] = np.pi / 2
+    return r
+
+
+@pytest.mark.parametrize("seed", range(12 * SOAK))
+def test_roi_align_random_geometry(cuda, oracle, seed):
+    from rs_detection_b200.jdet.ops import roi_align_rotated, roi_align_rotated_v1
+    rng = np.random.default_rng(1000 + seed)
+    C = int(rng.choice([1, 3, 4, 5, 12, 20, 64, 96, 256, 260, 512]))
+    out = (int(rng.integers(1, 9)), int(rng.integers(1, 9))) if seed % 3 else 7
+    sr = int(rng.choice([0, 1, 2, 2, 3]))
+    version = seed & 1
+    batch = int(rng.integers(1, 4))
+    H, Wd = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+    scale = float(rng.choice([1 / 4., 1 / 8., 1 / 16., 1 / 32.]))
+    K = int(rng.choice([1, 2, 7, 40, 300]))
+    feat = rng.standard_normal((batch, C, H, Wd)).astype(np.float32)
+    rois = _random_rois(rng, K, batch, H / scale, Wd / scale)
+    cls = roi_align_rotated_v1.ROIAlignRotated_v1 if version else roi_align_rotated.ROIAlignRotated
+    layer = cls(out, scale, sr)
+    x = _t(feat).requires_grad_(True)
+    y = layer(x, _t(rois))
+    want = oracle.roi_align_rotated_fwd(feat, rois, layer.output_size, scale, sr, version)
+    nbad, err, sc = _close(y.detach().cpu().numpy(), want, 1e-5)
+    print(f"seed {seed}: C={C} out={layer.output_size} sr={sr} v{version} {batch}x{H}x{Wd} K={K}: fwd err {err:.3g} (scale {sc:.3g})")
+    assert nbad == 0
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    y.backward(_t(g))
+    wantb = oracle.roi_align_rotated_bwd(g, rois, feat.shape, scale, sr, version)
+    nbad, err, sc = _close(x.grad.cpu().numpy(), wantb, 1e-4)
+    print(f"          bwd err {err:.3g} (scale {sc:.3g})")
+    assert nbad == 0
+
+
+@pytest.mark.parametrize("seed", range(6 * SOAK))
+def test_fused_extractor_random(cuda, oracle, seed):
+    """Fused multi-level extractor (level mapping + extension in-kernel) on random pyramids, C a multiple of 4 or not."""
+    from rs_detection_b200.jdet.models.roi_extractors.oriented_single_level import OrientedSingleRoIExtractor
+    rng = np.random.default_rng(2000 + seed)
+    C = int(rng.choice([4, 32, 36, 256]))
+    batch = int(rng.integers(1, 3))
+    nlev = int(rng.integers(1, 5))
+    strides = [4, 8, 16, 32][:nlev]
+    base = int(rng.choice([96, 160, 256]))
+    feats = [rng.standard_normal((batch, C, base // s, base // s)).astype(np.float32) for s in strides]
+    K = int(rng.choice([3, 64, 700]))
+    rois = W.proposals(K, 77 + seed, batch=batch, canvas=base)
+    rois[: min(K, 3), 3:5] = [[2, 2], [4 * base, 3], [base, base]][: min(K, 3)]
+    extend = (1.4, 1.2) if seed & 1 else (1.0, 1.0)
+    ext = OrientedSingleRoIExtractor(dict(type="ROIAlignRotated_v1", output_size=7, sampling_ratio=2), C, strides,
+                                     extend_factor=extend)
+    got = ext([_t(f) for f in feats], _t(rois)).cpu().numpy()
+    want, _ = oracle.oriented_extractor_fwd(feats, rois, strides, extend_factor=extend)
+    nbad, err, sc = _close(got, want, 1e-5)
+    print(f"seed {seed}: C={C} levels={nlev} base={base} K={K}: err {err:.3g} (scale {sc:.3g})")
+    assert nbad == 0
+
+
+def _random_boxes(rng, n, canvas):
+    d = W.rotated_boxes(n, int(rng.integers(1 << 30)), canvas=canvas, smin=4, smax=max(8, canvas // 3))
+    m = n // 8
+    if m:
+        d[:m] = d[m:2 * m]                                   # exact duplicates
+        d[2 * m:2 * m + m // 2, 2:4] = d[2 * m:2 * m + m // 2, 2:4] * 1e-4   # slivers
+    if n > 6:
+        d[-1, 2:4] = 0.0                                      # zero area
+        d[-2, 4] = 0.0
+        d[-3, 4] = np.pi / 2
+    return d
+
+
+@pytest.mark.parametrize("seed", range(10 * SOAK))
+def test_iou_random(cuda, oracle, seed):
+    from rs_detection_b200.jdet.ops import box_iou_rotated, box_iou_rotated_v1
+    rng = np.random.default_rng(3000 + seed)
+    n, m = int(rng.choice([1, 2, 63, 64, 65, 130, 700])), int(rng.choice([1, 5, 64, 129, 900]))
+    canvas = int(rng.choice([64, 512, 4096]))
+    a, b = _random_boxes(rng, n, canvas), _random_boxes(rng, m, canvas)
+    if seed % 4 == 3:                                         # far from the origin: the midpoint shift matters
+        a[:, :2] += 3.0e4
+        b[:, :2] += 3.0e4
+    version = seed & 1
+    fn = box_iou_rotated_v1 if version else box_iou_rotated
+    got = fn(_t(a), _t(b)).cpu().numpy()
+    want = oracle.box_iou_rotated(a, b, version, 1)
+    nbad = int((got != want).sum())
+    print(f"seed {seed}: {n}x{m} canvas {canvas} v{version}: {nbad} values not bit-identical, max|d| {np.abs(got - want).max():.3g}")
+    assert got.shape == (n, m) and np.abs(got - want).max() <= 1e-6
+
+
+@pytest.mark.parametrize("seed", range(12 * SOAK))
+def test_nms_random(cuda, oracle, seed):
+    from rs_detection_b200.jdet.ops.nms_rotated import ml_nms_rotated, nms_rotated
+    rng = np.random.default_rng(4000 + seed)
+    n = int(rng.choice([1, 2, 31, 63, 64, 65, 127, 128, 129, 640, 2500]))
+    canvas = int(rng.choice([96, 400, 2000]))
+    thr = float(rng.choice([0.05, 0.1, 0.3, 0.5, 0.75]))
+    d = _random_boxes(rng, n, canvas)
+    s = W.distinct_scores(n, 9 + seed)
+    iou = oracle.box_iou_rotated(d, d, 0, 1)
+    if band_pairs(iou[~np.eye(n, dtype=bool)], thr):
+        pytest.skip("a pair inside the 1e-6 band around the threshold")
+    got = nms_rotated(_t(d), _t(s), thr).cpu().numpy()
+    assert np.array_equal(got, oracle.nms_rotated(d, s, thr, ge=False)), (n, canvas, thr)
+    ncls = int(rng.choice([1, 2, 7, 40]))
+    lab = rng.integers(0, ncls, n)
+    got = ml_nms_rotated(_t(d), _t(s), _t(lab.astype(np.int64)), thr).cpu().numpy()
+    assert np.array_equal(got, oracle.ml_nms_rotated(d, s, lab, thr, ge=False)), (n, canvas, thr, ncls)
+
+
+@pytest.mark.parametrize("seed", range(8 * SOAK))
+def test_multiclass_nms_random(cuda, oracle, seed):
+    """multiclass_nms_rotated with random class counts, score thresholds and max_num; shared and per-class boxes."""
+    from rs_detection_b200.jdet.ops.nms_rotated import multiclass_nms_rotated
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice([1, 17, 64, 300, 1500]))
+    ncls = int(rng.choice([1, 2, 10, 15, 37]))
+    per_class = bool(seed & 1)
+    thr = float(rng.choice([0.1, 0.3, 0.5]))
+    score_thr = float(rng.choice([0.0, 0.001, 0.05, 0.3]))
+    max_num = int(rng.choice([-1, 1, 100, 2000]))
+    base = W.rotated_boxes(n, 50 + seed, canvas=600, smin=8, smax=200)
+    if per_class:
+        boxes = np.concatenate([base[:, None, :] + rng.normal(0, 1.0, (n, ncls + 1, 5)).astype(np.float32) * [3, 3, 1, 1, 0.02]], 1)
+        boxes[..., 2:4] = np.abs(boxes[..., 2:4]) + 1
+        mb = boxes.reshape(n, -1).astype(np.float32)
+    else:
+        mb = base
+    logits = rng.standard_normal((n, ncls + 1)).astype(np.float32) * 2
+    e = np.exp(logits - logits.max(1, keepdims=True))
+    ms = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    ms += (np.arange(ms.size, dtype=np.float32).reshape(ms.shape) * 1e-9)       # no exact score ties
+    wd, wl = oracle.multiclass_nms_rotated(mb, ms, score_thr, dict(iou_thr=thr), max_num)
+    gd, gl = multiclass_nms_rotated(_t(mb), _t(ms), score_thr, dict(type="nms_rotated", iou_thr=thr), max_num)
+    gd, gl = gd.cpu().numpy(), gl.cpu().numpy()
+    print(f"seed {seed}: n={n} classes={ncls} per_class={per_class} thr={thr} score_thr={score_thr} max_num={max_num}: kept {len(wl)}")
+    assert gd.shape == wd.shape and np.array_equal(gl, wl)
+    assert np.array_equal(gd, wd)
+
+
+@pytest.mark.parametrize("seed", range(6 * SOAK))
+def test_poly_nms_and_transforms_random(cuda, oracle, seed):
+    from rs_detection_b200.jdet.ops.bbox_transforms import obb2hbb, obb2poly, poly2hbb
+    from rs_detection_b200.jdet.ops.nms_poly import poly_nms
+    rng = np.random.default_rng(6000 + seed)
+    n = int(rng.choice([1, 33, 64, 65, 400, 1800]))
+    canvas = int(rng.choice([128, 1024]))
+    d = W.rotated_boxes(n, 60 + seed, canvas=canvas, smin=6, smax=canvas // 4)
+    polys = oracle.obb2poly(d)
+    got = obb2poly(_t(d)).cpu().numpy()
+    assert np.abs(got - polys).max() <= 1e-4 * canvas
+    assert np.abs(obb2hbb(_t(d)).cpu().numpy() - oracle.obb2hbb(d)).max() <= 1e-4 * canvas
+    assert np.abs(poly2hbb(_t(polys)).cpu().numpy() - oracle.poly2hbb(polys)).max() == 0
+    s = W.distinct_scores(n, 61 + seed)
+    thr = float(rng.choice([0.1, 0.3, 0.6]))
+    boxes = np.concatenate([polys, s[:, None]], 1).astype(np.float32)
+    iou = oracle.poly_iou_matrix(polys, polys)
+    if band_pairs(iou[~np.eye(n, dtype=bool)], thr):
+        pytest.skip("a pair inside the 1e-6 band around the threshold")
+    got = poly_nms(_t(boxes), thr).cpu().numpy()
+    assert np.array_equal(got, oracle.poly_nms(boxes, thr)), (n, canvas, thr)
