@@ -3,8 +3,8 @@ odd channel counts, every pooled size / sampling grid, both angle conventions, R
 duplicate boxes, box counts around the 64-box block edges, random label and threshold draws.  Every case goes through
 the jdet mirror -> C ABI and is compared with the oracle (oracle/rsdet_oracle.c, bit-pinned to the reference source by
 tests/test_oracle_vs_ref.py).  Contract as in the fixed-size tests: RoIAlign forward 1e-5 / backward 1e-4 of the tensor
-scale, IoU 1e-6 absolute, keep sets exact unless an IoU lies within 1e-6 of the threshold (such draws are skipped and
-counted)."""
+scale, IoU 1e-6 absolute, keep sets exact (a draw may differ only if one of its IoUs lies within 1e-6 of the threshold; it is then
+reported as skipped)."""
 import numpy as np
 import pytest
 import torch
@@ -142,14 +142,16 @@ def test_nms_random(cuda, oracle, seed):
     d = _random_boxes(rng, n, canvas)
     s = W.distinct_scores(n, 9 + seed)
     iou = oracle.box_iou_rotated(d, d, 0, 1)
-    if band_pairs(iou[~np.eye(n, dtype=bool)], thr):
-        pytest.skip("a pair inside the 1e-6 band around the threshold")
+    in_band = band_pairs(iou[~np.eye(n, dtype=bool)], thr)
     got = nms_rotated(_t(d), _t(s), thr).cpu().numpy()
-    assert np.array_equal(got, oracle.nms_rotated(d, s, thr, ge=False)), (n, canvas, thr)
     ncls = int(rng.choice([1, 2, 7, 40]))
     lab = rng.integers(0, ncls, n)
-    got = ml_nms_rotated(_t(d), _t(s), _t(lab.astype(np.int64)), thr).cpu().numpy()
-    assert np.array_equal(got, oracle.ml_nms_rotated(d, s, lab, thr, ge=False)), (n, canvas, thr, ncls)
+    got_ml = ml_nms_rotated(_t(d), _t(s), _t(lab.astype(np.int64)), thr).cpu().numpy()
+    same = np.array_equal(got, oracle.nms_rotated(d, s, thr, ge=False)) and \
+        np.array_equal(got_ml, oracle.ml_nms_rotated(d, s, lab, thr, ge=False))
+    if not same and in_band:
+        pytest.skip(f"{in_band} pairs inside the 1e-6 band around the threshold (outside the contract)")
+    assert same, (n, canvas, thr, ncls)
 
 
 @pytest.mark.parametrize("seed", range(8 * SOAK))
@@ -199,7 +201,9 @@ def test_poly_nms_and_transforms_random(cuda, oracle, seed):
     thr = float(rng.choice([0.1, 0.3, 0.6]))
     boxes = np.concatenate([polys, s[:, None]], 1).astype(np.float32)
     iou = oracle.poly_iou_matrix(polys, polys)
-    if band_pairs(iou[~np.eye(n, dtype=bool)], thr):
-        pytest.skip("a pair inside the 1e-6 band around the threshold")
+    in_band = band_pairs(iou[~np.eye(n, dtype=bool)], thr)
     got = poly_nms(_t(boxes), thr).cpu().numpy()
-    assert np.array_equal(got, oracle.poly_nms(boxes, thr)), (n, canvas, thr)
+    same = np.array_equal(got, oracle.poly_nms(boxes, thr))
+    if not same and in_band:
+        pytest.skip(f"{in_band} pairs inside the 1e-6 band around the threshold (outside the contract)")
+    assert same, (n, canvas, thr)
