@@ -207,3 +207,29 @@ def test_poly_nms_and_transforms_random(cuda, oracle, seed):
     if not same and in_band:
         pytest.skip(f"{in_band} pairs inside the 1e-6 band around the threshold (outside the contract)")
     assert same, (n, canvas, thr)
+
+
+@pytest.mark.parametrize("seed", range(6 * SOAK))
+def test_merge_stage_random(cuda, oracle, seed):
+    """Merge stage (float64): random scenes through the dense tiles (< 8192 detections) and the sparse path (>= 8192),
+    one launch for all classes vs one py_cpu_nms_poly_fast call per class; then merge.py's hbb rule on the same scene."""
+    from rs_detection_b200.jdet import merge as jmerge
+    from rs_detection_b200.jdet.data.devkits.result_merge import merge_detections
+    rng = np.random.default_rng(7000 + seed)
+    objects = int(rng.choice([1, 40, 700, 2200, 4500]))
+    scene = int(rng.choice([1100, 2500, 7000]))
+    jitter = float(rng.choice([0.3, 1.0, 4.0]))
+    sc = W.merge_scene(num_objects=objects, scene=scene, seed=100 + seed, jitter_px=jitter)
+    thr = rng.choice([0.05, 0.1, 0.3, 0.5], 10)
+    got = merge_detections(sc["polys"], sc["scores"], sc["labels"], group_thresh=thr)
+    want = []
+    for c in range(10):
+        idx = np.nonzero(sc["labels"] == c)[0]
+        dets = np.concatenate([sc["polys"][idx], sc["scores"][idx, None]], 1)
+        want += [idx[k] for k in oracle.py_cpu_nms_poly_fast(dets, thr[c], stable_ties=True)]
+    print(f"seed {seed}: {sc['scores'].size} detections of {objects} objects, scene {scene}, jitter {jitter}: kept {len(want)}")
+    assert sorted(got.tolist()) == sorted(want)
+    p = sc["polys"][: min(3000, sc["scores"].size)]
+    hbb = np.stack([p[:, 0::2].min(1), p[:, 1::2].min(1), p[:, 0::2].max(1), p[:, 1::2].max(1), sc["scores"][: p.shape[0]]], 1)
+    t = float(rng.choice([0.3, 0.625]))
+    assert np.array_equal(jmerge.nms(hbb, t), oracle.hbb_nms(hbb, t, stable_ties=True))
