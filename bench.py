@@ -483,7 +483,7 @@ def run_ours(args, rank, world, local_rank):
     U = float(np.mean([touched_pixels(t[1]) for t in tiles_np[:2]]))
     algo_bytes = 4.0 * K_ROIS * W.CHANNELS * 49 + 24.0 * K_ROIS + 4.0 * W.CHANNELS * U
     achieved = algo_bytes / (ms_fwd_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "roi_align_fwd77_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "roi_align_fwd77p_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": ms_fwd_kernel, "launches_timed": len(ks),
                 "call_ms_with_geometry_and_order_kernels": ms_fwd_call, "touched_pixels": U}

@@ -274,6 +274,8 @@ __global__ void roi_geometry_kernel(LevelSet L, const float* __restrict__ rois, 
                                     RoiGeom* __restrict__ geoms, RoiGeom* __restrict__ gsorted, int32_t* __restrict__ levels_out) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;   // position in processing order
     if (p >= K) return;
+    // record K of gsorted holds the work counter of the persistent forward kernel, which runs after this one
+    if (p == 0 && gsorted) *reinterpret_cast<unsigned*>(gsorted + K) = 0u;
     const int i = order ? order[p] : p;
     RoiGeom g = roi_geometry(rois + (size_t)i * 6, L);
     geoms[i] = g;
@@ -736,8 +738,8 @@ roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __re
 //   * a CTA starts from the geometry record in processing order (one global round trip instead of order -> geoms).
 // Arithmetic and tap order are those of roi_align_fwd_kernel<2>; results are bit-identical.
 constexpr size_t kStage77Offset = (8 * 49 * 17 + 15 + ((49 * 4 + 15) & ~15) + 127) & ~(size_t)127;   // lists + counts, rounded up
-template <int WARPS, int FLAVOUR = 0>
-__global__ void __launch_bounds__(32 * WARPS, 4)
+template <int WARPS, int FLAVOUR = 0, int MINB = 4>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
 roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, float* __restrict__ out) {
     constexpr int NB = 49, CAP = 16, PITCH = CAP + 1, THREADS = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -816,6 +818,155 @@ roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, f
     } else {
         for (int i = tid; i < 256 * NB; i += THREADS) __stcs(dst + i, s_stage[i]);
     }
+}
+
+// ---------------------------------------------------------------------------------- forward (7x7, persistent) -- the default
+// roi_align_fwd77_kernel as a PERSISTENT CTA, three per SM (profiles/README.md "third pass"):
+//   * 148 x 3 CTAs of 8 warps take (RoI, 256-channel chunk) items from a counter in the workspace (dynamic: RoIs differ
+//     in tap count); the counter is zeroed by roi_geometry_kernel, which always runs in front of this kernel on the
+//     same stream, so concurrent calls on different streams and CUDA-graph replays need nothing else;
+//   * three CTAs instead of four leave the compiler 78 registers (no spill at 8 warps) and -- what the experiments that
+//     forced the CTA count by padding shared memory could not show -- let the driver pick the 196 KB carve-out: L1 grows
+//     from 28 to 60 KB, its hit rate from 14 % to 27 %, the bytes pulled through the SM's L2 port fall by 16 %;
+//   * the merged lists are built IN PLACE (A1 writes the sixteen raw taps of a bin into the bin's own list slots, A2
+//     reads them into registers and writes the merged entries back), so the list build no longer borrows the staging
+//     block and runs while the previous item's bulk store is still reading it; the next item's geometry record is
+//     fetched with cp.async during the gather.
+// Lists have a pitch of 18 entries (16-byte aligned: a batch's four entries are two LDS.128; the count sits in entry 16).
+// Arithmetic and tap order are those of roi_align_fwd77_kernel: bit-identical results.
+constexpr size_t kStage77pOffset = (8 * 49 * 18 + 16 + 48 + 127) & ~(size_t)127;   // lists | next item | next record | staging
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, int chunks, float* __restrict__ out,
+                        unsigned* __restrict__ counter) {
+    constexpr int NB = 49, PITCH = 18, THREADS = 32 * WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2* s_list = reinterpret_cast<int2*>(smem_raw);
+    volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + 8 * NB * PITCH);
+    const RoiGeom* s_geom = reinterpret_cast<const RoiGeom*>(smem_raw + 8 * NB * PITCH + 16);
+    float* s_stage = reinterpret_cast<float*>(smem_raw + kStage77pOffset);
+    const int C = L.C, items = K * chunks;
+    const int oct = (lane >> 3) & 3;
+    float* const sbase = s_stage + lane * 4 * NB;
+    int idx = blockIdx.x;
+    if (tid < 3 && idx < items)
+        reinterpret_cast<float4*>(smem_raw + 8 * NB * PITCH + 16)[tid] = reinterpret_cast<const float4*>(gsorted + idx / chunks)[tid];
+    __syncthreads();
+#pragma unroll 1
+    while (idx < items) {
+        RoiGeom g = *s_geom;                   // this item's record (prefetched during the previous gather)
+        const int roi = g.gh;                  // processing-order record: gh carries the RoI index
+        g.gh = 2; g.gw = 2;
+        const int chunk0 = (idx % chunks) * 256;
+        const int H = L.H[g.level], W = L.W[g.level];
+        // A1: one thread per sample, raw taps straight into the bin's list slots
+        if (tid < NB * 4) {
+            const int b = tid >> 2, q = tid & 3;
+            const int ph = b / 7, pw = b - ph * 7, iy = q >> 1, ix = q & 1;
+            float x, y;
+            sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+            const Taps t = make_taps(H, W, y, x);
+#pragma unroll
+            for (int k = 0; k < 4; k++) s_list[b * PITCH + q * 4 + k] = make_int2(t.o[k] * (C >> 2), __float_as_int(t.w[k]));
+        }
+        __syncthreads();
+        // A2: one lane per bin, merge in registers, write back in place (same arithmetic and order as build_tap_lists)
+        if (tid < NB) {
+            const int b = tid;
+            int o[16];
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { const int2 e = s_list[b * PITCH + j]; o[j] = e.x; w[j] = __int_as_float(e.y); }
+            int pos = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float acc = w[j];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i <= j) continue;
+                    const bool same = o[i] == o[j] && w[j] != 0.f;
+                    acc += same ? w[i] : 0.f;
+                    w[i] = same ? 0.f : w[i];
+                }
+                if (w[j] != 0.f) s_list[b * PITCH + pos++] = make_int2(o[j], __float_as_int(acc));
+            }
+            s_list[b * PITCH + 16] = make_int2(pos, 0);
+        }
+        if (tid == THREADS - 1) {      // a thread without A1 / A2 work: the previous block must have left the staging area; next item
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // returns at once when nothing is pending
+            *s_next = (int)(atomicAdd(counter, 1u) + gridDim.x);
+        }
+        __syncthreads();
+        if (tid < 3 && *s_next < items) {      // the next record: three 16-byte async copies, in flight during the gather
+            const int nidx = *s_next;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_geom) + 16u * tid),
+                         "l"(reinterpret_cast<const char*>(gsorted + nidx / chunks) + 16 * tid) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+
+        const float4* __restrict__ feat =
+            reinterpret_cast<const float4*>(L.feat[g.level] + (size_t)g.batch * H * W * C + chunk0) + lane;
+        auto stage = [&](float4 a0, float4 a1, int b) {
+            a0.x *= 0.25f; a0.y *= 0.25f; a0.z *= 0.25f; a0.w *= 0.25f;   // output_val /= count (:143), count = 4: exact
+            a1.x *= 0.25f; a1.y *= 0.25f; a1.z *= 0.25f; a1.w *= 0.25f;
+            const float4 r0 = rot4(a0, oct), r1 = rot4(a1, oct);
+            float* const sb = sbase + b;
+            float* const q0 = sb + ((0 + oct) & 3) * NB;
+            float* const q1 = sb + ((1 + oct) & 3) * NB;
+            float* const q2 = sb + ((2 + oct) & 3) * NB;
+            float* const q3 = sb + ((3 + oct) & 3) * NB;
+            q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
+            q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
+        };
+#define RSDET_ACCP(P, WT, VA, VB)                                                                                       \
+        if (P) {                                                                                                        \
+            acc0.x = fmaf(WT, VA.x, acc0.x); acc0.y = fmaf(WT, VA.y, acc0.y); acc0.z = fmaf(WT, VA.z, acc0.z); acc0.w = fmaf(WT, VA.w, acc0.w); \
+            acc1.x = fmaf(WT, VB.x, acc1.x); acc1.y = fmaf(WT, VB.y, acc1.y); acc1.z = fmaf(WT, VB.z, acc1.z); acc1.w = fmaf(WT, VB.w, acc1.w); \
+        }
+        const int2* lp = s_list + warp * PITCH;
+        int4 ea = reinterpret_cast<const int4*>(lp)[0], eb = reinterpret_cast<const int4*>(lp)[1];
+        int cnt = lp[16].x;
+#pragma unroll 1
+        for (int b = warp; b < NB; b += WARPS) {
+            float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+            const int nbin = min(b + WARPS, NB - 1);
+            int ncnt = cnt;
+            int e = 0;
+#pragma unroll 1
+            do {
+                const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
+                float4 v00, v01, v10, v11, v20, v21, v30, v31;
+                if (p0) { const float* q = tap_ptr(feat, (unsigned)ea.x); v00 = ldg_nc_v4(q); v01 = ldg_nc_v4(q + 128); }
+                if (p1) { const float* q = tap_ptr(feat, (unsigned)ea.z); v10 = ldg_nc_v4(q); v11 = ldg_nc_v4(q + 128); }
+                if (p2) { const float* q = tap_ptr(feat, (unsigned)eb.x); v20 = ldg_nc_v4(q); v21 = ldg_nc_v4(q + 128); }
+                if (p3) { const float* q = tap_ptr(feat, (unsigned)eb.z); v30 = ldg_nc_v4(q); v31 = ldg_nc_v4(q + 128); }
+                const float w0 = __int_as_float(ea.y), w1 = __int_as_float(ea.w), w2 = __int_as_float(eb.y), w3 = __int_as_float(eb.w);
+                e += 4;
+                const bool more = e < cnt;
+                const int2* np = more ? lp + e : s_list + nbin * PITCH;
+                if (!more) ncnt = s_list[nbin * PITCH + 16].x;
+                ea = reinterpret_cast<const int4*>(np)[0]; eb = reinterpret_cast<const int4*>(np)[1];
+                RSDET_ACCP(p0, w0, v00, v01) RSDET_ACCP(p1, w1, v10, v11) RSDET_ACCP(p2, w2, v20, v21) RSDET_ACCP(p3, w3, v30, v31)
+            } while (e < cnt);
+            stage(acc0, acc1, b);
+            lp = s_list + nbin * PITCH;
+            cnt = ncnt;
+        }
+#undef RSDET_ACCP
+        if (tid < 3) asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == THREADS - 1) {      // the thread that will wait for it
+            unsigned long long pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         ::"l"(out + ((size_t)roi * C + chunk0) * NB), "r"((unsigned)__cvta_generic_to_shared(s_stage)), "r"(256u * NB * 4u), "l"(pol) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        idx = *s_next;
+    }
+    if (tid == THREADS - 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // cudaFuncSetAttribute is per device: remember what was set for each one (a process may drive several GPUs)
@@ -1062,7 +1213,9 @@ using namespace rsdet;
 extern "C" size_t rsdet_roi_align_rotated_workspace_bytes(const rsdet_roi_align_cfg* cfg, int num_rois, int backward) {
     (void)backward;
     if (check_cfg(cfg) != RSDET_OK) return 0;
-    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1) + 2 * ws_bytes<RoiGeom>(num_rois > 0 ? num_rois : 1);  // order, geometry, geometry in processing order
+    // order, geometry, geometry in processing order (+ one record: the work counter of the persistent forward kernel)
+    size_t b = ws_bytes<int>(num_rois > 0 ? num_rois : 1) + ws_bytes<RoiGeom>(num_rois > 0 ? num_rois : 1) +
+               ws_bytes<RoiGeom>((num_rois > 0 ? num_rois : 1) + 1);
 #ifdef RSDET_TUNING
     if (fast_path_ok(cfg) && split_path_ok(cfg))   // tap-list records of the A/B kernels
         b += ws_bytes<unsigned char>((size_t)(num_rois > 0 ? num_rois : 1) *
@@ -1101,7 +1254,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     Workspace ws(workspace, workspace_bytes);
     int* order_ws = ws.take<int>(num_rois);
     RoiGeom* geoms = ws.take<RoiGeom>(num_rois);
-    RoiGeom* gsorted = ws.take<RoiGeom>(num_rois);
+    RoiGeom* gsorted = ws.take<RoiGeom>(num_rois + 1);
     if (cfg->channels_last) {
         for (int l = 0; l < cfg->num_levels; l++) L.feat[l] = feats_host[l];
     } else {
@@ -1156,12 +1309,55 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
         if (flavour == 3) { set_dyn_smem((const void*)roi_align_fwd77_kernel<8, 3>, smem); roi_align_fwd77_kernel<8, 3><<<g77, 256, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
 #endif
 #ifdef RSDET_TUNING
+        if (const char* e = getenv("RSDET_ROI_MINB3")) {     // A/B: three CTAs per SM by launch bounds (more registers, smaller carve-out)
+            const int w = atoi(e);
+            const int carve = getenv("RSDET_ROI_CARVE") ? atoi(getenv("RSDET_ROI_CARVE")) : -1;
+#define RSDET_L3(W_) { set_dyn_smem((const void*)roi_align_fwd77_kernel<W_, 0, 3>, smem); \
+                       if (carve >= 0) cudaFuncSetAttribute(roi_align_fwd77_kernel<W_, 0, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+                       roi_align_fwd77_kernel<W_, 0, 3><<<g77, 32 * W_, smem, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+            if (w == 7) RSDET_L3(7)
+            if (w == 8) RSDET_L3(8)
+            if (w == 9) RSDET_L3(9)
+            if (w == 10) RSDET_L3(10)
+#undef RSDET_L3
+        }
         if (const char* e = getenv("RSDET_ROI_V8")) {       // A/B: 1 = LDS.128 list reads only, 2 = + 256-bit loads
             const size_t sm8 = kStage77v8Offset + sizeof(float) * 49 * 256;
             if (atoi(e) == 1) { set_dyn_smem((const void*)roi_align_fwd77v8_kernel<7, false>, sm8); roi_align_fwd77v8_kernel<7, false><<<g77, 224, sm8, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
+            if (atoi(e) == 4 && cfg->channels == 256 && (((size_t)out) & 15) == 0) {
+                unsigned* ctr = nullptr;
+                cudaGetSymbolAddress((void**)&ctr, g_roi77p_counter);
+                cudaMemsetAsync(ctr, 0, sizeof(unsigned), st);
+                const int ctas = getenv("RSDET_ROI_PCTAS") ? atoi(getenv("RSDET_ROI_PCTAS")) : kNumSMs * 3;
+                const int gw = getenv("RSDET_ROI_PWARPS") ? atoi(getenv("RSDET_ROI_PWARPS")) : 8;
+                const int grid = num_rois < ctas ? num_rois : ctas;
+                const size_t smw = ((2 * 8 * 49 * 18 + 32 + 127) & ~127) + sizeof(float) * 49 * 256;
+                if (gw == 7) { set_dyn_smem((const void*)roi_align_fwd77ws_kernel<7, 3>, smw); roi_align_fwd77ws_kernel<7, 3><<<grid, 256, smw, st>>>(L, gsorted, num_rois, out); }
+                else { set_dyn_smem((const void*)roi_align_fwd77ws_kernel<8, 3>, smw); roi_align_fwd77ws_kernel<8, 3><<<grid, 288, smw, st>>>(L, gsorted, num_rois, out); }
+                count_launch();
+                return cuda_status();
+            }
             if (atoi(e) == 2) { set_dyn_smem((const void*)roi_align_fwd77v8_kernel<7, true>, sm8); roi_align_fwd77v8_kernel<7, true><<<g77, 224, sm8, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
         }
 #endif
+        bool persistent = (((size_t)out) & 15) == 0;    // the bulk store needs a 16-byte aligned output block
+#ifdef RSDET_TUNING
+        if (getenv("RSDET_ROI_NOPERSIST")) persistent = false;
+#endif
+        if (persistent) {
+            const int chunks = cfg->channels / 256;
+            const long long items = (long long)num_rois * chunks;
+            int ctas = kNumSMs * 3;
+#ifdef RSDET_TUNING
+            if (const char* e = getenv("RSDET_ROI_PCTAS")) ctas = atoi(e);
+#endif
+            const size_t smp = kStage77pOffset + sizeof(float) * 49 * 256;
+            set_dyn_smem((const void*)roi_align_fwd77p_kernel<8, 3>, smp);
+            roi_align_fwd77p_kernel<8, 3><<<(int)(items < ctas ? items : ctas), 256, smp, st>>>(
+                L, gsorted, num_rois, chunks, out, reinterpret_cast<unsigned*>(gsorted + num_rois));
+            count_launch();
+            return cuda_status();
+        }
         if (warps == 7) {
             set_dyn_smem((const void*)roi_align_fwd77_kernel<7>, smem);
             roi_align_fwd77_kernel<7><<<dim3(num_rois, cfg->channels / 256), 224, smem, st>>>(L, gsorted, num_rois, out);

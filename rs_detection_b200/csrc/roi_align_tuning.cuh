@@ -126,6 +126,171 @@ roi_align_fwd77v8_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K,
     }
 }
 
+// ---------------------------------------------------------------------------------- forward (7x7, persistent, warp-specialised bin-major)
+// A/B only (RSDET_ROI_V8 = 4).  Persistent CTA of GW gather warps + one builder warp, double-buffered in-place lists:
+// the builder fetches the next RoI (global counter), builds its merged lists while the gather warps work on the current
+// one, and owns the bulk store of the finished block.  Hand-offs are named barriers (bar.arrive / bar.sync, 288 threads):
+//   FULL[p]  builder -> gatherers   lists + meta of the RoI in buffer p are published
+//   DONE     gatherers -> builder   every gather warp has staged its bins of the current RoI
+//   FREE     builder -> gatherers   the bulk store of the previous RoI has finished reading the staging block
+__device__ unsigned g_roi77p_counter;   // A/B kernel only: single-stream measurements
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+template <int GW, int MINB>
+__global__ void __launch_bounds__(32 * (GW + 1), MINB)
+roi_align_fwd77ws_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, float* __restrict__ out) {
+    constexpr int NB = 49, PITCH = 18, ALL = 32 * (GW + 1);
+    constexpr int kMetaOff = 2 * 8 * NB * PITCH, kStageOff = (kMetaOff + 32 + 127) & ~127;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2* s_lists = reinterpret_cast<int2*>(smem_raw);
+    volatile int4* s_meta = reinterpret_cast<volatile int4*>(smem_raw + kMetaOff);      // {roi, level, batch, valid} per buffer
+    float* s_stage = reinterpret_cast<float*>(smem_raw + kStageOff);
+    const int C = L.C;
+    if (warp == GW) {
+        // ------------------------------------------------------------------ builder warp
+        auto build = [&](int idx, int p) {
+            RoiGeom g = gsorted[idx];
+            const int roi = g.gh;
+            g.gh = 2; g.gw = 2;
+            const int H = L.H[g.level], W = L.W[g.level];
+            int2* sl = s_lists + p * NB * PITCH;
+#pragma unroll 1
+            for (int s = lane; s < NB * 4; s += 32) {       // A1: raw taps into the bin's own list slots
+                const int b = s >> 2, q = s & 3;
+                const int ph = b / 7, pw = b - ph * 7, iy = q >> 1, ix = q & 1;
+                float x, y;
+                sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+                const Taps t = make_taps(H, W, y, x);
+#pragma unroll
+                for (int k = 0; k < 4; k++) sl[b * PITCH + q * 4 + k] = make_int2(t.o[k] * (C >> 2), __float_as_int(t.w[k]));
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int b = lane; b < NB; b += 32) {           // A2: merge in registers, write back in place
+                int o[16];
+                float w[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) { const int2 e = sl[b * PITCH + j]; o[j] = e.x; w[j] = __int_as_float(e.y); }
+                int pos = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float acc = w[j];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        if (i <= j) continue;
+                        const bool same = o[i] == o[j] && w[j] != 0.f;
+                        acc += same ? w[i] : 0.f;
+                        w[i] = same ? 0.f : w[i];
+                    }
+                    if (w[j] != 0.f) sl[b * PITCH + pos++] = make_int2(o[j], __float_as_int(acc));
+                }
+                sl[b * PITCH + 16] = make_int2(pos, 0);
+            }
+            if (lane == 0) { s_meta[p].x = roi; s_meta[p].y = g.level; s_meta[p].z = g.batch; s_meta[p].w = 1; }
+            __syncwarp();
+        };
+        int p = 0;
+        build(blockIdx.x, 0);
+        __threadfence_block();
+        nb_arrive(1, ALL);
+#pragma unroll 1
+        for (;;) {
+            int nidx = 0;
+            if (lane == 0) nidx = (int)(atomicAdd(&g_roi77p_counter, 1u) + gridDim.x);
+            nidx = __shfl_sync(0xffffffffu, nidx, 0);
+            const bool nvalid = nidx < K;
+            if (nvalid) build(nidx, p ^ 1);
+            else if (lane == 0) s_meta[p ^ 1].w = 0;
+            __threadfence_block();
+            nb_arrive(1 + (p ^ 1), ALL);
+            nb_sync(3, ALL);                                // the current RoI's block is complete in the staging area
+            if (lane == 0) {
+                const int roi = s_meta[p].x;
+                unsigned long long pol;
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                             ::"l"(out + (size_t)roi * C * NB), "r"((unsigned)__cvta_generic_to_shared(s_stage)), "r"(256u * NB * 4u), "l"(pol) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            if (!nvalid) break;
+            nb_arrive(4, ALL);                              // staging area free again
+            p ^= 1;
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- gather warps
+    const int oct = (lane >> 3) & 3;
+    float* const sbase = s_stage + lane * 4 * NB;
+    int p = 0;
+    bool need_free = false;
+#pragma unroll 1
+    for (;;) {
+        nb_sync(1 + p, ALL);
+        const int roi_valid = s_meta[p].w;
+        if (!roi_valid) break;
+        const int level = s_meta[p].y, batch = s_meta[p].z;
+        const int H = L.H[level], W = L.W[level];
+        const int2* s_list = s_lists + p * NB * PITCH;
+        const float4* __restrict__ feat = reinterpret_cast<const float4*>(L.feat[level] + (size_t)batch * H * W * C) + lane;
+        auto stage = [&](float4 a0, float4 a1, int b) {
+            a0.x *= 0.25f; a0.y *= 0.25f; a0.z *= 0.25f; a0.w *= 0.25f;
+            a1.x *= 0.25f; a1.y *= 0.25f; a1.z *= 0.25f; a1.w *= 0.25f;
+            const float4 r0 = rot4(a0, oct), r1 = rot4(a1, oct);
+            float* const sb = sbase + b;
+            float* const q0 = sb + ((0 + oct) & 3) * NB;
+            float* const q1 = sb + ((1 + oct) & 3) * NB;
+            float* const q2 = sb + ((2 + oct) & 3) * NB;
+            float* const q3 = sb + ((3 + oct) & 3) * NB;
+            q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
+            q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
+        };
+#define RSDET_ACCW(P, WT, VA, VB)                                                                                       \
+        if (P) {                                                                                                        \
+            acc0.x = fmaf(WT, VA.x, acc0.x); acc0.y = fmaf(WT, VA.y, acc0.y); acc0.z = fmaf(WT, VA.z, acc0.z); acc0.w = fmaf(WT, VA.w, acc0.w); \
+            acc1.x = fmaf(WT, VB.x, acc1.x); acc1.y = fmaf(WT, VB.y, acc1.y); acc1.z = fmaf(WT, VB.z, acc1.z); acc1.w = fmaf(WT, VB.w, acc1.w); \
+        }
+        const int2* lp = s_list + warp * PITCH;
+        int4 ea = reinterpret_cast<const int4*>(lp)[0], eb = reinterpret_cast<const int4*>(lp)[1];
+        int cnt = lp[16].x;
+#pragma unroll 1
+        for (int b = warp; b < NB; b += GW) {
+            float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+            const int nbin = min(b + GW, NB - 1);
+            int ncnt = cnt;
+            int e = 0;
+#pragma unroll 1
+            do {
+                const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
+                float4 v00, v01, v10, v11, v20, v21, v30, v31;
+                if (p0) { const float* q = tap_ptr(feat, (unsigned)ea.x); v00 = ldg_nc_v4(q); v01 = ldg_nc_v4(q + 128); }
+                if (p1) { const float* q = tap_ptr(feat, (unsigned)ea.z); v10 = ldg_nc_v4(q); v11 = ldg_nc_v4(q + 128); }
+                if (p2) { const float* q = tap_ptr(feat, (unsigned)eb.x); v20 = ldg_nc_v4(q); v21 = ldg_nc_v4(q + 128); }
+                if (p3) { const float* q = tap_ptr(feat, (unsigned)eb.z); v30 = ldg_nc_v4(q); v31 = ldg_nc_v4(q + 128); }
+                const float w0 = __int_as_float(ea.y), w1 = __int_as_float(ea.w), w2 = __int_as_float(eb.y), w3 = __int_as_float(eb.w);
+                e += 4;
+                const bool more = e < cnt;
+                const int2* np = more ? lp + e : s_list + nbin * PITCH;
+                if (!more) ncnt = s_list[nbin * PITCH + 16].x;
+                ea = reinterpret_cast<const int4*>(np)[0]; eb = reinterpret_cast<const int4*>(np)[1];
+                RSDET_ACCW(p0, w0, v00, v01) RSDET_ACCW(p1, w1, v10, v11) RSDET_ACCW(p2, w2, v20, v21) RSDET_ACCW(p3, w3, v30, v31)
+            } while (e < cnt);
+            if (need_free) { nb_sync(4, ALL); need_free = false; }      // once per RoI and warp, before its first staging write
+            stage(acc0, acc1, b);
+            lp = s_list + nbin * PITCH;
+            cnt = ncnt;
+        }
+#undef RSDET_ACCW
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __threadfence_block();
+        nb_arrive(3, ALL);
+        need_free = true;
+        p ^= 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------- forward (channel-split passes)
 // Same tap lists and the same warp = bin gather, but a 256-channel chunk is produced in NP passes of 256/NP channels:
 // the staging block shrinks to 50/NP KB, so four resident CTAs leave most of the SM's 256 KB to L1 -- the pixel rows
