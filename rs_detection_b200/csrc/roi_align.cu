@@ -835,7 +835,7 @@ roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, f
 // Lists have a pitch of 18 entries (16-byte aligned: a batch's four entries are two LDS.128; the count sits in entry 16).
 // Arithmetic and tap order are those of roi_align_fwd77_kernel: bit-identical results.
 constexpr size_t kStage77pOffset = (8 * 49 * 18 + 16 + 48 + 127) & ~(size_t)127;   // lists | next item | next record | staging
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, int TAPS = 4>   // TAPS: list entries per batch (4, 6 or 8 = 8 / 12 / 16 16-byte loads in flight per thread)
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, int chunks, float* __restrict__ out,
                         unsigned* __restrict__ counter) {
@@ -891,6 +891,14 @@ roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, 
                 }
                 if (w[j] != 0.f) s_list[b * PITCH + pos++] = make_int2(o[j], __float_as_int(acc));
             }
+#ifdef RSDET_TUNING   // what-if: 1 of every `dbg_drop` entries removed (wrong results, timing of a deduplicated list)
+            if (L.dbg_drop > 1) {
+                int q = 0;
+                for (int e = 0; e < pos; e++)
+                    if ((e + b) % L.dbg_drop != 0) s_list[b * PITCH + q++] = s_list[b * PITCH + e];
+                pos = q;
+            }
+#endif
             s_list[b * PITCH + 16] = make_int2(pos, 0);
         }
         if (tid == THREADS - 1) {      // a thread without A1 / A2 work: the previous block must have left the staging area; next item
@@ -919,13 +927,10 @@ roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, 
             q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
             q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
         };
-#define RSDET_ACCP(P, WT, VA, VB)                                                                                       \
-        if (P) {                                                                                                        \
-            acc0.x = fmaf(WT, VA.x, acc0.x); acc0.y = fmaf(WT, VA.y, acc0.y); acc0.z = fmaf(WT, VA.z, acc0.z); acc0.w = fmaf(WT, VA.w, acc0.w); \
-            acc1.x = fmaf(WT, VB.x, acc1.x); acc1.y = fmaf(WT, VB.y, acc1.y); acc1.z = fmaf(WT, VB.z, acc1.z); acc1.w = fmaf(WT, VB.w, acc1.w); \
-        }
         const int2* lp = s_list + warp * PITCH;
-        int4 ea = reinterpret_cast<const int4*>(lp)[0], eb = reinterpret_cast<const int4*>(lp)[1];
+        int4 en[TAPS / 2];
+#pragma unroll
+        for (int t = 0; t < TAPS / 2; t++) en[t] = reinterpret_cast<const int4*>(lp)[t];
         int cnt = lp[16].x;
 #pragma unroll 1
         for (int b = warp; b < NB; b += WARPS) {
@@ -935,25 +940,32 @@ roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, 
             int e = 0;
 #pragma unroll 1
             do {
-                const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
-                float4 v00, v01, v10, v11, v20, v21, v30, v31;
-                if (p0) { const float* q = tap_ptr(feat, (unsigned)ea.x); v00 = ldg_nc_v4(q); v01 = ldg_nc_v4(q + 128); }
-                if (p1) { const float* q = tap_ptr(feat, (unsigned)ea.z); v10 = ldg_nc_v4(q); v11 = ldg_nc_v4(q + 128); }
-                if (p2) { const float* q = tap_ptr(feat, (unsigned)eb.x); v20 = ldg_nc_v4(q); v21 = ldg_nc_v4(q + 128); }
-                if (p3) { const float* q = tap_ptr(feat, (unsigned)eb.z); v30 = ldg_nc_v4(q); v31 = ldg_nc_v4(q + 128); }
-                const float w0 = __int_as_float(ea.y), w1 = __int_as_float(ea.w), w2 = __int_as_float(eb.y), w3 = __int_as_float(eb.w);
-                e += 4;
+                float4 va[TAPS], vb[TAPS];
+                float wt[TAPS];
+#pragma unroll
+                for (int t = 0; t < TAPS; t++) {
+                    const int off = (t & 1) ? en[t >> 1].z : en[t >> 1].x;
+                    wt[t] = __int_as_float((t & 1) ? en[t >> 1].w : en[t >> 1].y);
+                    if (e + t < cnt) { const float* q = tap_ptr(feat, (unsigned)off); va[t] = ldg_nc_v4(q); vb[t] = ldg_nc_v4(q + 128); }
+                }
+                const int e0 = e;
+                e += TAPS;
                 const bool more = e < cnt;
                 const int2* np = more ? lp + e : s_list + nbin * PITCH;
                 if (!more) ncnt = s_list[nbin * PITCH + 16].x;
-                ea = reinterpret_cast<const int4*>(np)[0]; eb = reinterpret_cast<const int4*>(np)[1];
-                RSDET_ACCP(p0, w0, v00, v01) RSDET_ACCP(p1, w1, v10, v11) RSDET_ACCP(p2, w2, v20, v21) RSDET_ACCP(p3, w3, v30, v31)
+#pragma unroll
+                for (int t = 0; t < TAPS / 2; t++) en[t] = reinterpret_cast<const int4*>(np)[t];
+#pragma unroll
+                for (int t = 0; t < TAPS; t++)
+                    if (e0 + t < cnt) {
+                        acc0.x = fmaf(wt[t], va[t].x, acc0.x); acc0.y = fmaf(wt[t], va[t].y, acc0.y); acc0.z = fmaf(wt[t], va[t].z, acc0.z); acc0.w = fmaf(wt[t], va[t].w, acc0.w);
+                        acc1.x = fmaf(wt[t], vb[t].x, acc1.x); acc1.y = fmaf(wt[t], vb[t].y, acc1.y); acc1.z = fmaf(wt[t], vb[t].z, acc1.z); acc1.w = fmaf(wt[t], vb[t].w, acc1.w);
+                    }
             } while (e < cnt);
             stage(acc0, acc1, b);
             lp = s_list + nbin * PITCH;
             cnt = ncnt;
         }
-#undef RSDET_ACCP
         if (tid < 3) asm volatile("cp.async.wait_all;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -1350,6 +1362,40 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
             int ctas = kNumSMs * 3;
 #ifdef RSDET_TUNING
             if (const char* e = getenv("RSDET_ROI_PCTAS")) ctas = atoi(e);
+#endif
+#ifdef RSDET_TUNING
+            if (getenv("RSDET_ROI_Q")) {      // A/B: pipelined list build (1: dynamic bins, 2: static columns)
+                const size_t smq = kStage77qOffset + sizeof(float) * 49 * 256;
+                unsigned* ctr = reinterpret_cast<unsigned*>(gsorted + num_rois);
+                const int grid = (int)(items < ctas ? items : ctas);
+                if (atoi(getenv("RSDET_ROI_Q")) == 2) {
+                    set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 1>, smq);
+                    roi_align_fwd77q_kernel<8, 3, 1><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
+                } else {
+                    set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 0>, smq);
+                    roi_align_fwd77q_kernel<8, 3, 0><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
+                }
+                count_launch();
+                return cuda_status();
+            }
+            if (const char* e = getenv("RSDET_ROI_PVAR")) {     // A/B: warps x CTAs/SM x taps per batch of the persistent kernel
+                const size_t smv = kStage77pOffset + sizeof(float) * 49 * 256;
+                unsigned* ctr = reinterpret_cast<unsigned*>(gsorted + num_rois);
+                const int v = atoi(e);
+#define RSDET_PV(W_, M_, T_) { const int grid = (int)(items < kNumSMs * M_ ? items : kNumSMs * M_); \
+                               set_dyn_smem((const void*)roi_align_fwd77p_kernel<W_, M_, T_>, smv); \
+                               roi_align_fwd77p_kernel<W_, M_, T_><<<grid, 32 * W_, smv, st>>>(L, gsorted, num_rois, chunks, out, ctr); \
+                               count_launch(); return cuda_status(); }
+                if (v == 1062) RSDET_PV(10, 2, 6)
+                if (v == 1262) RSDET_PV(12, 2, 6)
+                if (v == 882) RSDET_PV(8, 2, 8)
+                if (v == 1082) RSDET_PV(10, 2, 8)
+                if (v == 763) RSDET_PV(7, 3, 6)
+                if (v == 863) RSDET_PV(8, 3, 6)
+                if (v == 1442) RSDET_PV(14, 2, 4)
+                if (v == 1242) RSDET_PV(12, 2, 4)
+#undef RSDET_PV
+            }
 #endif
             const size_t smp = kStage77pOffset + sizeof(float) * 49 * 256;
             set_dyn_smem((const void*)roi_align_fwd77p_kernel<8, 3>, smp);

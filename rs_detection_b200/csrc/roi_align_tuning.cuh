@@ -291,6 +291,203 @@ roi_align_fwd77ws_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K,
     }
 }
 
+// ---------------------------------------------------------------------------------- forward (7x7, persistent, pipelined lists)
+// A/B only (RSDET_ROI_Q = 1 dynamic bins / 2 static columns): measured 126.8 / 125.4 us per tile against 119.2 us for
+// roi_align_fwd77p_kernel -- the warps that merge the next item's lists become the stragglers of the current one
+// (barrier stall 1.88 -> 2.46 per issue), so the shipped kernel keeps the list build in front of the gather.
+// roi_align_fwd77p_kernel with the list build of item i+1 moved under the gather of item i:
+//   * two list buffers; at the top of iteration i every thread computes the raw taps of item i+1 (A1, ~150 instructions),
+//     after the barrier warps 0 and 1 merge them in place (A2, the ~600-instruction dependent chain that used to hold the
+//     other six warps at a barrier) while the other warps already gather item i, then join;
+//   * bins are handed out dynamically (a shared counter, one ATOMS per bin, taken at the start of a bin's last batch so
+//     its latency lies under that batch's loads): the late joiners and the uneven tap counts balance out, and 49 bins no
+//     longer have to be split 7 + 6 x 7 over eight warps;
+//   * two CTA barriers per item instead of three.
+// Same arithmetic and per-bin tap order: bit-identical results.
+constexpr size_t kMeta77qOffset = 2 * 8 * 49 * 18;                                   // two list buffers
+constexpr size_t kStage77qOffset = (kMeta77qOffset + 128 + 127) & ~(size_t)127;     // + meta block
+template <int WARPS, int MINB, int MODE>   // MODE 0: dynamic bins, A2 on warps 0-1; 1: static columns, A2 on warps 6-7 (which share column 6)
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+roi_align_fwd77q_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, int chunks, float* __restrict__ out,
+                        unsigned* __restrict__ counter) {
+    constexpr int NB = 49, PITCH = 18, THREADS = 32 * WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2* s_lists = reinterpret_cast<int2*>(smem_raw);
+    volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + kMeta77qOffset);            // item after the next one
+    int* s_binctr = reinterpret_cast<int*>(smem_raw + kMeta77qOffset + 4);
+    const RoiGeom* s_geom = reinterpret_cast<const RoiGeom*>(smem_raw + kMeta77qOffset + 16);     // record of the NEXT item
+    volatile int4* s_meta = reinterpret_cast<volatile int4*>(smem_raw + kMeta77qOffset + 64);     // per buffer: {roi, chunk0, level, batch}
+    float* s_stage = reinterpret_cast<float*>(smem_raw + kStage77qOffset);
+    const int C = L.C, items = K * chunks;
+    const int oct = (lane >> 3) & 3;
+    float* const sbase = s_stage + lane * 4 * NB;
+
+    // raw taps of item `idx` (record in s_geom) into list buffer `buf`, one thread per sample
+    auto a1 = [&](int idx, int buf) {
+        RoiGeom g = *s_geom;
+        const int roi = g.gh;                  // processing-order record: gh carries the RoI index
+        g.gh = 2; g.gw = 2;
+        const int H = L.H[g.level], W = L.W[g.level];
+        int2* sl = s_lists + buf * NB * PITCH;
+        if (tid < NB * 4) {
+            const int b = tid >> 2, q = tid & 3;
+            const int ph = b / 7, pw = b - ph * 7, iy = q >> 1, ix = q & 1;
+            float x, y;
+            sample_xy(g, L.version, ph, pw, iy, ix, x, y);
+            const Taps t = make_taps(H, W, y, x);
+#pragma unroll
+            for (int k = 0; k < 4; k++) sl[b * PITCH + q * 4 + k] = make_int2(t.o[k] * (C >> 2), __float_as_int(t.w[k]));
+        }
+        if (tid == THREADS - 2) { s_meta[buf].x = roi; s_meta[buf].y = (idx % chunks) * 256; s_meta[buf].z = g.level; s_meta[buf].w = g.batch; }
+    };
+    // merge in place, one lane per bin (same arithmetic and order as build_tap_lists)
+    auto a2 = [&](int buf) {
+        const int t2 = MODE == 1 ? tid - 6 * 32 : tid;
+        if (t2 >= 0 && t2 < NB) {
+            int2* sl = s_lists + buf * NB * PITCH;
+            const int b = t2;
+            int o[16];
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) { const int2 e = sl[b * PITCH + j]; o[j] = e.x; w[j] = __int_as_float(e.y); }
+            int pos = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float acc = w[j];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i <= j) continue;
+                    const bool same = o[i] == o[j] && w[j] != 0.f;
+                    acc += same ? w[i] : 0.f;
+                    w[i] = same ? 0.f : w[i];
+                }
+                if (w[j] != 0.f) sl[b * PITCH + pos++] = make_int2(o[j], __float_as_int(acc));
+            }
+            sl[b * PITCH + 16] = make_int2(pos, 0);
+        }
+    };
+    auto load_record = [&](int idx) {          // three 16-byte async copies into s_geom
+        if (tid < 3 && idx < items) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_geom) + 16u * tid),
+                         "l"(reinterpret_cast<const char*>(gsorted + idx / chunks) + 16 * tid) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+
+    // prologue: lists of the first item, record of the second
+    int idx = blockIdx.x;
+    if (idx >= items) return;
+    load_record(idx);
+    if (tid < 3) asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    a1(idx, 0);
+    if (tid == THREADS - 1) *s_next = (int)(atomicAdd(counter, 1u) + gridDim.x);
+    __syncthreads();
+    int nidx = *s_next;
+    a2(0);
+    load_record(nidx);
+    if (tid < 3) asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    int buf = 0;
+#pragma unroll 1
+    while (true) {
+        const bool have_next = nidx < items;
+        if (have_next) a1(nidx, buf ^ 1);
+        if (tid == THREADS - 1) {      // a thread without A1 / A2 work
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous block has left the staging area
+            *s_binctr = 0;
+            if (have_next) *s_next = (int)(atomicAdd(counter, 1u) + gridDim.x);
+        }
+        __syncthreads();
+        const int nnidx = have_next ? *s_next : items;
+        load_record(nnidx);
+        if (have_next && (MODE == 1 ? warp >= 6 : warp < 2)) a2(buf ^ 1);
+
+        const int roi = s_meta[buf].x, chunk0 = s_meta[buf].y, level = s_meta[buf].z, batch = s_meta[buf].w;
+        const int H = L.H[level], W = L.W[level];
+        const int2* s_list = s_lists + buf * NB * PITCH;
+        const float4* __restrict__ feat = reinterpret_cast<const float4*>(L.feat[level] + (size_t)batch * H * W * C + chunk0) + lane;
+        auto stage = [&](float4 a0, float4 a1_, int b) {
+            a0.x *= 0.25f; a0.y *= 0.25f; a0.z *= 0.25f; a0.w *= 0.25f;   // output_val /= count (:143), count = 4: exact
+            a1_.x *= 0.25f; a1_.y *= 0.25f; a1_.z *= 0.25f; a1_.w *= 0.25f;
+            const float4 r0 = rot4(a0, oct), r1 = rot4(a1_, oct);
+            float* const sb = sbase + b;
+            float* const q0 = sb + ((0 + oct) & 3) * NB;
+            float* const q1 = sb + ((1 + oct) & 3) * NB;
+            float* const q2 = sb + ((2 + oct) & 3) * NB;
+            float* const q3 = sb + ((3 + oct) & 3) * NB;
+            q0[0] = r0.x; q1[0] = r0.y; q2[0] = r0.z; q3[0] = r0.w;
+            q0[128 * NB] = r1.x; q1[128 * NB] = r1.y; q2[128 * NB] = r1.z; q3[128 * NB] = r1.w;
+        };
+        auto grab = [&]() {                    // next unclaimed bin of this item (>= NB: none left)
+            int b = 0;
+            if (lane == 0) b = atomicAdd(s_binctr, 1);
+            return __shfl_sync(0xffffffffu, b, 0);
+        };
+#define RSDET_ACCQ(P, WT, VA, VB)                                                                                       \
+        if (P) {                                                                                                        \
+            acc0.x = fmaf(WT, VA.x, acc0.x); acc0.y = fmaf(WT, VA.y, acc0.y); acc0.z = fmaf(WT, VA.z, acc0.z); acc0.w = fmaf(WT, VA.w, acc0.w); \
+            acc1.x = fmaf(WT, VB.x, acc1.x); acc1.y = fmaf(WT, VB.y, acc1.y); acc1.z = fmaf(WT, VB.z, acc1.z); acc1.w = fmaf(WT, VB.w, acc1.w); \
+        }
+        const int bend = MODE == 1 ? (warp == 6 ? 28 : NB) : NB;
+        auto next_bin = [&](int cur) { if (MODE == 1) return cur + 7 < bend ? cur + 7 : NB; return grab(); };
+        int b = MODE == 1 ? (warp == 7 ? 34 : warp) : grab();
+        if (b < NB) {
+            const int2* lp = s_list + b * PITCH;
+            int4 ea = reinterpret_cast<const int4*>(lp)[0], eb = reinterpret_cast<const int4*>(lp)[1];
+            int cnt = lp[16].x;
+#pragma unroll 1
+            while (b < NB) {
+                float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+                int nbin = NB, ncnt = 0;
+                int e = 0;
+#pragma unroll 1
+                do {
+                    const bool p0 = e < cnt, p1 = e + 1 < cnt, p2 = e + 2 < cnt, p3 = e + 3 < cnt;
+                    float4 v00, v01, v10, v11, v20, v21, v30, v31;
+                    if (p0) { const float* q = tap_ptr(feat, (unsigned)ea.x); v00 = ldg_nc_v4(q); v01 = ldg_nc_v4(q + 128); }
+                    if (p1) { const float* q = tap_ptr(feat, (unsigned)ea.z); v10 = ldg_nc_v4(q); v11 = ldg_nc_v4(q + 128); }
+                    if (p2) { const float* q = tap_ptr(feat, (unsigned)eb.x); v20 = ldg_nc_v4(q); v21 = ldg_nc_v4(q + 128); }
+                    if (p3) { const float* q = tap_ptr(feat, (unsigned)eb.z); v30 = ldg_nc_v4(q); v31 = ldg_nc_v4(q + 128); }
+                    const float w0 = __int_as_float(ea.y), w1 = __int_as_float(ea.w), w2 = __int_as_float(eb.y), w3 = __int_as_float(eb.w);
+                    e += 4;
+                    const int2* np;
+                    if (e < cnt) np = lp + e;
+                    else {                     // last batch of this bin: claim the next one while the loads fly
+                        nbin = next_bin(b);
+                        const int nb_ = min(nbin, NB - 1);
+                        np = s_list + nb_ * PITCH;
+                        ncnt = np[16].x;
+                    }
+                    ea = reinterpret_cast<const int4*>(np)[0]; eb = reinterpret_cast<const int4*>(np)[1];
+                    RSDET_ACCQ(p0, w0, v00, v01) RSDET_ACCQ(p1, w1, v10, v11) RSDET_ACCQ(p2, w2, v20, v21) RSDET_ACCQ(p3, w3, v30, v31)
+                } while (e < cnt);
+                stage(acc0, acc1, b);
+                b = nbin;
+                lp = s_list + min(nbin, NB - 1) * PITCH;
+                cnt = ncnt;
+            }
+        }
+#undef RSDET_ACCQ
+        if (tid < 3) asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == THREADS - 1) {      // the thread that will wait for it
+            unsigned long long pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         ::"l"(out + ((size_t)roi * C + chunk0) * NB), "r"((unsigned)__cvta_generic_to_shared(s_stage)), "r"(256u * NB * 4u), "l"(pol) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (!have_next) break;
+        nidx = nnidx;
+        buf ^= 1;
+    }
+    if (tid == THREADS - 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------- forward (channel-split passes)
 // Same tap lists and the same warp = bin gather, but a 256-channel chunk is produced in NP passes of 256/NP channels:
 // the staging block shrinks to 50/NP KB, so four resident CTAs leave most of the SM's 256 KB to L1 -- the pixel rows

@@ -190,3 +190,22 @@ def test_fused_extractor_full_size_subset(cuda, oracle):
         sub = np.sort(np.random.default_rng(K).choice(K, 200, replace=False))
         want, _ = oracle.oriented_extractor_fwd(fs, r[sub], list(W.STRIDES), extend_factor=B.EXTEND)
         _check(got[torch.from_numpy(sub).cuda()].cpu().numpy(), want, 1e-5, f"full-size extractor K={K} (200-RoI subset)")
+
+
+def test_persistent_kernel_two_chunks_many_items(cuda, oracle):
+    """The persistent 7x7 kernel with C = 512 (two 256-channel items per RoI) and more items than resident CTAs
+    (148 x 3): every CTA loops, items of one RoI may land on different CTAs.  NCHW and channels-last callers."""
+    from rs_detection_b200 import core
+    tile, C, K = 128, 512, 700
+    shapes = W.fpn_shapes(1, tile=tile, channels=C)
+    rng = np.random.default_rng(5)
+    feats = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    rois = W.proposals(K, 21, canvas=tile)
+    want, _ = oracle.oriented_extractor_fwd(feats, rois, [4, 8, 16, 32])
+    for cl in (False, True):
+        cfg = core.make_roi_cfg(shapes, [1 / s for s in W.STRIDES], 7, 2, 1, (1.4, 1.2), 56.0, channels_last=cl)
+        f = [_t(x) for x in feats]
+        if cl:
+            f = [core.nchw_to_nhwc(x) for x in f]
+        got = core.roi_align_rotated_forward(cfg, f, _t(rois)).cpu().numpy()
+        _check(got, want, 1e-5, f"persistent kernel, C=512, channels_last={cl}")

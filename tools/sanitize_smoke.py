@@ -10,6 +10,19 @@ import workloads as W
 from rs_detection_b200 import core
 from rs_detection_b200._lib import NMS_HBB, NMS_MERGE, NMS_POLY, NMS_ROTATED, NMS_ROTATED_GE
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+if "--roi-persistent" in sys.argv:
+    # the persistent 7x7 forward kernel with more items than CTAs (every CTA loops: next-record prefetch, in-place list
+    # rebuild under the previous bulk store, counter hand-out), single chunk and two chunks, channels-last and NCHW
+    for C, K in ((256, 2500), (512, 900)):
+        shapes = W.fpn_shapes(1, tile=256, channels=C)
+        feats = [torch.randn(sh, device="cuda") for sh in shapes]
+        rois = t(W.proposals(K, 4, batch=1, canvas=256))
+        for cl in (False, True):
+            cfg = core.make_roi_cfg(shapes, [1 / s_ for s_ in W.STRIDES], 7, 2, 1, (1.4, 1.2), 56.0, channels_last=cl)
+            f = [core.nchw_to_nhwc(x) for x in feats] if cl else feats
+            core.roi_align_rotated_forward(cfg, f, rois)
+    torch.cuda.synchronize()
+    sys.exit(0)
 n = 700
 b = W.rotated_boxes(n, 1, canvas=300, smin=8, smax=96)
 s = W.distinct_scores(n, 1)
