@@ -617,9 +617,10 @@ __device__ __forceinline__ float4 unrot4(float4 v, int o) { return rot4(v, (4 - 
 
 // ---------------------------------------------------------------------------------- forward (fast)
 // One CTA per (RoI, chunk of up to 64 channel quads), thread = (channel quad(s), bin group).  QPT = 2:
-// the second channel quad is an immediate +512 B off the same address.
+// the second channel quad is an immediate +512 B off the same address.  Launch bounds for THREE CTAs per SM: the driver then
+// picks the 196 KB carve-out (60 KB of L1 instead of 28) -- 143.2 -> 131.9 us per bench tile (profiles/README.md, third pass).
 template <int QPT>
-__global__ void __launch_bounds__(kRoiThreads, 4)
+__global__ void __launch_bounds__(kRoiThreads, 3)
 roi_align_fwd_kernel(LevelSet L, const float* __restrict__ rois, const int* __restrict__ order, const RoiGeom* __restrict__ geoms,
                      int K, float* __restrict__ out, int32_t* __restrict__ levels_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
