@@ -128,6 +128,10 @@ struct PrepArgs {                 // order block riding along with the NCHW->NHW
     const float* rois;
     int K;
     int* order;
+    // lean flow (persistent forward kernel): geometry blocks ride along as well
+    RoiGeom* geoms = nullptr;
+    int32_t* levels_out = nullptr;
+    unsigned* counter = nullptr;
 };
 static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
                             int C, cudaStream_t st, const PrepArgs* prep = nullptr);
@@ -346,8 +350,7 @@ __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* 
     }
 }
 
-__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, int K,
-                                                         int* __restrict__ order) {
+__device__ __forceinline__ void roi_order_1024(const LevelSet& L, const float* __restrict__ rois, int K, int* __restrict__ order) {
     __shared__ int s_hist[kBuckets];
     __shared__ int s_warp[32];
     const int tid = threadIdx.x;
@@ -406,9 +409,38 @@ __global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float
     }
 }
 
+__global__ void __launch_bounds__(1024) roi_order_kernel(LevelSet L, const float* __restrict__ rois, int K,
+                                                         int* __restrict__ order) {
+    roi_order_1024(L, rois, K, order);
+}
+
+// Lean prologue of the persistent forward kernel, ONE launch: block 0 = the locality order (when there is one), the other
+// blocks = the per-RoI geometry records BY ROI INDEX (the persistent kernel looks a record up through order[] while it
+// gathers the previous item, so nothing has to be written in processing order) + the reset of its work counter.
+__device__ __forceinline__ void roi_geometry_by_index(const LevelSet& L, const float* __restrict__ rois, int K, int i,
+                                                      RoiGeom* __restrict__ geoms, int32_t* __restrict__ levels_out) {
+    if (i >= K) return;
+    const RoiGeom g = roi_geometry(rois + (size_t)i * 6, L);
+    geoms[i] = g;
+    if (levels_out) levels_out[i] = g.level;
+}
+__global__ void __launch_bounds__(1024) roi_prep_kernel(LevelSet L, const float* __restrict__ rois, int K, int* __restrict__ order,
+                                                        RoiGeom* __restrict__ geoms, int32_t* __restrict__ levels_out,
+                                                        unsigned* __restrict__ counter) {
+    int gb = blockIdx.x;
+    if (order) {
+        if (gb == 0) { roi_order_1024(L, rois, K, order); return; }
+        gb--;
+    }
+    if (gb == 0 && threadIdx.x == 0) *counter = 0u;
+    roi_geometry_by_index(L, rois, K, gb * 1024 + threadIdx.x, geoms, levels_out);
+}
+
 // NCHW callers: the pyramid transpose with the order block riding along as block 0
 __global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, LevelSet L, const float* __restrict__ rois, int K,
-                                                             int* __restrict__ order) {
+                                                             int* __restrict__ order, RoiGeom* __restrict__ geoms,
+                                                             int32_t* __restrict__ levels_out, unsigned* __restrict__ counter,
+                                                             int geom_blocks) {
     __shared__ float tile[64][65];
     static_assert(sizeof(float) * 64 * 65 >= sizeof(int) * (kBuckets + 32), "the prep block borrows the transpose tile");
     if (blockIdx.x == 0) {
@@ -419,7 +451,12 @@ __global__ void __launch_bounds__(256) transpose_prep_kernel(TransposeJob job, L
         roi_order_block<256>(L, rois, K, order, s_hist, s_hist + kBuckets, s_bkt, bkt_cap);
         return;
     }
-    transpose_tile<true>(job, blockIdx.x - 1, tile);
+    if ((int)blockIdx.x <= geom_blocks) {      // lean flow: geometry records by RoI index, 256 per block
+        if (blockIdx.x == 1 && threadIdx.x == 0) *counter = 0u;
+        roi_geometry_by_index(L, rois, K, ((int)blockIdx.x - 1) * 256 + threadIdx.x, geoms, levels_out);
+        return;
+    }
+    transpose_tile<true>(job, blockIdx.x - 1 - geom_blocks, tile);
 }
 
 static int launch_transpose(bool to_nhwc, const float* const* src, float* const* dst, const int* H, const int* W, int L, int N,
@@ -434,7 +471,9 @@ static int launch_transpose(bool to_nhwc, const float* const* src, float* const*
     }
     job.tile_begin[L] = total;
     if (prep && to_nhwc) {
-        transpose_prep_kernel<<<total + 1, 256, 0, st>>>(job, *prep->L, prep->rois, prep->K, prep->order);
+        const int geom_blocks = prep->geoms ? ceil_div(prep->K, 256) : 0;
+        transpose_prep_kernel<<<total + 1 + geom_blocks, 256, 0, st>>>(job, *prep->L, prep->rois, prep->K, prep->order, prep->geoms,
+                                                                        prep->levels_out, prep->counter, geom_blocks);
         count_launch();
         return cuda_status();
     }
@@ -838,26 +877,30 @@ roi_align_fwd77_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, f
 constexpr size_t kStage77pOffset = (8 * 49 * 18 + 16 + 48 + 127) & ~(size_t)127;   // lists | next item | next record | staging
 template <int WARPS, int MINB, int TAPS = 4>   // TAPS: list entries per batch (4, 6 or 8 = 8 / 12 / 16 16-byte loads in flight per thread)
 __global__ void __launch_bounds__(32 * WARPS, MINB)
-roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, int chunks, float* __restrict__ out,
-                        unsigned* __restrict__ counter) {
+roi_align_fwd77p_kernel(LevelSet L, const int* __restrict__ order, const RoiGeom* __restrict__ geoms, int K, int chunks,
+                        float* __restrict__ out, unsigned* __restrict__ counter) {
     constexpr int NB = 49, PITCH = 18, THREADS = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int2* s_list = reinterpret_cast<int2*>(smem_raw);
     volatile int* s_next = reinterpret_cast<volatile int*>(smem_raw + 8 * NB * PITCH);
+    volatile int* s_roi = reinterpret_cast<volatile int*>(smem_raw + 8 * NB * PITCH + 4);      // RoI index of the record in s_geom
     const RoiGeom* s_geom = reinterpret_cast<const RoiGeom*>(smem_raw + 8 * NB * PITCH + 16);
     float* s_stage = reinterpret_cast<float*>(smem_raw + kStage77pOffset);
     const int C = L.C, items = K * chunks;
     const int oct = (lane >> 3) & 3;
     float* const sbase = s_stage + lane * 4 * NB;
     int idx = blockIdx.x;
-    if (tid < 3 && idx < items)
-        reinterpret_cast<float4*>(smem_raw + 8 * NB * PITCH + 16)[tid] = reinterpret_cast<const float4*>(gsorted + idx / chunks)[tid];
+    if (tid < 3 && idx < items) {
+        const int r = order ? order[idx / chunks] : idx / chunks;      // position in processing order -> RoI
+        reinterpret_cast<float4*>(smem_raw + 8 * NB * PITCH + 16)[tid] = reinterpret_cast<const float4*>(geoms + r)[tid];
+        if (tid == 0) *s_roi = r;
+    }
     __syncthreads();
 #pragma unroll 1
     while (idx < items) {
         RoiGeom g = *s_geom;                   // this item's record (prefetched during the previous gather)
-        const int roi = g.gh;                  // processing-order record: gh carries the RoI index
+        const int roi = *s_roi;
         g.gh = 2; g.gw = 2;
         const int chunk0 = (idx % chunks) * 256;
         const int H = L.H[g.level], W = L.W[g.level];
@@ -909,8 +952,10 @@ roi_align_fwd77p_kernel(LevelSet L, const RoiGeom* __restrict__ gsorted, int K, 
         __syncthreads();
         if (tid < 3 && *s_next < items) {      // the next record: three 16-byte async copies, in flight during the gather
             const int nidx = *s_next;
+            const int r = order ? __ldg(order + nidx / chunks) : nidx / chunks;
+            if (tid == 0) *s_roi = r;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(s_geom) + 16u * tid),
-                         "l"(reinterpret_cast<const char*>(gsorted + nidx / chunks) + 16 * tid) : "memory");
+                         "l"(reinterpret_cast<const char*>(geoms + r) + 16 * tid) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
 
@@ -1284,16 +1329,30 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
     if (getenv("RSDET_ROI_NOORDER")) order = nullptr;
 #endif
     const bool ride = !cfg->channels_last && order && num_rois <= kPrepMaxRois;
-    launch_prep(L, rois, num_rois, geoms, order, levels_out, st, ride, gsorted);
+    // lean prologue (the persistent 7x7 kernel follows): records by RoI index only, one launch, and for NCHW callers
+    // no launch at all -- order block and geometry blocks ride with the transpose
+    bool lean = fwd77_ok(cfg) && roi_path_choice() == 1 && (((size_t)out) & 15) == 0;
+#ifdef RSDET_TUNING
+    if (getenv("RSDET_ROI_NOPERSIST") || getenv("RSDET_ROI_V8") || getenv("RSDET_ROI_MINB3") || getenv("RSDET_ROI_Q") ||
+        getenv("RSDET_ROI_LD") || getenv("RSDET_ROI_WARPS") || getenv("RSDET_ROI_OLDPREP"))
+        lean = false;
+#endif
+    unsigned* const counter = reinterpret_cast<unsigned*>(gsorted + num_rois);
+    if (!lean) launch_prep(L, rois, num_rois, geoms, order, levels_out, st, ride, gsorted);
+    else if (!ride) {
+        roi_prep_kernel<<<(order ? 1 : 0) + ceil_div(num_rois, 1024), 1024, 0, st>>>(L, rois, num_rois, order, geoms, levels_out, counter);
+        count_launch();
+    }
     if (!cfg->channels_last) {
         // NCHW -> NHWC copy of the pyramid; the locality-order block rides along as block 0 of the same launch
-        const PrepArgs prep = {&L, rois, num_rois, order};
+        PrepArgs prep = {&L, rois, num_rois, order};
+        if (lean) { prep.geoms = geoms; prep.levels_out = levels_out; prep.counter = counter; }
         float* dst[RSDET_MAX_LEVELS];
         for (int l = 0; l < cfg->num_levels; l++) dst[l] = const_cast<float*>(L.feat[l]);
         rc = launch_transpose(true, feats_host, dst, cfg->height, cfg->width, cfg->num_levels, cfg->batch, cfg->channels, st,
                               ride ? &prep : nullptr);
         if (rc != RSDET_OK) return rc;
-        if (ride) launch_geometry(L, rois, num_rois, order, geoms, gsorted, levels_out, st);
+        if (ride && !lean) launch_geometry(L, rois, num_rois, order, geoms, gsorted, levels_out, st);
     }
     size_t smem = fwd_smem_bytes(cfg);
 #ifdef RSDET_TUNING
@@ -1353,11 +1412,26 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
             if (atoi(e) == 2) { set_dyn_smem((const void*)roi_align_fwd77v8_kernel<7, true>, sm8); roi_align_fwd77v8_kernel<7, true><<<g77, 224, sm8, st>>>(L, gsorted, num_rois, out); count_launch(); return cuda_status(); }
         }
 #endif
-        bool persistent = (((size_t)out) & 15) == 0;    // the bulk store needs a 16-byte aligned output block
 #ifdef RSDET_TUNING
-        if (getenv("RSDET_ROI_NOPERSIST")) persistent = false;
+        if (getenv("RSDET_ROI_Q")) {      // A/B (old prologue: records in processing order): pipelined list build (1: dynamic bins, 2: static columns)
+            const int chunks = cfg->channels / 256;
+            const long long items = (long long)num_rois * chunks;
+            const int ctas = kNumSMs * 3;
+            const size_t smq = kStage77qOffset + sizeof(float) * 49 * 256;
+            unsigned* ctr = reinterpret_cast<unsigned*>(gsorted + num_rois);
+            const int grid = (int)(items < ctas ? items : ctas);
+            if (atoi(getenv("RSDET_ROI_Q")) == 2) {
+                set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 1>, smq);
+                roi_align_fwd77q_kernel<8, 3, 1><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
+            } else {
+                set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 0>, smq);
+                roi_align_fwd77q_kernel<8, 3, 0><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
+            }
+            count_launch();
+            return cuda_status();
+        }
 #endif
-        if (persistent) {
+        if (lean) {                                     // persistent kernel (needs a 16-byte aligned output block for its bulk store)
             const int chunks = cfg->channels / 256;
             const long long items = (long long)num_rois * chunks;
             int ctas = kNumSMs * 3;
@@ -1365,27 +1439,13 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
             if (const char* e = getenv("RSDET_ROI_PCTAS")) ctas = atoi(e);
 #endif
 #ifdef RSDET_TUNING
-            if (getenv("RSDET_ROI_Q")) {      // A/B: pipelined list build (1: dynamic bins, 2: static columns)
-                const size_t smq = kStage77qOffset + sizeof(float) * 49 * 256;
-                unsigned* ctr = reinterpret_cast<unsigned*>(gsorted + num_rois);
-                const int grid = (int)(items < ctas ? items : ctas);
-                if (atoi(getenv("RSDET_ROI_Q")) == 2) {
-                    set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 1>, smq);
-                    roi_align_fwd77q_kernel<8, 3, 1><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
-                } else {
-                    set_dyn_smem((const void*)roi_align_fwd77q_kernel<8, 3, 0>, smq);
-                    roi_align_fwd77q_kernel<8, 3, 0><<<grid, 256, smq, st>>>(L, gsorted, num_rois, chunks, out, ctr);
-                }
-                count_launch();
-                return cuda_status();
-            }
             if (const char* e = getenv("RSDET_ROI_PVAR")) {     // A/B: warps x CTAs/SM x taps per batch of the persistent kernel
                 const size_t smv = kStage77pOffset + sizeof(float) * 49 * 256;
                 unsigned* ctr = reinterpret_cast<unsigned*>(gsorted + num_rois);
                 const int v = atoi(e);
 #define RSDET_PV(W_, M_, T_) { const int grid = (int)(items < kNumSMs * M_ ? items : kNumSMs * M_); \
                                set_dyn_smem((const void*)roi_align_fwd77p_kernel<W_, M_, T_>, smv); \
-                               roi_align_fwd77p_kernel<W_, M_, T_><<<grid, 32 * W_, smv, st>>>(L, gsorted, num_rois, chunks, out, ctr); \
+                               roi_align_fwd77p_kernel<W_, M_, T_><<<grid, 32 * W_, smv, st>>>(L, order, geoms, num_rois, chunks, out, ctr); \
                                count_launch(); return cuda_status(); }
                 if (v == 1062) RSDET_PV(10, 2, 6)
                 if (v == 1262) RSDET_PV(12, 2, 6)
@@ -1401,7 +1461,7 @@ extern "C" int rsdet_roi_align_rotated_forward(const rsdet_roi_align_cfg* cfg, c
             const size_t smp = kStage77pOffset + sizeof(float) * 49 * 256;
             set_dyn_smem((const void*)roi_align_fwd77p_kernel<8, 3>, smp);
             roi_align_fwd77p_kernel<8, 3><<<(int)(items < ctas ? items : ctas), 256, smp, st>>>(
-                L, gsorted, num_rois, chunks, out, reinterpret_cast<unsigned*>(gsorted + num_rois));
+                L, order, geoms, num_rois, chunks, out, counter);
             count_launch();
             return cuda_status();
         }
