@@ -50,6 +50,10 @@ IOU_THR = 0.1
 MAX_NUM = 2000
 EXTEND = (1.4, 1.2)
 NSTREAMS = int(os.environ.get("RSDET_BENCH_STREAMS", "8"))
+# tiles per extractor call in the timed step (1, 2, 4 or 8).  Measured on B200 (profiles/README.md): `value` 5 190 / 5 195 /
+# 5 150 / 4 860 tiles/s for 1 / 2 / 4 / 8 -- larger batches amortise the persistent gather's start-up and tail (kernel
+# fraction 0.404 / 0.433 / 0.446 / 0.450) but leave the other tiles' NMS kernels fewer gaps to run in; 4 is the default.
+ROI_BATCH = int(os.environ.get("RSDET_BENCH_ROI_BATCH", "4"))
 METRIC = "tiles/s (Oriented R-CNN rotated-box hot path: RoIAlignRotated fwd + obb2poly + per-class nms_rotated)"
 WORKLOAD = ("configs[1]: orcnn_van3 inference hot path, 8 synthetic 1024x1024 tiles/GPU, 4000 rotated proposals/tile, "
             "4 FPN levels C=256 fp32 NCHW, RoIAlignRotated_v1 7x7x2x2 -> obb2poly -> multiclass_nms_rotated "
@@ -289,28 +293,35 @@ def merge_component(dev, rank, world, dist, max_over_ranks, barrier):
     return out
 
 
-def verify_tile0(tile_np, tile_dev, out_bufs, device_step, cfg, core):
+def verify_tile0(tile_np, tile_dev, out_bufs, device_step, cfg, core, last_np=None):
     """Compare what one more (untimed) device step leaves behind for tile 0 with the CPU oracle: the kept set of
     `multiclass_nms_rotated` (4000 x 10 candidates, score_thr 0.001) must be identical, RoI features of 64 RoIs
-    must agree to 1e-5 (relative to the tensor's scale, the contract of tests/test_gpu_roi_align.py)."""
+    must agree to 1e-5 (relative to the tensor's scale, the contract of tests/test_gpu_roi_align.py).  The step
+    extracts all tiles in one batched call: 32 RoIs of the LAST tile (batch index 7) are checked as well."""
     import torch
     from oracle import oracle as O
     feats, rois, boxes, scores = tile_np
     device_step()
     torch.cuda.synchronize()
-    got_feat = out_bufs[0]                                   # tile 0 writes slot 0 (tiles 0 and NSTREAMS share it: see below)
-    got_feat = core.roi_align_rotated_forward(cfg, tile_dev[0], tile_dev[1]) if TILES_PER_GPU > NSTREAMS else got_feat
+    got_feat = out_bufs[0]                                   # tile 0's rows of the batched output
     sub = np.sort(np.random.default_rng(0).choice(K_ROIS, 64, replace=False))
     want, _ = O.oriented_extractor_fwd(feats, rois[sub], list(W.STRIDES), extend_factor=EXTEND)
     g = got_feat[torch.from_numpy(sub).to(got_feat.device)].cpu().numpy()
     scale = float(np.abs(want).max())
     roi_err = float(np.abs(g - want).max())
+    if last_np is not None:
+        sub2 = np.sort(np.random.default_rng(1).choice(K_ROIS, 32, replace=False))
+        want2, _ = O.oriented_extractor_fwd(last_np[0], last_np[1][sub2], list(W.STRIDES), extend_factor=EXTEND)
+        g2 = out_bufs[-1][torch.from_numpy(sub2).to(got_feat.device)].cpu().numpy()
+        roi_err = max(roi_err, float(np.abs(g2 - want2).max()))
+        scale = max(scale, float(np.abs(want2).max()))
     dets, labels, cnt = core.multiclass_nms_rotated(tile_dev[2], tile_dev[3], SCORE_THR, IOU_THR, MAX_NUM)
     k = int(cnt.item())
     wd, wl = O.multiclass_nms_rotated(boxes, scores, SCORE_THR, dict(iou_thr=IOU_THR), MAX_NUM)
     nms_ok = bool(k == wd.shape[0] and np.array_equal(dets[:k].cpu().numpy(), wd) and np.array_equal(labels[:k].cpu().numpy(), wl))
     return {"ok": bool(nms_ok and roi_err <= 1e-5 * 2 * scale), "nms_kept": k, "nms_kept_oracle": int(wd.shape[0]),
-            "nms_identical": nms_ok, "roi_max_abs_err": roi_err, "roi_scale": scale, "roi_rois_checked": int(len(sub)),
+            "nms_identical": nms_ok, "roi_max_abs_err": roi_err, "roi_scale": scale,
+            "roi_rois_checked": int(len(sub)) + (32 if last_np is not None else 0),
             "checksum_out_tile0": float(got_feat.double().sum())}
 
 
@@ -335,8 +346,20 @@ def run_ours(args, rank, world, local_rank):
     cfg = core.make_roi_cfg(shapes, scales, 7, 2, 1, EXTEND, 56.0)
     cfg_cl = core.make_roi_cfg(shapes, scales, 7, 2, 1, EXTEND, 56.0, channels_last=True)
     tiles_np = [tile_inputs(1000 * rank + t) for t in range(TILES_PER_GPU)]
-    tiles = [([torch.from_numpy(f).to(dev) for f in fs], torch.from_numpy(r).to(dev), torch.from_numpy(b).to(dev),
-              torch.from_numpy(s).to(dev)) for fs, r, b, s in tiles_np]
+    # the 8 tiles of a step are a BATCH of 8 images for the extractor (one (8, C, H, W) tensor per level, RoIs carrying their
+    # batch index, as the reference's extractor takes them); a tile's own tensors are views into the batch
+    feats8 = [torch.from_numpy(np.concatenate([t[0][l] for t in tiles_np], 0)).to(dev) for l in range(len(shapes))]
+    tiles = [([f8[i:i + 1] for f8 in feats8], torch.from_numpy(r).to(dev), torch.from_numpy(b).to(dev),
+              torch.from_numpy(s).to(dev)) for i, (fs, r, b, s) in enumerate(tiles_np)]
+    rois8 = torch.cat([torch.cat([torch.full((t[1].shape[0], 1), float(i), device=dev), t[1][:, 1:]], 1)
+                       for i, t in enumerate(tiles)], 0).contiguous()
+    shapes8 = [(TILES_PER_GPU,) + tuple(sh[1:]) for sh in shapes]
+    cfg8 = core.make_roi_cfg(shapes8, scales, 7, 2, 1, EXTEND, 56.0)
+    out8 = torch.empty((TILES_PER_GPU * K_ROIS, W.CHANNELS, 7, 7), dtype=torch.float32, device=dev)
+    # ROI_BATCH tiles per extractor call of the timed step (RSDET_BENCH_ROI_BATCH, default all 8)
+    cfgb = core.make_roi_cfg([(ROI_BATCH,) + tuple(sh[1:]) for sh in shapes], scales, 7, 2, 1, EXTEND, 56.0)
+    roisb = [torch.cat([torch.cat([torch.full((K_ROIS, 1), float(j), device=dev), tiles[g * ROI_BATCH + j][1][:, 1:]], 1)
+                        for j in range(ROI_BATCH)], 0).contiguous() for g in range(TILES_PER_GPU // ROI_BATCH)]
     out_buf = torch.empty((K_ROIS, W.CHANNELS, 7, 7), dtype=torch.float32, device=dev)
 
     # tiles are independent: they are issued round-robin on NSTREAMS streams (each with its own scratch,
@@ -344,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
     # (sorts, greedy scan) overlap the throughput-bound phases of the others.
     side = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
     side2 = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
-    out_bufs = [torch.empty((K_ROIS, W.CHANNELS, 7, 7), dtype=torch.float32, device=dev) for _ in range(NSTREAMS)]
+    out_bufs = [out8[i * K_ROIS:(i + 1) * K_ROIS] for i in range(TILES_PER_GPU)]   # tile i's rows of the batched output
 
     def device_step():
         main = torch.cuda.current_stream()
@@ -357,9 +380,15 @@ def run_ours(args, rank, world, local_rank):
             with torch.cuda.stream(side[i % NSTREAMS]):
                 core.obb2poly(boxes)
                 core.multiclass_nms_rotated(boxes, scores, SCORE_THR, IOU_THR, MAX_NUM)
-        for i, (feats, rois, boxes, scores) in enumerate(tiles):
-            with torch.cuda.stream(side2[i % NSTREAMS]):
-                core.roi_align_rotated_forward(cfg, feats, rois, out=out_bufs[i % NSTREAMS])
+        # the RoI features of all 8 tiles: ONE extractor call (32 000 RoIs; the persistent gather pays its start-up and
+        # tail once per step instead of once per tile)
+        for g in range(TILES_PER_GPU // ROI_BATCH):
+            with torch.cuda.stream(side2[g % NSTREAMS]):
+                if ROI_BATCH == TILES_PER_GPU:
+                    core.roi_align_rotated_forward(cfg8, feats8, rois8, out=out8)
+                else:
+                    lo, hi = g * ROI_BATCH, (g + 1) * ROI_BATCH
+                    core.roi_align_rotated_forward(cfgb, [f8[lo:hi] for f8 in feats8], roisb[g], out=out8[lo * K_ROIS:hi * K_ROIS])
         for st in side + side2:
             main.wait_stream(st)
 
@@ -427,6 +456,20 @@ def run_ours(args, rank, world, local_rank):
         core.roi_gather_kernel_ms(cfg_cl, fcl, t[1], out_buf)
     ks = [core.roi_gather_kernel_ms(cfg_cl, fcl, t[1], out_buf) for _ in range(reps) for fcl, t in zip(feats_cl, tiles)]
     ms_fwd_kernel = float(np.mean(ks))
+    # the launch of the timed step: ROI_BATCH tiles go through ONE extractor call (a batch of images, RoIs with their batch
+    # index), so the persistent grid pays its start-up and tail once per ROI_BATCH tiles.  Measured like the per-tile
+    # launch: channels-last batch resident, library events around the gather kernel, the step's groups cycled.
+    cfgb_cl = core.make_roi_cfg([(ROI_BATCH,) + tuple(sh[1:]) for sh in shapes], scales, 7, 2, 1, EXTEND, 56.0, channels_last=True)
+    groups_cl = [[torch.cat([feats_cl[g * ROI_BATCH + j][l] for j in range(ROI_BATCH)], 0).contiguous() for l in range(len(shapes))]
+                 for g in range(TILES_PER_GPU // ROI_BATCH)]
+    outb = out8[:ROI_BATCH * K_ROIS]
+    for g, fb in enumerate(groups_cl):
+        core.roi_gather_kernel_ms(cfgb_cl, fb, roisb[g], outb)
+    ks8 = [core.roi_gather_kernel_ms(cfgb_cl, fb, roisb[g], outb) for _ in range(reps) for g, fb in enumerate(groups_cl)]
+    ms_fwd_kernel_b8 = float(np.mean(ks8))
+    ms_ext8 = timed(lambda: [core.roi_align_rotated_forward(cfgb, [f8[g * ROI_BATCH:(g + 1) * ROI_BATCH] for f8 in feats8], roisb[g],
+                                                            out=outb) for g in range(TILES_PER_GPU // ROI_BATCH)], reps) / TILES_PER_GPU
+    del groups_cl
     # training-side figures (config 3): fwd+bwd on 512 sampled RoIs, IoU 512x2000 + assignment
     rois512 = tiles[0][1][:512].contiguous()
     gout = torch.randn((512, W.CHANNELS, 7, 7), device=dev)
@@ -482,11 +525,18 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     U = float(np.mean([touched_pixels(t[1]) for t in tiles_np[:2]]))
     algo_bytes = 4.0 * K_ROIS * W.CHANNELS * 49 + 24.0 * K_ROIS + 4.0 * W.CHANNELS * U
-    achieved = algo_bytes / (ms_fwd_kernel * 1e-3) / 1e9
+    algo_bytes8 = ROI_BATCH * algo_bytes
+    achieved = algo_bytes8 / (ms_fwd_kernel_b8 * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "roi_align_fwd77p_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": ms_fwd_kernel, "launches_timed": len(ks),
-                "call_ms_with_geometry_and_order_kernels": ms_fwd_call, "touched_pixels": U}
+                "units_per_launch": f"{ROI_BATCH} tiles = {ROI_BATCH * K_ROIS} RoIs (one extractor call of the timed step)",
+                "algorithmic_bytes_per_launch": algo_bytes8, "launch_ms": ms_fwd_kernel_b8, "launches_timed": len(ks8),
+                "touched_pixels_per_tile": U,
+                "single_tile_launch": {"launch_ms": ms_fwd_kernel, "algorithmic_bytes": algo_bytes,
+                                       "frac": algo_bytes / (ms_fwd_kernel * 1e-3) / 1e9 / peak, "launches_timed": len(ks),
+                                       "call_ms_with_prologue": ms_fwd_call,
+                                       "note": "the same kernel launched for ONE tile (4000 RoIs): start-up and tail of the "
+                                               "persistent grid are then paid per tile"}}
     prof = os.path.join(ROOT, "profiles", "roi_fwd_traffic.json")
     if os.path.exists(prof):
         try:
@@ -583,7 +633,7 @@ def run_ours(args, rank, world, local_rank):
     merge_comp = merge_component(dev, rank, world, dist, max_over_ranks, barrier)
 
     # ---- self-check of what the timed region produced (rank 0): tile 0 against the CPU oracle
-    verified = verify_tile0(tiles_np[0], tiles[0], out_bufs, device_step, cfg, core) if rank == 0 and not args.no_verify else None
+    verified = verify_tile0(tiles_np[0], tiles[0], out_bufs, device_step, cfg, core, tiles_np[-1]) if rank == 0 and not args.no_verify else None
 
     # ---- FP32-ALU roofline of the IoU / NMS components: algorithmic FLOPs of the reference's rotated-IoU
     # algorithm per pair, counted by the instrumented CPU restatement on THESE inputs, x the pairs the reference
@@ -631,7 +681,10 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "tiles_per_gpu": TILES_PER_GPU, "rois_per_tile": K_ROIS,
                        "nms_candidates_per_tile": K_ROIS * NUM_CLASSES,
                        "l2_policy": "inputs larger than L2 (8 pyramids = 713 MB per GPU cycled every step)",
-                       "streams": 2 * NSTREAMS, "launch": "one CUDA graph replay per step", "cpu_affinity": numa},
+                       "streams": NSTREAMS + TILES_PER_GPU // ROI_BATCH, "launch": "one CUDA graph replay per step",
+                       "step": f"8 per-tile NMS chains on 8 streams + {TILES_PER_GPU // ROI_BATCH} RoI-extractor calls of {ROI_BATCH} tiles each "
+                               f"(a batch of {ROI_BATCH} images, {ROI_BATCH * K_ROIS} RoIs per call) on further streams; e2e: per-tile calls, streamed",
+                       "cpu_affinity": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h[0]),
                     "ms_per_step": ms_e2e / args.steps},
@@ -640,6 +693,8 @@ def run_ours(args, rank, world, local_rank):
                 "merge": merge_comp, "fp32": fp32,
                 "roi_extractor_fwd_ms_per_tile": ms_ext, "roi_extractor_fwd_rois_per_s": K_ROIS / (ms_ext * 1e-3),
                 "roi_fwd_kernel_ms_per_tile": ms_fwd_kernel, "roi_fwd_call_channels_last_ms_per_tile": ms_fwd_call,
+                "roi_fwd_kernel_batched_ms_per_tile": ms_fwd_kernel_b8 / ROI_BATCH, "roi_extractor_fwd_batched_ms_per_tile": ms_ext8,
+                "roi_tiles_per_extractor_call": ROI_BATCH,
                 "multiclass_nms_ms_per_tile": ms_nms, "nms_boxes_per_s": K_ROIS * NUM_CLASSES / (ms_nms * 1e-3),
                 "train_roi_fwd_bwd_512_ms": ms_fb, "train_roi_fwd_bwd_rois_per_s": 512 / (ms_fb * 1e-3),
                 "train_roi_bwd_512": {"ms": ms_bwd, "algorithmic_bytes": bwd_bytes, "achieved_gbs": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
