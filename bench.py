@@ -15,12 +15,15 @@ scores, decoded boxes) are synthetic, random-init-like softmax scores.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-`value` : tiles/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
+`value` : tiles/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.  The 8 tiles of a step are a batch
+          of images for the extractor (the reference's batched call, RoIs carrying their batch index): the step issues
+          8 // RSDET_BENCH_ROI_BATCH extractor calls (default: two calls of four tiles) and one NMS chain per tile.
 `e2e`   : tiles/s through the public jdet-mirror API with HOST (pinned) inputs: per tile the pyramid,
           proposals, boxes and scores are copied H2D and detections + polygons are read back D2H inside
           the timed region (copies double-buffered against compute on a second stream).
-`roofline`: RoIAlignRotated forward kernel (HBM bound), timed alone (channels-last pyramid resident, one
-          launch per tile) with CUDA events in this same process.
+`roofline`: RoIAlignRotated forward kernel (HBM bound): the launch of the timed step (RSDET_BENCH_ROI_BATCH tiles per
+          launch), timed alone (channels-last batch resident) with CUDA events recorded by the library around that kernel
+          in this same process; `roofline.single_tile_launch` = the same kernel launched for one tile.
 `cpu_baseline` / `--impl reference`: the reference's own kernel source compiled for the host
           (oracle/_ref; RoIAlignRotated has no CPU body in the reference, so this is its CUDA source
           run serially) on all host cores, on a bounded sample (1 tile per step).
