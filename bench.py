@@ -17,7 +17,8 @@ scores, decoded boxes) are synthetic, random-init-like softmax scores.
 
 `value` : tiles/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.  The 8 tiles of a step are a batch
           of images for the extractor (the reference's batched call, RoIs carrying their batch index): the step issues
-          8 // RSDET_BENCH_ROI_BATCH extractor calls (default: two calls of four tiles) and one NMS chain per tile.
+          8 // RSDET_BENCH_ROI_BATCH extractor calls (default: ONE call for the 8 tiles) and one NMS chain per tile on a
+          high-priority stream.
 `e2e`   : tiles/s through the public jdet-mirror API with HOST (pinned) inputs: per tile the pyramid,
           proposals, boxes and scores are copied H2D and detections + polygons are read back D2H inside
           the timed region (copies double-buffered against compute on a second stream).
@@ -53,10 +54,13 @@ IOU_THR = 0.1
 MAX_NUM = 2000
 EXTEND = (1.4, 1.2)
 NSTREAMS = int(os.environ.get("RSDET_BENCH_STREAMS", "8"))
-# tiles per extractor call in the timed step (1, 2, 4 or 8).  Measured on B200 (profiles/README.md): `value` 5 190 / 5 195 /
-# 5 150 / 4 860 tiles/s for 1 / 2 / 4 / 8 -- larger batches amortise the persistent gather's start-up and tail (kernel
-# fraction 0.404 / 0.433 / 0.446 / 0.450) but leave the other tiles' NMS kernels fewer gaps to run in; 4 is the default.
-ROI_BATCH = int(os.environ.get("RSDET_BENCH_ROI_BATCH", "4"))
+# tiles per extractor call in the timed step (1, 2, 4 or 8) and the priority of the NMS streams.  Measured on B200
+# (profiles/README.md): larger batches amortise the persistent gather's start-up and tail (kernel fraction 0.404 / 0.433 /
+# 0.447 / 0.451 for 1 / 2 / 4 / 8 tiles per call) but the gather then holds every SM for longer; with the NMS chains on
+# HIGH-PRIORITY streams their CTAs are placed first whenever an SM has room, and `value` is 5 410 / 5 450 / 5 550 tiles/s for
+# 2 / 4 / 8 (equal priorities: 5 195 / 5 150 / 4 860).
+ROI_BATCH = int(os.environ.get("RSDET_BENCH_ROI_BATCH", "8"))
+NMS_PRIO = int(os.environ.get("RSDET_BENCH_NMS_PRIO", "-1"))
 METRIC = "tiles/s (Oriented R-CNN rotated-box hot path: RoIAlignRotated fwd + obb2poly + per-class nms_rotated)"
 WORKLOAD = ("configs[1]: orcnn_van3 inference hot path, 8 synthetic 1024x1024 tiles/GPU, 4000 rotated proposals/tile, "
             "4 FPN levels C=256 fp32 NCHW, RoIAlignRotated_v1 7x7x2x2 -> obb2poly -> multiclass_nms_rotated "
@@ -368,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
     # tiles are independent: they are issued round-robin on NSTREAMS streams (each with its own scratch,
     # rs_detection_b200/_lib.py keys workspaces by stream) so that the latency-bound phases of one tile
     # (sorts, greedy scan) overlap the throughput-bound phases of the others.
-    side = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
+    side = [torch.cuda.Stream(device=dev, priority=NMS_PRIO) for _ in range(NSTREAMS)]   # NMS chains: high priority
     side2 = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
     out_bufs = [out8[i * K_ROIS:(i + 1) * K_ROIS] for i in range(TILES_PER_GPU)]   # tile i's rows of the batched output
 
@@ -686,7 +690,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2_policy": "inputs larger than L2 (8 pyramids = 713 MB per GPU cycled every step)",
                        "streams": NSTREAMS + TILES_PER_GPU // ROI_BATCH, "launch": "one CUDA graph replay per step",
                        "step": f"8 per-tile NMS chains on 8 streams + {TILES_PER_GPU // ROI_BATCH} RoI-extractor calls of {ROI_BATCH} tiles each "
-                               f"(a batch of {ROI_BATCH} images, {ROI_BATCH * K_ROIS} RoIs per call) on further streams; e2e: per-tile calls, streamed",
+                               f"(a batch of {ROI_BATCH} images, {ROI_BATCH * K_ROIS} RoIs per call) on further streams; NMS streams at priority "
+                               f"{NMS_PRIO}; e2e: per-tile calls, streamed",
                        "cpu_affinity": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h[0]),

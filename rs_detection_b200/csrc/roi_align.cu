@@ -303,6 +303,24 @@ constexpr int kBuckets = RSDET_MAX_LEVELS * kCellsPerAxis * kCellsPerAxis;
 // front of every gather, the transpose of a 1024^2 pyramid keeps the other SMs busy for 30 us anyway.  (Doing the
 // geometry in the same block as well was measured and dropped: sin/cos/log2 of 4000 RoIs on one SM take longer than
 // the two launches they replace.)  geoms[] must have been written by roi_geometry_kernel.  s_hist: kBuckets ints.
+// bucket of a RoI in the locality order.  One image: (level, 128-px cell, boustrophedon rows).  A batch of images: the image
+// is the major key -- CTAs that run at the same time then read ONE image's maps (8 images x 89 MB do not fit L2 together) --
+// with 256-px cells so that (image slot, level, cell) still fits kBuckets.
+__device__ __forceinline__ int roi_bucket(const float* __restrict__ r, int lvl, const LevelSet& L) {
+    if (L.batch > 1 && L.num_levels * 64 <= kBuckets) {
+        const int slots = kBuckets / (L.num_levels * 64);
+        int cx = min(max((int)r[1] >> (kCellShift + 1), 0), 7);
+        const int cy = min(max((int)r[2] >> (kCellShift + 1), 0), 7);
+        if (cy & 1) cx = 7 - cx;
+        const int b = min(max((int)r[0], 0), L.batch - 1) % slots;
+        return ((b * L.num_levels + lvl) * 8 + cy) * 8 + cx;
+    }
+    int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
+    const int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
+    if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
+    return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+}
+
 constexpr int kPrepMaxRois = 16384;
 template <int THREADS>
 __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* __restrict__ rois, int K,
@@ -310,12 +328,7 @@ __device__ __forceinline__ void roi_order_block(const LevelSet& L, const float* 
     const int tid = threadIdx.x;
     for (int i = tid; i < kBuckets; i += THREADS) s_hist[i] = 0;
     __syncthreads();
-    auto bucket_of = [&](const float* r, int lvl) {
-        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
-        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
-        if (cy & 1) cx = kCellsPerAxis - 1 - cx;                      // boustrophedon rows: neighbouring buckets = neighbouring cells
-        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
-    };
+    auto bucket_of = [&](const float* r, int lvl) { return roi_bucket(r, lvl, L); };
     for (int i = tid; i < K; i += THREADS) {   // s_bkt: the buckets of the first bkt_cap RoIs are kept for the scatter pass
         const float* r = rois + (size_t)i * 6;
         const int bkt = bucket_of(r, roi_level(r, L));
@@ -359,11 +372,7 @@ __device__ __forceinline__ void roi_order_1024(const LevelSet& L, const float* _
     auto bucket_of = [&](int i, int& lvl) {
         const float* r = rois + (size_t)i * 6;
         lvl = roi_level(r, L);
-        int cx = min(max((int)r[1] >> kCellShift, 0), kCellsPerAxis - 1);
-        int cy = min(max((int)r[2] >> kCellShift, 0), kCellsPerAxis - 1);
-        // boustrophedon rows: neighbouring buckets are neighbouring cells
-        if (cy & 1) cx = kCellsPerAxis - 1 - cx;
-        return (lvl * kCellsPerAxis + cy) * kCellsPerAxis + cx;
+        return roi_bucket(r, lvl, L);
     };
     int cached[4] = {0, 0, 0, 0};   // buckets of this thread's first four RoIs: the scatter pass reloads nothing for K <= 4096
 #pragma unroll
