@@ -61,6 +61,7 @@ NSTREAMS = int(os.environ.get("RSDET_BENCH_STREAMS", "8"))
 # 2 / 4 / 8 (equal priorities: 5 195 / 5 150 / 4 860).
 ROI_BATCH = int(os.environ.get("RSDET_BENCH_ROI_BATCH", "8"))
 NMS_PRIO = int(os.environ.get("RSDET_BENCH_NMS_PRIO", "-1"))
+assert ROI_BATCH in (1, 2, 4, 8), "RSDET_BENCH_ROI_BATCH must be 1, 2, 4 or 8"
 METRIC = "tiles/s (Oriented R-CNN rotated-box hot path: RoIAlignRotated fwd + obb2poly + per-class nms_rotated)"
 WORKLOAD = ("configs[1]: orcnn_van3 inference hot path, 8 synthetic 1024x1024 tiles/GPU, 4000 rotated proposals/tile, "
             "4 FPN levels C=256 fp32 NCHW, RoIAlignRotated_v1 7x7x2x2 -> obb2poly -> multiclass_nms_rotated "
